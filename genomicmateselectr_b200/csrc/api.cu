@@ -1,0 +1,635 @@
+// C ABI (include/gms_b200.h) and the engine handle: owns the HBM-resident LD-decay tile images,
+// the bit-packed haplotypes and the work plan, and drives the kernels on one stream.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/gms_b200.h"
+#include "common.cuh"
+#include "kernels.cuh"
+
+using namespace gms;
+
+namespace {
+
+std::mutex g_err_mu;
+std::string g_create_err = "";
+
+template <typename T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t cap = 0;  // elements
+    cudaError_t ensure(size_t n) {
+        if (n <= cap && p) return cudaSuccess;
+        if (p) { cudaFree(p); p = nullptr; cap = 0; }
+        if (n == 0) n = 1;
+        cudaError_t e = cudaMalloc(&p, n * sizeof(T));
+        if (e == cudaSuccess) cap = n;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+struct Plan {       // one contraction launch
+    int ntiles = 0, nsplit = 1;
+    std::vector<int> split_begin;
+};
+
+}  // namespace
+
+struct gms_handle {
+    int device = 0;
+    int num_sms = 148;
+    size_t smem_limit = 0;
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    std::string err;
+
+    // geometry
+    int C = 0;
+    std::vector<ChromDesc> chrom;
+    DevBuf<ChromDesc> chrom_d;
+    long long m = 0, mp_total = 0, wpp = 0, tile_doubles = 0;
+    int c_begin = 0, c_end = 0;
+    bool have_tiles = false, have_haps = false, staged = false, computed = false;
+    DevBuf<double> R, R2;
+
+    // haplotypes
+    long long P = 0;
+    DevBuf<unsigned> planeA, planeB;
+
+    // work list for the chromosome shard
+    std::vector<RowTile> rowtiles;
+    DevBuf<RowTile> rowtiles_d;
+    double lower_elems = 0;   // padded elements in the stored lower block triangles of the shard
+    long long S2 = 0;
+
+    // staged problem
+    int model = 0, T = 0, npairs = 0, ncomp = 0;
+    long long N = 0, nP = 0;
+    DevBuf<double> eff_raw, emat_add, emat_dom, emat_asub;
+    DevBuf<int> sire_d, dam_d, sire_slot_d, dam_slot_d, plist_d, pair1_d, pair2_d, split_par_d, split_x_d, flag_d;
+    DevBuf<double> Z, QA, PD, QB, X, out_d, gebv_d, mean_d;
+    DevBuf<int> nseg_d;
+    Plan plan_par, plan_x;
+    int stages = 0;
+
+    cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    gms_stats st{};
+};
+
+namespace {
+
+int fail(gms_handle* h, int code, const std::string& msg) {
+    if (h) h->err = msg;
+    else { std::lock_guard<std::mutex> lk(g_err_mu); g_create_err = msg; }
+    return code;
+}
+#define CU(call)                                                                              \
+    do {                                                                                      \
+        cudaError_t e__ = (call);                                                             \
+        if (e__ != cudaSuccess)                                                               \
+            return fail(h, e__ == cudaErrorMemoryAllocation ? GMS_ENOMEM : GMS_ECUDA,         \
+                        std::string(#call) + ": " + cudaGetErrorString(e__));                 \
+    } while (0)
+
+int bind(gms_handle* h) {
+    CU(cudaSetDevice(h->device));
+    return GMS_OK;
+}
+
+int set_geometry(gms_handle* h, int C, const int64_t* m_c) {
+    if (C <= 0 || !m_c) return fail(h, GMS_EINVAL, "need C >= 1 chromosomes and m_c");
+    h->chrom.assign(C, ChromDesc{});
+    long long snp = 0, pad = 0, tiles = 0;
+    for (int c = 0; c < C; ++c) {
+        if (m_c[c] <= 0 || m_c[c] > (1LL << 30)) return fail(h, GMS_EINVAL, "m_c[c] must be in 1..2^30");
+        ChromDesc& cd = h->chrom[c];
+        cd.m = (int)m_c[c];
+        cd.mp = (int)((m_c[c] + BM - 1) / BM * BM);
+        cd.snp_off = (int)snp;
+        cd.pad_off = (int)pad;
+        cd.tile_off = tiles;
+        snp += cd.m;
+        pad += cd.mp;
+        tiles += chunks_of_chrom(cd.mp / BM) * CHUNK;
+        if (pad > (1LL << 31) - 1) return fail(h, GMS_EINVAL, "padded SNP axis exceeds 2^31");
+    }
+    h->C = C;
+    h->m = snp;
+    h->mp_total = pad;
+    h->wpp = pad / 32;
+    h->tile_doubles = tiles;
+    h->c_begin = 0;
+    h->c_end = C;
+    h->have_tiles = h->have_haps = h->staged = h->computed = false;
+    CU(h->chrom_d.ensure(C));
+    CU(cudaMemcpyAsync(h->chrom_d.p, h->chrom.data(), sizeof(ChromDesc) * C, cudaMemcpyHostToDevice, h->stream));
+    CU(h->R.ensure((size_t)tiles));
+    CU(h->R2.ensure((size_t)tiles));
+    return GMS_OK;
+}
+
+int build_worklist(gms_handle* h) {
+    h->rowtiles.clear();
+    h->lower_elems = 0;
+    h->S2 = 0;
+    for (int c = h->c_begin; c < h->c_end; ++c) {
+        const int nI = h->chrom[c].mp / BM;
+        for (int I = 0; I < nI; ++I) {
+            h->rowtiles.push_back(RowTile{c, I});
+            h->lower_elems += (double)BM * BM * (I + 1);
+        }
+        h->S2 += (long long)h->chrom[c].m * h->chrom[c].m;
+    }
+    CU(h->rowtiles_d.ensure(h->rowtiles.size()));
+    CU(cudaMemcpyAsync(h->rowtiles_d.p, h->rowtiles.data(), sizeof(RowTile) * h->rowtiles.size(),
+                       cudaMemcpyHostToDevice, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return GMS_OK;
+}
+
+// contiguous partition of the row-tile list into nsplit ranges of ~equal work (weight I+1)
+void make_plan(const gms_handle* h, long long n_units, int NU, Plan& pl) {
+    const int nrt = (int)h->rowtiles.size();
+    pl.ntiles = (int)((n_units + NU - 1) / NU);
+    int ns = 1;
+    if (pl.ntiles > 0) {
+        const int sms = h->num_sms;
+        if (pl.ntiles < 2 * sms) {
+            ns = (2 * sms + pl.ntiles - 1) / pl.ntiles;
+        } else {  // many tiles: pick the split (1..8) with the smallest last-wave loss
+            double best = 1e30;
+            for (int cand = 1; cand <= 8; ++cand) {
+                const double ctas = (double)pl.ntiles * cand;
+                const double waves = std::ceil(ctas / sms);
+                const double cost = waves * sms / ctas * (1.0 + 0.01 * (cand - 1));
+                if (cost < best - 1e-12) { best = cost; ns = cand; }
+            }
+        }
+    }
+    ns = std::max(1, std::min(ns, std::max(1, nrt)));
+    pl.nsplit = ns;
+    pl.split_begin.assign(ns + 1, 0);
+    double total = 0;
+    for (const RowTile& r : h->rowtiles) total += r.I + 1;
+    double acc = 0;
+    int sp = 1;
+    for (int i = 0; i < nrt && sp < ns; ++i) {
+        acc += h->rowtiles[i].I + 1;
+        // close split sp-1 after tile i once its share is reached, keeping >= 1 tile for the rest
+        while (sp < ns && acc >= total * sp / ns && (nrt - (i + 1)) >= (ns - sp)) {
+            pl.split_begin[sp++] = i + 1;
+        }
+    }
+    for (; sp < ns; ++sp) pl.split_begin[sp] = std::max(pl.split_begin[sp - 1], nrt - (ns - sp));
+    pl.split_begin[ns] = nrt;
+    for (int i = 1; i <= ns; ++i) pl.split_begin[i] = std::max(pl.split_begin[i], pl.split_begin[i - 1]);
+}
+
+int run_contract(gms_handle* h, const double* tiles, const double* emat, int mode, const int* ua, const int* ub,
+                 long long n_units, const Plan& pl, const int* split_d, double* Xout,
+                 cudaEvent_t e_before = nullptr, cudaEvent_t e_after = nullptr) {
+    if (n_units == 0) return GMS_OK;
+    ContractParams p{};
+    p.tiles = tiles;
+    p.chrom = h->chrom_d.p;
+    p.rowtiles = h->rowtiles_d.p;
+    p.split_begin = split_d;
+    p.emat = emat;
+    p.mp_total = h->mp_total;
+    p.planeA = h->planeA.p;
+    p.planeB = h->planeB.p;
+    p.wpp = h->wpp;
+    p.unit_a = ua;
+    p.unit_b = ub;
+    p.n_units = n_units;
+    p.T = h->T;
+    p.NU = BN / h->T;
+    p.mode = mode;
+    p.stages = h->stages;
+    p.Z = h->Z.p;
+    if (e_before) CU(cudaEventRecord(e_before, h->stream));
+    CU(launch_contract(p, pl.ntiles, pl.nsplit, h->stream));
+    if (e_after) CU(cudaEventRecord(e_after, h->stream));
+    CU(launch_finalize_sym(h->Z.p, pl.nsplit, n_units, h->T, Xout, h->stream));
+    h->st.last_launches += 2;
+    return GMS_OK;
+}
+
+int upload_effects(gms_handle* h, const double* host, DevBuf<double>& emat) {
+    const size_t n = (size_t)h->m * h->T;
+    CU(h->eff_raw.ensure(n));
+    CU(emat.ensure((size_t)h->mp_total * h->T));
+    CU(cudaMemcpyAsync(h->eff_raw.p, host, n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    CU(launch_scatter_effects(h->eff_raw.p, h->m, h->T, h->chrom_d.p, h->C, emat.p, h->mp_total, h->stream));
+    // eff_raw is reused by the next class: order on the stream keeps this safe
+    return GMS_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* gms_version(void) { return "gms_b200 0.1 (sm_100a; FP64 DMMA contraction; cp.async.bulk staged)"; }
+
+const char* gms_last_error(const gms_handle* h) {
+    if (h) return h->err.c_str();
+    std::lock_guard<std::mutex> lk(g_err_mu);
+    static thread_local std::string copy;
+    copy = g_create_err;
+    return copy.c_str();
+}
+
+int gms_create(gms_handle** out, int device) {
+    gms_handle* h = nullptr;
+    if (!out) return fail(h, GMS_EINVAL, "out is NULL");
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(h, GMS_ECUDA, std::string("no CUDA device (there is no CPU fallback): ") + cudaGetErrorString(e));
+    if (device < 0 || device >= ndev) return fail(h, GMS_EINVAL, "device index out of range");
+    gms_handle* nh = new (std::nothrow) gms_handle();
+    if (!nh) return fail(h, GMS_ENOMEM, "host allocation failed");
+    nh->device = device;
+    cudaDeviceProp prop;
+    if ((e = cudaSetDevice(device)) != cudaSuccess || (e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) {
+        delete nh;
+        return fail(h, GMS_ECUDA, std::string("cudaSetDevice: ") + cudaGetErrorString(e));
+    }
+    if (prop.major < 9) {
+        delete nh;
+        return fail(h, GMS_ECUDA, "device is not sm_100-class (this library is built for sm_100a only)");
+    }
+    nh->num_sms = prop.multiProcessorCount;
+    nh->smem_limit = prop.sharedMemPerBlockOptin;
+    if ((e = cudaStreamCreateWithFlags(&nh->own_stream, cudaStreamNonBlocking)) != cudaSuccess) {
+        delete nh;
+        return fail(h, GMS_ECUDA, std::string("cudaStreamCreate: ") + cudaGetErrorString(e));
+    }
+    nh->stream = nh->own_stream;
+    for (auto& ev : nh->ev) cudaEventCreate(&ev);
+    *out = nh;
+    return GMS_OK;
+}
+
+void gms_destroy(gms_handle* h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    h->chrom_d.release(); h->R.release(); h->R2.release(); h->planeA.release(); h->planeB.release();
+    h->rowtiles_d.release(); h->eff_raw.release(); h->emat_add.release(); h->emat_dom.release();
+    h->emat_asub.release(); h->sire_d.release(); h->dam_d.release(); h->sire_slot_d.release();
+    h->dam_slot_d.release(); h->plist_d.release(); h->pair1_d.release(); h->pair2_d.release();
+    h->split_par_d.release(); h->split_x_d.release(); h->flag_d.release(); h->Z.release(); h->QA.release();
+    h->PD.release(); h->QB.release(); h->X.release(); h->out_d.release(); h->nseg_d.release();
+    h->gebv_d.release(); h->mean_d.release();
+    for (auto& ev : h->ev) if (ev) cudaEventDestroy(ev);
+    if (h->own_stream) cudaStreamDestroy(h->own_stream);
+    delete h;
+}
+
+int gms_set_stream(gms_handle* h, void* cuda_stream) {
+    if (!h) return GMS_EINVAL;
+    if (int rc = bind(h)) return rc;
+    CU(cudaStreamSynchronize(h->stream));
+    h->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : h->own_stream;
+    return GMS_OK;
+}
+
+int gms_set_genmap(gms_handle* h, int C, const int64_t* m_c, const double* cM) {
+    if (!h) return GMS_EINVAL;
+    if (!cM) return fail(h, GMS_EINVAL, "cM is NULL");
+    if (int rc = bind(h)) return rc;
+    if (int rc = set_geometry(h, C, m_c)) return rc;
+    for (long long j = 0; j < h->m; ++j)
+        if (!std::isfinite(cM[j])) return fail(h, GMS_EINVAL, "non-finite map position");
+    DevBuf<double> cm_d;
+    CU(cm_d.ensure((size_t)h->m));
+    CU(cudaMemcpyAsync(cm_d.p, cM, sizeof(double) * h->m, cudaMemcpyHostToDevice, h->stream));
+    for (int c = 0; c < C; ++c)
+        CU(launch_build_tiles_from_map(cm_d.p + h->chrom[c].snp_off, h->chrom[c], h->R.p, h->R2.p, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    cm_d.release();
+    h->have_tiles = true;
+    return build_worklist(h);
+}
+
+int gms_set_recomb_blocks(gms_handle* h, int C, const int64_t* m_c, const double* const* blocks) {
+    if (!h) return GMS_EINVAL;
+    if (!blocks) return fail(h, GMS_EINVAL, "blocks is NULL");
+    if (int rc = bind(h)) return rc;
+    if (int rc = set_geometry(h, C, m_c)) return rc;
+    long long mmax = 0;
+    for (int c = 0; c < C; ++c) {
+        if (!blocks[c]) return fail(h, GMS_EINVAL, "blocks[c] is NULL");
+        mmax = std::max<long long>(mmax, m_c[c]);
+    }
+    DevBuf<double> blk_d;
+    CU(blk_d.ensure((size_t)mmax * mmax));
+    CU(h->flag_d.ensure(4));
+    CU(cudaMemsetAsync(h->flag_d.p, 0, sizeof(int) * 4, h->stream));
+    for (int c = 0; c < C; ++c) {
+        const size_t n = (size_t)m_c[c] * m_c[c];
+        CU(cudaMemcpyAsync(blk_d.p, blocks[c], n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+        CU(launch_build_tiles_from_block(blk_d.p, h->chrom[c], h->R.p, h->R2.p, h->flag_d.p, h->stream));
+        CU(cudaStreamSynchronize(h->stream));   // blk_d is reused
+    }
+    int asym = 0;
+    CU(cudaMemcpy(&asym, h->flag_d.p, sizeof(int), cudaMemcpyDeviceToHost));
+    blk_d.release();
+    if (asym) {
+        char buf[160];
+        snprintf(buf, sizeof buf, "recombFreqMat block is not symmetric / finite (%d entries differ from their transpose)", asym);
+        return fail(h, GMS_EINVAL, buf);
+    }
+    h->have_tiles = true;
+    return build_worklist(h);
+}
+
+static int set_haps_common(gms_handle* h, long long P, long long m, const void* hap, bool i32cm) {
+    if (!h) return GMS_EINVAL;
+    if (!h->have_tiles) return fail(h, GMS_ESTATE, "set the map / recombination blocks before the haplotypes");
+    if (!hap || P <= 0) return fail(h, GMS_EINVAL, "hap is NULL or P <= 0");
+    if (m != h->m) return fail(h, GMS_EINVAL, "haplotype matrix has a different number of SNPs than the map");
+    if (P > 65535 * 128LL) return fail(h, GMS_EINVAL, "too many parents");
+    if (int rc = bind(h)) return rc;
+    CU(h->planeA.ensure((size_t)P * h->wpp));
+    CU(h->planeB.ensure((size_t)P * h->wpp));
+    CU(h->flag_d.ensure(4));
+    CU(cudaMemsetAsync(h->flag_d.p, 0, sizeof(int) * 4, h->stream));
+    const size_t elems = (size_t)2 * P * m;
+    void* raw = nullptr;
+    CU(cudaMalloc(&raw, elems * (i32cm ? 4 : 1)));
+    cudaError_t e = cudaMemcpyAsync(raw, hap, elems * (i32cm ? 4 : 1), cudaMemcpyHostToDevice, h->stream);
+    if (e == cudaSuccess)
+        e = i32cm ? launch_pack_i32cm((const int32_t*)raw, P, m, h->chrom_d.p, h->C, h->planeA.p, h->planeB.p, h->wpp,
+                                      h->flag_d.p, h->stream)
+                  : launch_pack_u8rm((const uint8_t*)raw, P, m, h->chrom_d.p, h->C, h->planeA.p, h->planeB.p, h->wpp,
+                                     h->flag_d.p, h->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    cudaFree(raw);
+    CU(e);
+    int bad = 0;
+    CU(cudaMemcpy(&bad, h->flag_d.p, sizeof(int), cudaMemcpyDeviceToHost));
+    if (bad) {
+        h->have_haps = false;
+        char buf[128];
+        snprintf(buf, sizeof buf, "haploMat has %d values outside {0,1}", bad);
+        return fail(h, GMS_EINVAL, buf);
+    }
+    h->P = P;
+    h->have_haps = true;
+    h->staged = h->computed = false;
+    return GMS_OK;
+}
+
+int gms_set_haplotypes_i32cm(gms_handle* h, int64_t P, int64_t m, const int32_t* hap) {
+    return set_haps_common(h, P, m, hap, true);
+}
+int gms_set_haplotypes_u8rm(gms_handle* h, int64_t P, int64_t m, const uint8_t* hap) {
+    return set_haps_common(h, P, m, hap, false);
+}
+
+int gms_set_chromosome_shard(gms_handle* h, int c_begin, int c_end) {
+    if (!h) return GMS_EINVAL;
+    if (!h->have_tiles) return fail(h, GMS_ESTATE, "set the map / recombination blocks first");
+    if (c_begin < 0 || c_end > h->C || c_begin >= c_end) return fail(h, GMS_EINVAL, "bad chromosome range");
+    if (int rc = bind(h)) return rc;
+    h->c_begin = c_begin;
+    h->c_end = c_end;
+    h->staged = h->computed = false;
+    return build_worklist(h);
+}
+
+int gms_trait_pairs(int T, int32_t* t1, int32_t* t2) {
+    if (T < 1) return GMS_EINVAL;
+    int n = 0;
+    for (int t = 0; t < T; ++t, ++n) if (t1 && t2) { t1[n] = t; t2[n] = t; }
+    for (int a = 0; a < T; ++a)
+        for (int b = a + 1; b < T; ++b, ++n) if (t1 && t2) { t1[n] = a; t2[n] = b; }
+    return n;
+}
+
+int gms_stage_inputs(gms_handle* h, int model, int T, const double* add, const double* dom, const double* asub,
+                     int64_t N, const int32_t* sire, const int32_t* dam) {
+    if (!h) return GMS_EINVAL;
+    if (!h->have_tiles || !h->have_haps) return fail(h, GMS_ESTATE, "map and haplotypes must be set before predict");
+    if (model < GMS_MODEL_A || model > GMS_MODEL_DIRDOM) return fail(h, GMS_EINVAL, "unknown model");
+    if (T < 1 || T > MAX_T) return fail(h, GMS_EINVAL, "T must be in 1..32");
+    if (!add) return fail(h, GMS_EINVAL, "add effects are NULL");
+    if (model >= GMS_MODEL_AD && !dom) return fail(h, GMS_EINVAL, "dominance effects are required for AD / DirDom");
+    if (model == GMS_MODEL_DIRDOM && !asub) return fail(h, GMS_EINVAL, "allele-substitution effects are required for DirDom");
+    if (N < 0 || (N > 0 && (!sire || !dam))) return fail(h, GMS_EINVAL, "bad cross list");
+    if (N > (1LL << 31) - 1) return fail(h, GMS_EINVAL, "too many crosses in one call");
+    if (int rc = bind(h)) return rc;
+    h->staged = h->computed = false;
+    h->model = model;
+    h->T = T;
+    h->N = N;
+    h->ncomp = model + 1;
+    h->npairs = T * (T + 1) / 2;
+    h->stages = contract_pick_stages(T, h->smem_limit);
+    if (h->stages < 2) return fail(h, GMS_ECUDA, "not enough shared memory per block for the contraction kernel");
+
+    // distinct parents -> table slots (R/predCrossVar.R:44-46 subsets haploMat to the used parents)
+    std::vector<int> slot((size_t)h->P, -1), plist, ss((size_t)N), ds((size_t)N);
+    for (long long x = 0; x < N; ++x) {
+        const int s = sire[x], d = dam[x];
+        if (s < 0 || s >= h->P || d < 0 || d >= h->P) {
+            char buf[128];
+            snprintf(buf, sizeof buf, "cross %lld: parent index out of range (P = %lld)", (long long)x, h->P);
+            return fail(h, GMS_EINVAL, buf);
+        }
+        if (slot[s] < 0) { slot[s] = (int)plist.size(); plist.push_back(s); }
+        if (slot[d] < 0) { slot[d] = (int)plist.size(); plist.push_back(d); }
+        ss[x] = slot[s];
+        ds[x] = slot[d];
+    }
+    h->nP = (long long)plist.size();
+
+    CU(h->sire_d.ensure((size_t)N)); CU(h->dam_d.ensure((size_t)N));
+    CU(h->sire_slot_d.ensure((size_t)N)); CU(h->dam_slot_d.ensure((size_t)N));
+    CU(h->plist_d.ensure(plist.size()));
+    if (N) {
+        CU(cudaMemcpyAsync(h->sire_d.p, sire, sizeof(int) * N, cudaMemcpyHostToDevice, h->stream));
+        CU(cudaMemcpyAsync(h->dam_d.p, dam, sizeof(int) * N, cudaMemcpyHostToDevice, h->stream));
+        CU(cudaMemcpyAsync(h->sire_slot_d.p, ss.data(), sizeof(int) * N, cudaMemcpyHostToDevice, h->stream));
+        CU(cudaMemcpyAsync(h->dam_slot_d.p, ds.data(), sizeof(int) * N, cudaMemcpyHostToDevice, h->stream));
+        CU(cudaMemcpyAsync(h->plist_d.p, plist.data(), sizeof(int) * plist.size(), cudaMemcpyHostToDevice, h->stream));
+    }
+    std::vector<int32_t> p1(h->npairs), p2(h->npairs);
+    gms_trait_pairs(T, p1.data(), p2.data());
+    CU(h->pair1_d.ensure(h->npairs)); CU(h->pair2_d.ensure(h->npairs));
+    CU(cudaMemcpyAsync(h->pair1_d.p, p1.data(), sizeof(int) * h->npairs, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(h->pair2_d.p, p2.data(), sizeof(int) * h->npairs, cudaMemcpyHostToDevice, h->stream));
+
+    if (int rc = upload_effects(h, add, h->emat_add)) return rc;
+    if (model >= GMS_MODEL_AD) if (int rc = upload_effects(h, dom, h->emat_dom)) return rc;
+    if (model == GMS_MODEL_DIRDOM) if (int rc = upload_effects(h, asub, h->emat_asub)) return rc;
+
+    // plans and workspaces
+    const int NU = BN / T, TT = T * T;
+    make_plan(h, h->nP, NU, h->plan_par);
+    make_plan(h, model >= GMS_MODEL_AD ? N : 0, NU, h->plan_x);
+    CU(h->split_par_d.ensure(h->plan_par.split_begin.size()));
+    CU(h->split_x_d.ensure(h->plan_x.split_begin.size()));
+    CU(cudaMemcpyAsync(h->split_par_d.p, h->plan_par.split_begin.data(), sizeof(int) * h->plan_par.split_begin.size(),
+                       cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(h->split_x_d.p, h->plan_x.split_begin.data(), sizeof(int) * h->plan_x.split_begin.size(),
+                       cudaMemcpyHostToDevice, h->stream));
+    const size_t zneed = std::max<size_t>((size_t)h->plan_par.nsplit * (size_t)h->nP * TT,
+                                          model >= GMS_MODEL_AD ? (size_t)h->plan_x.nsplit * (size_t)N * TT : (size_t)0);
+    CU(h->Z.ensure(zneed));
+    CU(h->QA.ensure((size_t)h->nP * TT));
+    if (model >= GMS_MODEL_AD) { CU(h->PD.ensure((size_t)h->nP * TT)); CU(h->X.ensure((size_t)N * TT)); }
+    if (model == GMS_MODEL_DIRDOM) CU(h->QB.ensure((size_t)h->nP * TT));
+    CU(h->out_d.ensure((size_t)N * h->npairs * h->ncomp));
+    CU(h->nseg_d.ensure((size_t)N));
+    // the host vectors above go out of scope: make sure the copies are done
+    CU(cudaStreamSynchronize(h->stream));
+    h->staged = true;
+    return GMS_OK;
+}
+
+int gms_compute(gms_handle* h, int sync) {
+    if (!h) return GMS_EINVAL;
+    if (!h->staged) return fail(h, GMS_ESTATE, "gms_stage_inputs has not been called");
+    if (int rc = bind(h)) return rc;
+    h->st.last_launches = 0;
+    CU(cudaEventRecord(h->ev[0], h->stream));
+    // per-parent tables: Q_P = (a o delta_P)' R (a o delta_P), P_P = (d o het_P)' RoR (d o het_P)
+    if (int rc = run_contract(h, h->R.p, h->emat_add.p, MASK_DELTA, h->plist_d.p, nullptr, h->nP, h->plan_par,
+                              h->split_par_d.p, h->QA.p)) return rc;
+    if (h->model >= GMS_MODEL_AD)
+        if (int rc = run_contract(h, h->R2.p, h->emat_dom.p, MASK_HET, h->plist_d.p, nullptr, h->nP, h->plan_par,
+                                  h->split_par_d.p, h->PD.p)) return rc;
+    if (h->model == GMS_MODEL_DIRDOM)
+        if (int rc = run_contract(h, h->R.p, h->emat_asub.p, MASK_DELTA, h->plist_d.p, nullptr, h->nP, h->plan_par,
+                                  h->split_par_d.p, h->QB.p)) return rc;
+    CU(cudaEventRecord(h->ev[1], h->stream));
+    // per-cross dominance term X = (d o xi)' RoR (d o xi), xi = delta_sire o delta_dam
+    if (h->model >= GMS_MODEL_AD)
+        if (int rc = run_contract(h, h->R2.p, h->emat_dom.p, MASK_XI, h->sire_d.p, h->dam_d.p, h->N, h->plan_x,
+                                  h->split_x_d.p, h->X.p, h->ev[4], h->ev[5])) return rc;
+    CU(cudaEventRecord(h->ev[2], h->stream));
+    const long long w0 = h->chrom[h->c_begin].pad_off / 32;
+    const long long w1 = ((long long)h->chrom[h->c_end - 1].pad_off + h->chrom[h->c_end - 1].mp) / 32;
+    CU(launch_nseg(h->planeA.p, h->planeB.p, h->wpp, w0, w1, h->sire_d.p, h->dam_d.p, h->N, h->nseg_d.p, h->stream));
+    AssembleParams ap{};
+    ap.QA = h->QA.p; ap.PD = h->PD.p; ap.QB = h->QB.p; ap.X = h->X.p;
+    ap.sire_slot = h->sire_slot_d.p; ap.dam_slot = h->dam_slot_d.p;
+    ap.pair_t1 = h->pair1_d.p; ap.pair_t2 = h->pair2_d.p;
+    ap.N = h->N; ap.T = h->T; ap.npairs = h->npairs; ap.ncomp = h->ncomp; ap.out = h->out_d.p;
+    CU(launch_assemble(ap, h->stream));
+    h->st.last_launches += 2;
+    CU(cudaEventRecord(h->ev[3], h->stream));
+    h->computed = true;
+    if (sync) CU(cudaStreamSynchronize(h->stream));
+    return GMS_OK;
+}
+
+int gms_fetch_outputs(gms_handle* h, double* out, int32_t* nseg) {
+    if (!h) return GMS_EINVAL;
+    if (!h->computed) return fail(h, GMS_ESTATE, "gms_compute has not been called");
+    if (int rc = bind(h)) return rc;
+    if (h->N) {
+        if (out) CU(cudaMemcpyAsync(out, h->out_d.p, sizeof(double) * h->N * h->npairs * h->ncomp, cudaMemcpyDeviceToHost, h->stream));
+        if (nseg) CU(cudaMemcpyAsync(nseg, h->nseg_d.p, sizeof(int) * h->N, cudaMemcpyDeviceToHost, h->stream));
+    }
+    CU(cudaStreamSynchronize(h->stream));
+    return GMS_OK;
+}
+
+int gms_predict(gms_handle* h, int model, int T, const double* add, const double* dom, const double* asub,
+                int64_t N, const int32_t* sire, const int32_t* dam, double* out, int32_t* nseg) {
+    if (!h) return GMS_EINVAL;
+    if (N > 0 && (!out || !nseg)) return fail(h, GMS_EINVAL, "out / nseg is NULL");
+    if (int rc = gms_stage_inputs(h, model, T, add, dom, asub, N, sire, dam)) return rc;
+    if (int rc = gms_compute(h, 0)) return rc;
+    return gms_fetch_outputs(h, out, nseg);
+}
+
+int gms_selind(int model, int T, int64_t N, const double* out, const double* w, double* si) {
+    if (model < GMS_MODEL_A || model > GMS_MODEL_DIRDOM || T < 1 || N < 0 || !out || !w || !si) return GMS_EINVAL;
+    const int ncomp = model + 1, npairs = T * (T + 1) / 2;
+    std::vector<int32_t> p1(npairs), p2(npairs);
+    gms_trait_pairs(T, p1.data(), p2.data());
+    for (int64_t x = 0; x < N; ++x)
+        for (int c = 0; c < ncomp; ++c) {
+            double v = 0.0;
+            for (int pr = 0; pr < npairs; ++pr) {
+                const double g = out[(x * npairs + pr) * ncomp + c];
+                v += (p1[pr] == p2[pr] ? 1.0 : 2.0) * w[p1[pr]] * w[p2[pr]] * g;   // G symmetric (R/gmsFunctions.R:841)
+            }
+            si[x * ncomp + c] = v;
+        }
+    return GMS_OK;
+}
+
+int gms_cross_means(gms_handle* h, int T, const double* add, const double* dom, int64_t N, const int32_t* sire,
+                    const int32_t* dam, double* gebv, double* mean_bv, double* mean_tgv) {
+    if (!h) return GMS_EINVAL;
+    if (!h->have_tiles || !h->have_haps) return fail(h, GMS_ESTATE, "map and haplotypes must be set first");
+    if (T < 1 || T > MAX_T || !add || N < 0 || (N > 0 && (!sire || !dam))) return fail(h, GMS_EINVAL, "bad arguments");
+    if ((dom == nullptr) != (mean_tgv == nullptr)) return fail(h, GMS_EINVAL, "mean_tgv is required iff dom is given");
+    for (int64_t x = 0; x < N; ++x)
+        if (sire[x] < 0 || sire[x] >= h->P || dam[x] < 0 || dam[x] >= h->P) return fail(h, GMS_EINVAL, "parent index out of range");
+    if (int rc = bind(h)) return rc;
+    const int savedT = h->T;
+    h->T = T;
+    h->staged = h->computed = false;   // effect buffers are about to be overwritten
+    int rc = upload_effects(h, add, h->emat_add);
+    if (!rc && dom) rc = upload_effects(h, dom, h->emat_dom);
+    h->T = savedT;
+    if (rc) return rc;
+    CU(h->gebv_d.ensure((size_t)h->P * T));
+    CU(launch_gebv(h->planeA.p, h->planeB.p, h->wpp, nullptr, h->P, h->emat_add.p, h->mp_total, T, h->gebv_d.p, h->stream));
+    std::vector<double> g((size_t)h->P * T);
+    CU(cudaMemcpyAsync(g.data(), h->gebv_d.p, sizeof(double) * g.size(), cudaMemcpyDeviceToHost, h->stream));
+    if (dom && N) {
+        CU(h->sire_d.ensure((size_t)N)); CU(h->dam_d.ensure((size_t)N)); CU(h->mean_d.ensure((size_t)N * T));
+        CU(cudaMemcpyAsync(h->sire_d.p, sire, sizeof(int) * N, cudaMemcpyHostToDevice, h->stream));
+        CU(cudaMemcpyAsync(h->dam_d.p, dam, sizeof(int) * N, cudaMemcpyHostToDevice, h->stream));
+        CU(launch_tgv_mean(h->planeA.p, h->planeB.p, h->wpp, h->sire_d.p, h->dam_d.p, N, h->emat_add.p, h->emat_dom.p,
+                           h->mp_total, T, h->mean_d.p, h->stream));
+        CU(cudaMemcpyAsync(mean_tgv, h->mean_d.p, sizeof(double) * N * T, cudaMemcpyDeviceToHost, h->stream));
+    }
+    CU(cudaStreamSynchronize(h->stream));
+    if (gebv) memcpy(gebv, g.data(), sizeof(double) * g.size());
+    if (mean_bv)
+        for (int64_t x = 0; x < N; ++x)
+            for (int t = 0; t < T; ++t)
+                mean_bv[x * T + t] = (g[(size_t)sire[x] * T + t] + g[(size_t)dam[x] * T + t]) / 2.0;   // R/predCrossVar.R:369
+    return GMS_OK;
+}
+
+int gms_get_stats(gms_handle* h, gms_stats* s) {
+    if (!h || !s) return GMS_EINVAL;
+    if (int rc = bind(h)) return rc;
+    gms_stats& st = h->st;
+    st.m = h->m; st.m_padded = h->mp_total; st.S2 = h->S2; st.tile_bytes = 2 * h->tile_doubles * 8;
+    st.C = h->C; st.P = (int)h->P; st.last_T = h->T; st.last_model = h->model; st.last_N = h->N;
+    st.last_parents_used = h->nP;
+    if (h->computed) {
+        CU(cudaEventSynchronize(h->ev[3]));
+        cudaEventElapsedTime(&st.last_ms_parent_stage, h->ev[0], h->ev[1]);
+        cudaEventElapsedTime(&st.last_ms_cross_stage, h->ev[1], h->ev[2]);
+        cudaEventElapsedTime(&st.last_ms_assemble, h->ev[2], h->ev[3]);
+        cudaEventElapsedTime(&st.last_ms_total, h->ev[0], h->ev[3]);
+        st.last_ms_cross_kernel = 0.f;
+        if (h->model >= GMS_MODEL_AD && h->N > 0) cudaEventElapsedTime(&st.last_ms_cross_kernel, h->ev[4], h->ev[5]);
+        const double per_col = 2.0 * h->lower_elems;   // FMA = 2 flops, per (unit, trait) column
+        st.last_flops_cross = h->model >= GMS_MODEL_AD ? per_col * (double)h->N * h->T : 0.0;
+        st.last_flops_parent = per_col * (double)h->nP * h->T * (h->model + 1);
+    }
+    *s = st;
+    return GMS_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,68 @@
+// Shared constants and device-side descriptors of the cross-variance engine (sm_100a).
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace gms {
+
+// ---- tiling of the contraction  C[rows j, cols (unit,trait)] = L'[j,k] * W[k,(unit,trait)] ----
+constexpr int BM = 128;                 // rows of one row-tile I (SNP j)
+constexpr int BK = 32;                  // k per pipeline stage == one 32-bit haplotype word
+constexpr int BN = 80;                  // columns per unit-tile: NU = BN / T units x T traits
+constexpr int CHUNK = BM * BK;          // doubles per A chunk (32 KiB), fragment-major image
+constexpr int BCHUNK = BK * BN;         // doubles per generated B chunk (20 KiB)
+constexpr int MATH_WARPS = 8;           // 4 (M) x 2 (N); warp tile 32 x 40
+constexpr int PROD_WARPS = 2;           // operand producers (bulk copy + on-the-fly W generation)
+constexpr int NTHREADS = 32 * (MATH_WARPS + PROD_WARPS);
+constexpr int MAX_T = 32;
+
+enum MaskMode : int { MASK_DELTA = 0, MASK_HET = 1, MASK_XI = 2 };
+
+// One chromosome of the padded SNP axis. Chromosome c occupies padded indices
+// [pad_off, pad_off + mp), mp = roundup(m, 128); padded SNPs have zero effects and zero bits.
+struct ChromDesc {
+    long long tile_off;  // offset (doubles) of the chromosome's first chunk in a tile image
+    int m;               // real SNPs
+    int mp;              // padded SNPs (multiple of BM)
+    int snp_off;         // first SNP in the caller's (unpadded) order
+    int pad_off;         // first padded index (multiple of BM)
+};
+
+struct RowTile { int c; int I; };
+
+// Tile image layout (built by recomb.cu, consumed by contract.cu via cp.async.bulk):
+// per chromosome only the lower block triangle is stored: row-tile I owns chunks kc = 0 .. 4(I+1)-1
+// (k = 32 kc .. 32 kc + 31), chunk index within the chromosome = 2 I (I+1) + kc. The diagonal
+// 128 x 128 block is stored times 0.5, so that  x' M y = Z[t,s] + Z[s,t]  with Z from the lower
+// block triangle only (M symmetric).
+// Inside a chunk (4096 doubles) the order is the mma.m16n8k4 A-fragment order:
+//   e = ((q * 8 + mb) * 32 + lane) * 2 + hi,  q = k4-step (0..7), mb = 16-row block (0..7)
+//   row = 16 mb + (lane >> 2) + 8 hi,  k = 4 q + (lane & 3)
+__host__ __device__ inline long long chunks_before_rowtile(int I) { return 2LL * I * (I + 1); }
+__host__ __device__ inline long long chunks_of_chrom(int nI) { return 2LL * nI * (nI + 1); }
+
+struct ContractParams {
+    const double* tiles;         // R or RoR tile image
+    const ChromDesc* chrom;
+    const RowTile* rowtiles;     // work list, ordered by (c, I)
+    const int* split_begin;      // [nsplit + 1] ranges of rowtiles
+    const double* emat;          // T x mp_total effects on the padded axis
+    long long mp_total;
+    const unsigned* planeA;      // [P][wpp] HapA bits
+    const unsigned* planeB;      // [P][wpp] HapB bits
+    long long wpp;               // words per parent = mp_total / 32
+    const int* unit_a;           // parent (DELTA/HET) or sire (XI) of each unit
+    const int* unit_b;           // dam (XI)
+    long long n_units;
+    int T;
+    int NU;                      // units per tile = BN / T
+    int mode;
+    int stages;
+    double* Z;                   // [nsplit][n_units][T*T]: Z[t][s] = sum_j e_t[j] mask[j] (L' W_s)[j]
+};
+
+size_t contract_smem_bytes(int T, int stages);
+int contract_pick_stages(int T, size_t smem_limit);
+cudaError_t launch_contract(const ContractParams& p, int ntiles, int nsplit, cudaStream_t st);
+
+}  // namespace gms

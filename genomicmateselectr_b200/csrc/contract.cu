@@ -1,0 +1,294 @@
+// The dominant kernel: fused "generate W -> FP64 tensor contraction -> quadratic-form reduce".
+//
+// For a tile of NU units (crosses, or parents) and T traits it evaluates, for every unit u and
+// trait pair (t,s),
+//        Z_u[t,s] = sum_j  e_t[j] mask_u[j] * ( sum_k L'[j,k] * e_s[k] mask_u[k] )
+// where L' is the lower block triangle (diagonal block halved) of R or RoR for one chromosome,
+// e_t the SNP effects and mask_u in {-1,0,+1}^m comes straight from the bit-packed haplotypes:
+//   MASK_DELTA : delta_P = HapA - HapB            -> additive term    a' (R o dd') a
+//   MASK_HET   : het_P   = HapA xor HapB          -> dominance, per-parent part
+//   MASK_XI    : xi = delta_sire * delta_dam      -> dominance, per-cross part
+// The symmetric result is x' M y = Z[t,s] + Z[s,t] (finalize_sym in assemble.cu).
+// This replaces calcGameticLD + calcCrossLD + D*D + quadform of the reference
+// (R/predCrossVar.R:209-222,261-282; R/helpers.R:302) without ever forming an m x m LD matrix.
+//
+// Structure (one CTA = one unit-tile x one range of row-tiles, 10 warps):
+//   warps 8-9  producers: one thread issues cp.async.bulk (TMA engine, mbarrier complete_tx) for the
+//              pre-tiled 32 KiB A chunk; both warps generate the 32 x 80 W chunk on the fly from
+//              one haplotype word per unit and write it to shared memory in B-fragment order.
+//   warps 0-7  consumers: mma.sync.m16n8k4.f64 (DMMA) on a 32 x 40 warp tile, accumulators in
+//              registers; after each row-tile they fold the accumulators with e_t[j] mask_u[j]
+//              (warp shuffles) into a per-warp T x 40 table in shared memory.
+//   full/empty mbarrier ring of `stages` slots; no CTA-wide barrier in the main loop.
+#include "common.cuh"
+
+namespace gms {
+
+__device__ __forceinline__ unsigned smem_u32(const void* p) {
+    return static_cast<unsigned>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
+    unsigned ok;
+    do {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(ok)
+            : "r"(bar), "r"(parity)
+            : "memory");
+    } while (!ok);
+}
+// 1-D bulk async copy global -> shared, completion signalled on an mbarrier (SASS: UBLKCP).
+__device__ __forceinline__ void bulk_g2s(unsigned dst, const void* src, unsigned bytes, unsigned bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void dmma_16x8x4(double (&c)[4], double a0, double a1, double b0) {
+    asm volatile("mma.sync.aligned.m16n8k4.row.col.f64.f64.f64.f64 {%0,%1,%2,%3}, {%4,%5}, {%6}, {%0,%1,%2,%3};"
+                 : "+d"(c[0]), "+d"(c[1]), "+d"(c[2]), "+d"(c[3])
+                 : "d"(a0), "d"(a1), "d"(b0));
+}
+
+// nz / neg words of a unit for one 32-SNP word.
+__device__ __forceinline__ void unit_mask(const ContractParams& p, int pa, int pb, long long w,
+                                          unsigned& nz, unsigned& ng) {
+    nz = 0u; ng = 0u;
+    if (pa < 0) return;
+    const unsigned A = __ldg(p.planeA + (long long)pa * p.wpp + w);
+    const unsigned B = __ldg(p.planeB + (long long)pa * p.wpp + w);
+    if (p.mode == MASK_XI) {
+        const unsigned A2 = __ldg(p.planeA + (long long)pb * p.wpp + w);
+        const unsigned B2 = __ldg(p.planeB + (long long)pb * p.wpp + w);
+        nz = (A ^ B) & (A2 ^ B2);
+        ng = ((~A & B) ^ (~A2 & B2)) & nz;
+    } else {
+        nz = A ^ B;
+        ng = (p.mode == MASK_DELTA) ? (~A & B) : 0u;
+    }
+}
+
+__global__ void __launch_bounds__(NTHREADS, 1) contract_kernel(const ContractParams p) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int S = p.stages;
+    const int T = p.T;
+    double* As = reinterpret_cast<double*>(smem_raw);
+    double* Bs = As + (size_t)S * CHUNK;
+    double* Zacc = Bs + (size_t)S * BCHUNK;                       // [8 warps][40][T]
+    unsigned long long* bars = reinterpret_cast<unsigned long long*>(Zacc + MATH_WARPS * 40 * T);
+    const unsigned full0 = smem_u32(bars);
+    const unsigned empty0 = smem_u32(bars + S);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int g = lane >> 2, tig = lane & 3;
+    const int NU = p.NU;
+    const long long u0 = (long long)blockIdx.x * NU;
+    const int split = blockIdx.y;
+    const int rt_begin = p.split_begin[split], rt_end = p.split_begin[split + 1];
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < S; ++s) {
+            mbar_init(full0 + 8 * s, 1 + PROD_WARPS);   // expect_tx arrive + one arrive per producer warp
+            mbar_init(empty0 + 8 * s, MATH_WARPS);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    for (int i = threadIdx.x; i < MATH_WARPS * 40 * T; i += NTHREADS) Zacc[i] = 0.0;
+    __syncthreads();
+
+    if (warp >= MATH_WARPS) {
+        // ------------------------------------------------------------------ producers
+        const int pw = warp - MATH_WARPS;
+        int colu[5], colt[5];
+#pragma unroll
+        for (int b = 0; b < 5; ++b) {
+            const int n = 40 * pw + 8 * b + g;
+            if (n < NU * T) { colu[b] = n / T; colt[b] = n - colu[b] * T; }
+            else { colu[b] = -1; colt[b] = 0; }
+        }
+        const int ulo = (40 * pw) / T;
+        // lane keeps the parents of units ulo+lane and ulo+32+lane of this tile
+        int pa0 = -1, pb0 = -1, pa1 = -1, pb1 = -1;
+        {
+            const int ua = ulo + lane, ub = ulo + 32 + lane;
+            if (ua < NU && u0 + ua < p.n_units) { pa0 = p.unit_a[u0 + ua]; pb0 = (p.mode == MASK_XI) ? p.unit_b[u0 + ua] : 0; }
+            if (ub < NU && u0 + ub < p.n_units) { pa1 = p.unit_a[u0 + ub]; pb1 = (p.mode == MASK_XI) ? p.unit_b[u0 + ub] : 0; }
+        }
+        unsigned it = 0;
+        for (int rt = rt_begin; rt < rt_end; ++rt) {
+            const RowTile tile = p.rowtiles[rt];
+            const ChromDesc cd = p.chrom[tile.c];
+            const int nkc = 4 * (tile.I + 1);
+            const double* src = p.tiles + cd.tile_off + chunks_before_rowtile(tile.I) * CHUNK;
+            for (int kc = 0; kc < nkc; ++kc, ++it) {
+                const unsigned slot = it % S, ph = (it / S) & 1u;
+                mbar_wait(empty0 + 8 * slot, ph ^ 1u);
+                if (pw == 0 && lane == 0) {
+                    mbar_arrive_expect_tx(full0 + 8 * slot, CHUNK * 8);
+                    bulk_g2s(smem_u32(As + (size_t)slot * CHUNK), src + (size_t)kc * CHUNK, CHUNK * 8, full0 + 8 * slot);
+                }
+                const long long w = (cd.pad_off >> 5) + kc;
+                unsigned nz0, ng0, nz1, ng1;
+                unit_mask(p, pa0, pb0, w, nz0, ng0);
+                unit_mask(p, pa1, pb1, w, nz1, ng1);
+                const double* ebase = p.emat + cd.pad_off + 32 * kc;
+                double* bdst = Bs + (size_t)slot * BCHUNK + (5 * pw) * 32 + lane;
+#pragma unroll
+                for (int b = 0; b < 5; ++b) {
+                    const int rel = (colu[b] < 0 ? 0 : colu[b] - ulo);
+                    const int srcl = rel & 31;
+                    const unsigned a0 = __shfl_sync(0xffffffffu, nz0, srcl), a1 = __shfl_sync(0xffffffffu, nz1, srcl);
+                    const unsigned c0 = __shfl_sync(0xffffffffu, ng0, srcl), c1 = __shfl_sync(0xffffffffu, ng1, srcl);
+                    unsigned nz = (rel >> 5) ? a1 : a0, ng = (rel >> 5) ? c1 : c0;
+                    if (colu[b] < 0) nz = 0u;
+                    const double* ecol = ebase + (long long)colt[b] * p.mp_total;
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        const int k = 4 * q + tig;
+                        double e = 0.0;
+                        if ((nz >> k) & 1u) e = __ldg(ecol + k);
+                        if ((ng >> k) & 1u) e = -e;
+                        bdst[(q * 10 + b) * 32] = e;
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(full0 + 8 * slot);
+            }
+        }
+    } else {
+        // ------------------------------------------------------------------ consumers
+        const int wm = warp & 3, wn = warp >> 2;
+        double acc[2][5][4];
+        unsigned it = 0;
+        for (int rt = rt_begin; rt < rt_end; ++rt) {
+            const RowTile tile = p.rowtiles[rt];
+            const ChromDesc cd = p.chrom[tile.c];
+            const int nkc = 4 * (tile.I + 1);
+#pragma unroll
+            for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+                for (int ni = 0; ni < 5; ++ni)
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) acc[mi][ni][r] = 0.0;
+
+            for (int kc = 0; kc < nkc; ++kc, ++it) {
+                const unsigned slot = it % S, ph = (it / S) & 1u;
+                mbar_wait(full0 + 8 * slot, ph);
+                const double* a = As + (size_t)slot * CHUNK + ((2 * wm) * 32 + lane) * 2;
+                const double* b = Bs + (size_t)slot * BCHUNK + (5 * wn) * 32 + lane;
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const double2 a0 = *reinterpret_cast<const double2*>(a + (q * 8) * 64);
+                    const double2 a1 = *reinterpret_cast<const double2*>(a + (q * 8 + 1) * 64);
+                    double bf[5];
+#pragma unroll
+                    for (int ni = 0; ni < 5; ++ni) bf[ni] = b[(q * 10 + ni) * 32];
+#pragma unroll
+                    for (int ni = 0; ni < 5; ++ni) {
+                        dmma_16x8x4(acc[0][ni], a0.x, a0.y, bf[ni]);
+                        dmma_16x8x4(acc[1][ni], a1.x, a1.y, bf[ni]);
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(empty0 + 8 * slot);
+            }
+
+            // ---- row-tile epilogue: Zacc[col][t] += sum_rows e_t[row] * mask_u(col)[row] * acc[row][col]
+            const long long wrow = (cd.pad_off >> 5) + 4 * tile.I + wm;   // haplotype word of this warp's 32 rows
+#pragma unroll
+            for (int ni = 0; ni < 5; ++ni) {
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    const int n = 40 * wn + 8 * ni + 2 * tig + j;
+                    int pa = -1, pb = 0;
+                    if (n < NU * T) {
+                        const long long u = u0 + n / T;
+                        if (u < p.n_units) { pa = p.unit_a[u]; pb = (p.mode == MASK_XI) ? p.unit_b[u] : 0; }
+                    }
+                    unsigned nz, ng;
+                    unit_mask(p, pa, pb, wrow, nz, ng);
+#pragma unroll
+                    for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) {
+                            const int bit = 16 * mi + 8 * h + g;
+                            double v = acc[mi][ni][2 * h + j];
+                            if (!((nz >> bit) & 1u)) v = 0.0;
+                            if ((ng >> bit) & 1u) v = -v;
+                            acc[mi][ni][2 * h + j] = v;
+                        }
+                }
+            }
+            const double* erow = p.emat + cd.pad_off + BM * tile.I + 32 * wm + g;
+            double* zw = Zacc + (size_t)(warp * 40) * T;
+            for (int t = 0; t < T; ++t) {
+                const double* et = erow + (long long)t * p.mp_total;
+                const double e00 = __ldg(et), e01 = __ldg(et + 8), e10 = __ldg(et + 16), e11 = __ldg(et + 24);
+#pragma unroll
+                for (int ni = 0; ni < 5; ++ni) {
+#pragma unroll
+                    for (int j = 0; j < 2; ++j) {
+                        double s = e00 * acc[0][ni][j];
+                        s = fma(e01, acc[0][ni][2 + j], s);
+                        s = fma(e10, acc[1][ni][j], s);
+                        s = fma(e11, acc[1][ni][2 + j], s);
+                        s += __shfl_xor_sync(0xffffffffu, s, 4);
+                        s += __shfl_xor_sync(0xffffffffu, s, 8);
+                        s += __shfl_xor_sync(0xffffffffu, s, 16);
+                        if (g == 0) zw[(8 * ni + 2 * tig + j) * T + t] += s;
+                    }
+                }
+            }
+        }
+
+        // ---- write Z for this (tile, split): fixed summation order over the 4 M-warps
+        asm volatile("bar.sync 1, %0;" ::"n"(MATH_WARPS * 32) : "memory");
+        const int TT = T * T;
+        for (int idx = threadIdx.x; idx < NU * TT; idx += MATH_WARPS * 32) {
+            const int u = idx / TT;
+            const int rem = idx - u * TT;
+            const int t = rem / T, s = rem - t * T;
+            const int n = u * T + s;
+            const int wn2 = n / 40, cl = n - wn2 * 40;
+            double v = 0.0;
+#pragma unroll
+            for (int m4 = 0; m4 < 4; ++m4) v += Zacc[(size_t)((wn2 * 4 + m4) * 40 + cl) * T + t];
+            const long long unit = u0 + u;
+            if (unit < p.n_units) p.Z[((long long)split * p.n_units + unit) * TT + rem] = v;
+        }
+    }
+}
+
+size_t contract_smem_bytes(int T, int stages) {
+    return (size_t)stages * (CHUNK + BCHUNK) * 8 + (size_t)MATH_WARPS * 40 * T * 8 + (size_t)2 * stages * 8;
+}
+
+int contract_pick_stages(int T, size_t smem_limit) {
+    for (int s = 4; s >= 2; --s)
+        if (contract_smem_bytes(T, s) <= smem_limit) return s;
+    return 0;
+}
+
+cudaError_t launch_contract(const ContractParams& p, int ntiles, int nsplit, cudaStream_t st) {
+    const size_t smem = contract_smem_bytes(p.T, p.stages);
+    cudaError_t e = cudaFuncSetAttribute(contract_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    dim3 grid(ntiles, nsplit, 1);
+    contract_kernel<<<grid, NTHREADS, smem, st>>>(p);
+    return cudaGetLastError();
+}
+
+}  // namespace gms

@@ -1,0 +1,336 @@
+// HBM-bound kernels around the contraction: LD-decay tile builders (stage 1 of the path),
+// haplotype bit-packing, effect scatter, table finalisation, per-cross assembly, Nsegsnps, means.
+#include "kernels.cuh"
+
+namespace gms {
+
+// ------------------------------------------------------------------------------------------
+// Tile images. One block per 32 KiB chunk; element order documented in common.cuh.
+__device__ __forceinline__ void chunk_to_tile(long long ch, int& I, int& kc) {
+    int i = (int)((sqrt(1.0 + 2.0 * (double)ch) - 1.0) * 0.5);
+    while (chunks_before_rowtile(i + 1) <= ch) ++i;
+    while (chunks_before_rowtile(i) > ch) --i;
+    I = i;
+    kc = (int)(ch - chunks_before_rowtile(i));
+}
+
+__device__ __forceinline__ void elem_to_rowcol(int e, int I, int kc, int& row, int& col) {
+    const int hi = e & 1, lane = (e >> 1) & 31, mb = (e >> 6) & 7, q = e >> 9;
+    row = I * BM + mb * 16 + (lane >> 2) + 8 * hi;
+    col = kc * BK + 4 * q + (lane & 3);
+}
+
+// R/helpers.R:204-213 + `1-(2*c1)` (vignettes/start_here.Rmd:112), same operation order as R.
+__global__ void build_tiles_from_map_kernel(const double* __restrict__ cM, int m, long long tile_off,
+                                            double* __restrict__ R, double* __restrict__ R2) {
+    int I, kc;
+    chunk_to_tile(blockIdx.x, I, kc);
+    double* r_out = R + tile_off + (long long)blockIdx.x * CHUNK;
+    double* r2_out = R2 + tile_off + (long long)blockIdx.x * CHUNK;
+    const bool diag = (kc >> 2) == I;
+    for (int e = threadIdx.x; e < CHUNK; e += blockDim.x) {
+        int row, col;
+        elem_to_rowcol(e, I, kc, row, col);
+        double r = 0.0;
+        if (row < m && col < m) {
+            const double d = fabs(cM[row] - cM[col]);
+            const double c1 = 0.5 * (1.0 - exp(-2.0 * (d / 100.0)));
+            r = 1.0 - (2.0 * c1);
+        }
+        double r2 = r * r;                       // D*D of R/predCrossVar.R:219 up to exact powers of two
+        if (diag) { r *= 0.5; r2 *= 0.5; }
+        r_out[e] = r;
+        r2_out[e] = r2;
+    }
+}
+
+__global__ void build_tiles_from_block_kernel(const double* __restrict__ blk, int m, long long tile_off,
+                                              double* __restrict__ R, double* __restrict__ R2,
+                                              int* __restrict__ asym_count) {
+    int I, kc;
+    chunk_to_tile(blockIdx.x, I, kc);
+    double* r_out = R + tile_off + (long long)blockIdx.x * CHUNK;
+    double* r2_out = R2 + tile_off + (long long)blockIdx.x * CHUNK;
+    const bool diag = (kc >> 2) == I;
+    int bad = 0;
+    for (int e = threadIdx.x; e < CHUNK; e += blockDim.x) {
+        int row, col;
+        elem_to_rowcol(e, I, kc, row, col);
+        double r = 0.0;
+        if (row < m && col < m) {
+            r = blk[(long long)row + (long long)m * col];
+            const double rt = blk[(long long)col + (long long)m * row];
+            const double scale = fmax(1.0, fmax(fabs(r), fabs(rt)));
+            if (!(fabs(r - rt) <= 1e-12 * scale)) ++bad;    // also catches NaN
+        }
+        double r2 = r * r;
+        if (diag) { r *= 0.5; r2 *= 0.5; }
+        r_out[e] = r;
+        r2_out[e] = r2;
+    }
+    if (bad) atomicAdd(asym_count, bad);
+}
+
+cudaError_t launch_build_tiles_from_map(const double* cM_dev, const ChromDesc& cd, double* R, double* R2,
+                                        cudaStream_t st) {
+    const long long nch = chunks_of_chrom(cd.mp / BM);
+    build_tiles_from_map_kernel<<<(unsigned)nch, 256, 0, st>>>(cM_dev, cd.m, cd.tile_off, R, R2);
+    return cudaGetLastError();
+}
+cudaError_t launch_build_tiles_from_block(const double* blk_dev, const ChromDesc& cd, double* R, double* R2,
+                                          int* asym_count, cudaStream_t st) {
+    const long long nch = chunks_of_chrom(cd.mp / BM);
+    build_tiles_from_block_kernel<<<(unsigned)nch, 256, 0, st>>>(blk_dev, cd.m, cd.tile_off, R, R2, asym_count);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------
+// Haplotype bit-planes. Word w covers padded indices [32w, 32w+32); chromosomes start on
+// multiples of 128 so a word never straddles two chromosomes.
+__device__ __forceinline__ bool word_to_snp(long long w, const ChromDesc* chrom, int C, long long& snp0, int& nvalid) {
+    const long long pidx = w * 32;
+    for (int c = 0; c < C; ++c) {
+        const ChromDesc cd = chrom[c];
+        if (pidx >= cd.pad_off && pidx < (long long)cd.pad_off + cd.mp) {
+            const long long local = pidx - cd.pad_off;
+            snp0 = cd.snp_off + local;
+            const long long left = (long long)cd.m - local;
+            nvalid = left <= 0 ? 0 : (left >= 32 ? 32 : (int)left);
+            return true;
+        }
+    }
+    nvalid = 0;
+    snp0 = 0;
+    return false;
+}
+
+__global__ void pack_i32cm_kernel(const int32_t* __restrict__ hap, long long P, long long m,
+                                  const ChromDesc* __restrict__ chrom, int C, unsigned* __restrict__ planeA,
+                                  unsigned* __restrict__ planeB, long long wpp, int* __restrict__ bad_count) {
+    const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long w = blockIdx.y;
+    if (p >= P) return;
+    long long snp0; int nvalid;
+    word_to_snp(w, chrom, C, snp0, nvalid);
+    unsigned a = 0, b = 0; int bad = 0;
+    for (int i = 0; i < nvalid; ++i) {
+        const long long j = snp0 + i;
+        const int va = hap[2 * p + 2 * P * j], vb = hap[2 * p + 1 + 2 * P * j];
+        bad += ((unsigned)va > 1u) + ((unsigned)vb > 1u);
+        a |= (unsigned)(va & 1) << i;
+        b |= (unsigned)(vb & 1) << i;
+    }
+    planeA[p * wpp + w] = a;
+    planeB[p * wpp + w] = b;
+    if (bad) atomicAdd(bad_count, bad);
+}
+
+__global__ void pack_u8rm_kernel(const uint8_t* __restrict__ hap, long long P, long long m,
+                                 const ChromDesc* __restrict__ chrom, int C, unsigned* __restrict__ planeA,
+                                 unsigned* __restrict__ planeB, long long wpp, int* __restrict__ bad_count) {
+    const long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long p = blockIdx.y;
+    if (w >= wpp) return;
+    long long snp0; int nvalid;
+    word_to_snp(w, chrom, C, snp0, nvalid);
+    const uint8_t* ra = hap + (2 * p) * m + snp0;
+    const uint8_t* rb = hap + (2 * p + 1) * m + snp0;
+    unsigned a = 0, b = 0; int bad = 0;
+    for (int i = 0; i < nvalid; ++i) {
+        const unsigned va = ra[i], vb = rb[i];
+        bad += (va > 1u) + (vb > 1u);
+        a |= (va & 1u) << i;
+        b |= (vb & 1u) << i;
+    }
+    planeA[p * wpp + w] = a;
+    planeB[p * wpp + w] = b;
+    if (bad) atomicAdd(bad_count, bad);
+}
+
+cudaError_t launch_pack_i32cm(const int32_t* hap_dev, long long P, long long m, const ChromDesc* chrom, int C,
+                              unsigned* planeA, unsigned* planeB, long long wpp, int* bad_count, cudaStream_t st) {
+    dim3 grid((unsigned)((P + 127) / 128), (unsigned)wpp);
+    pack_i32cm_kernel<<<grid, 128, 0, st>>>(hap_dev, P, m, chrom, C, planeA, planeB, wpp, bad_count);
+    return cudaGetLastError();
+}
+cudaError_t launch_pack_u8rm(const uint8_t* hap_dev, long long P, long long m, const ChromDesc* chrom, int C,
+                             unsigned* planeA, unsigned* planeB, long long wpp, int* bad_count, cudaStream_t st) {
+    dim3 grid((unsigned)((wpp + 127) / 128), (unsigned)P);
+    pack_u8rm_kernel<<<grid, 128, 0, st>>>(hap_dev, P, m, chrom, C, planeA, planeB, wpp, bad_count);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------
+__global__ void scatter_effects_kernel(const double* __restrict__ eff, long long m, int T,
+                                       const ChromDesc* __restrict__ chrom, int C, double* __restrict__ emat,
+                                       long long mp_total) {
+    const long long pidx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int t = blockIdx.y;
+    if (pidx >= mp_total) return;
+    double v = 0.0;
+    for (int c = 0; c < C; ++c) {
+        const ChromDesc cd = chrom[c];
+        if (pidx >= cd.pad_off && pidx < (long long)cd.pad_off + cd.mp) {
+            const long long local = pidx - cd.pad_off;
+            if (local < cd.m) v = eff[(long long)t * m + cd.snp_off + local];
+            break;
+        }
+    }
+    emat[(long long)t * mp_total + pidx] = v;
+}
+cudaError_t launch_scatter_effects(const double* eff_dev, long long m, int T, const ChromDesc* chrom, int C,
+                                   double* emat, long long mp_total, cudaStream_t st) {
+    dim3 grid((unsigned)((mp_total + 255) / 256), (unsigned)T);
+    scatter_effects_kernel<<<grid, 256, 0, st>>>(eff_dev, m, T, chrom, C, emat, mp_total);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------
+__global__ void finalize_sym_kernel(const double* __restrict__ Z, int nsplit, long long n, int T,
+                                    double* __restrict__ X) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int TT = T * T;
+    if (idx >= n * TT) return;
+    const long long u = idx / TT;
+    const int rem = (int)(idx - u * TT);
+    const int t = rem / T, s = rem - t * T;
+    double v = 0.0;
+    for (int sp = 0; sp < nsplit; ++sp) {           // fixed order: bit-reproducible
+        const double* z = Z + ((long long)sp * n + u) * TT;
+        v += z[t * T + s] + z[s * T + t];
+    }
+    X[idx] = v;
+}
+cudaError_t launch_finalize_sym(const double* Z, int nsplit, long long n, int T, double* X, cudaStream_t st) {
+    const long long total = n * T * T;
+    if (total == 0) return cudaSuccess;
+    finalize_sym_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(Z, nsplit, n, T, X);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------
+// Nsegsnps (R/predCrossVar.R:111-113): x = sum of the 4 haplotype rows, keep 0 < x < 4.
+__global__ void nseg_kernel(const unsigned* __restrict__ planeA, const unsigned* __restrict__ planeB, long long wpp,
+                            long long w_begin, long long w_end, const int* __restrict__ sire,
+                            const int* __restrict__ dam, long long N, int* __restrict__ nseg) {
+    const long long x = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (x >= N) return;
+    const unsigned* As = planeA + (long long)sire[x] * wpp;
+    const unsigned* Bs = planeB + (long long)sire[x] * wpp;
+    const unsigned* Ad = planeA + (long long)dam[x] * wpp;
+    const unsigned* Bd = planeB + (long long)dam[x] * wpp;
+    int cnt = 0;
+    for (long long w = w_begin + lane; w < w_end; w += 32) {
+        const unsigned a = As[w], b = Bs[w], c = Ad[w], d = Bd[w];
+        cnt += __popc((a | b | c | d) & ~(a & b & c & d));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    if (lane == 0) nseg[x] = cnt;
+}
+cudaError_t launch_nseg(const unsigned* planeA, const unsigned* planeB, long long wpp, long long w_begin,
+                        long long w_end, const int* sire, const int* dam, long long N, int* nseg, cudaStream_t st) {
+    if (N == 0) return cudaSuccess;
+    const long long threads = N * 32;
+    nseg_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(planeA, planeB, wpp, w_begin, w_end, sire, dam, N, nseg);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------
+// VarA = 1/4 (Q_sire + Q_dam); VarD = 1/16 (P_sire + P_dam + 2 X); VarBV likewise from asub.
+__global__ void assemble_kernel(const AssembleParams p) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= p.N * p.npairs) return;
+    const long long x = idx / p.npairs;
+    const int pr = (int)(idx - x * p.npairs);
+    const int TT = p.T * p.T;
+    const int i = p.pair_t1[pr] * p.T + p.pair_t2[pr];
+    const long long ss = (long long)p.sire_slot[x] * TT + i, ds = (long long)p.dam_slot[x] * TT + i;
+    double* o = p.out + idx * p.ncomp;
+    o[0] = 0.25 * (p.QA[ss] + p.QA[ds]);
+    if (p.ncomp >= 2) o[1] = 0.0625 * (p.PD[ss] + p.PD[ds] + 2.0 * p.X[x * TT + i]);
+    if (p.ncomp >= 3) o[2] = 0.25 * (p.QB[ss] + p.QB[ds]);
+}
+cudaError_t launch_assemble(const AssembleParams& p, cudaStream_t st) {
+    const long long total = p.N * p.npairs;
+    if (total == 0) return cudaSuccess;
+    assemble_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(p);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------
+// predCrossMeans (R/predCrossVar.R:336-399).
+__device__ __forceinline__ double block_sum(double v, double* sh) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    __syncthreads();
+    if (lane == 0) sh[warp] = v;
+    __syncthreads();
+    double r = 0.0;
+    if (threadIdx.x == 0)
+        for (int i = 0; i < (int)(blockDim.x >> 5); ++i) r += sh[i];
+    return r;   // valid on thread 0
+}
+
+__global__ void gebv_kernel(const unsigned* __restrict__ planeA, const unsigned* __restrict__ planeB, long long wpp,
+                            const int* __restrict__ plist, const double* __restrict__ emat, long long mp_total, int T,
+                            double* __restrict__ gebv) {
+    __shared__ double sh[8];
+    const int par = plist ? plist[blockIdx.x] : (int)blockIdx.x;
+    const unsigned* A = planeA + (long long)par * wpp;
+    const unsigned* B = planeB + (long long)par * wpp;
+    for (int t = 0; t < T; ++t) {
+        const double* e = emat + (long long)t * mp_total;
+        double s = 0.0;
+        for (long long j = threadIdx.x; j < mp_total; j += blockDim.x) {
+            const int dose = ((A[j >> 5] >> (j & 31)) & 1u) + ((B[j >> 5] >> (j & 31)) & 1u);
+            s += dose * e[j];
+        }
+        const double tot = block_sum(s, sh);
+        if (threadIdx.x == 0) gebv[(long long)blockIdx.x * T + t] = tot;
+    }
+}
+cudaError_t launch_gebv(const unsigned* planeA, const unsigned* planeB, long long wpp, const int* plist,
+                        long long nP, const double* emat, long long mp_total, int T, double* gebv, cudaStream_t st) {
+    if (nP == 0) return cudaSuccess;
+    gebv_kernel<<<(unsigned)nP, 256, 0, st>>>(planeA, planeB, wpp, plist, emat, mp_total, T, gebv);
+    return cudaGetLastError();
+}
+
+__global__ void tgv_mean_kernel(const unsigned* __restrict__ planeA, const unsigned* __restrict__ planeB,
+                                long long wpp, const int* __restrict__ sire, const int* __restrict__ dam,
+                                const double* __restrict__ ea, const double* __restrict__ ed, long long mp_total,
+                                int T, double* __restrict__ out) {
+    __shared__ double sh[8];
+    const long long x = blockIdx.x;
+    const unsigned* As = planeA + (long long)sire[x] * wpp;
+    const unsigned* Bs = planeB + (long long)sire[x] * wpp;
+    const unsigned* Ad = planeA + (long long)dam[x] * wpp;
+    const unsigned* Bd = planeB + (long long)dam[x] * wpp;
+    for (int t = 0; t < T; ++t) {
+        const double* a = ea + (long long)t * mp_total;
+        const double* d = ed + (long long)t * mp_total;
+        double s = 0.0;
+        for (long long j = threadIdx.x; j < mp_total; j += blockDim.x) {
+            const int sh_ = (int)(j & 31);
+            const long long w = j >> 5;
+            const double p1 = 0.5 * (((As[w] >> sh_) & 1u) + ((Bs[w] >> sh_) & 1u));
+            const double p2 = 0.5 * (((Ad[w] >> sh_) & 1u) + ((Bd[w] >> sh_) & 1u));
+            const double q = 1.0 - p1, y = p1 - p2;
+            s += a[j] * (p1 - q - y) + d[j] * ((2.0 * p1 * q) + y * (p1 - q));
+        }
+        const double tot = block_sum(s, sh);
+        if (threadIdx.x == 0) out[x * T + t] = tot;
+    }
+}
+cudaError_t launch_tgv_mean(const unsigned* planeA, const unsigned* planeB, long long wpp, const int* sire,
+                            const int* dam, long long N, const double* emat_add, const double* emat_dom,
+                            long long mp_total, int T, double* mean_tgv, cudaStream_t st) {
+    if (N == 0) return cudaSuccess;
+    tgv_mean_kernel<<<(unsigned)N, 256, 0, st>>>(planeA, planeB, wpp, sire, dam, emat_add, emat_dom, mp_total, T, mean_tgv);
+    return cudaGetLastError();
+}
+
+}  // namespace gms

@@ -1,0 +1,54 @@
+// Launchers of the small (HBM-bound) kernels around the contraction; see kernels.cu.
+#pragma once
+#include "common.cuh"
+
+namespace gms {
+
+// stage (1): LD-decay tile images (R and RoR) in HBM, straight from the genetic map or from a
+// caller-made recombFreqMat block. `asym_count` (device int) counts asymmetric entries.
+cudaError_t launch_build_tiles_from_map(const double* cM_dev, const ChromDesc& cd, double* R, double* R2,
+                                        cudaStream_t st);
+cudaError_t launch_build_tiles_from_block(const double* blk_dev, const ChromDesc& cd, double* R, double* R2,
+                                          int* asym_count, cudaStream_t st);
+
+// haplotype bit-planes on the padded SNP axis. `bad_count` counts values outside {0,1}.
+cudaError_t launch_pack_i32cm(const int32_t* hap_dev, long long P, long long m, const ChromDesc* chrom, int C,
+                              unsigned* planeA, unsigned* planeB, long long wpp, int* bad_count, cudaStream_t st);
+cudaError_t launch_pack_u8rm(const uint8_t* hap_dev, long long P, long long m, const ChromDesc* chrom, int C,
+                             unsigned* planeA, unsigned* planeB, long long wpp, int* bad_count, cudaStream_t st);
+
+// effects: caller layout (m x T column-major, unpadded) -> padded emat (T x mp_total)
+cudaError_t launch_scatter_effects(const double* eff_dev, long long m, int T, const ChromDesc* chrom, int C,
+                                   double* emat, long long mp_total, cudaStream_t st);
+
+// X[n][t][s] = sum_split Z[split][n][t][s] + Z[split][n][s][t]
+cudaError_t launch_finalize_sym(const double* Z, int nsplit, long long n, int T, double* X, cudaStream_t st);
+
+// Nsegsnps per cross over words [w_begin, w_end) of the padded axis.
+cudaError_t launch_nseg(const unsigned* planeA, const unsigned* planeB, long long wpp, long long w_begin,
+                        long long w_end, const int* sire, const int* dam, long long N, int* nseg, cudaStream_t st);
+
+// out[x][pair][comp] from the per-parent tables and the per-cross table.
+struct AssembleParams {
+    const double* QA;    // [P'][T][T] additive table of (add, R, delta)
+    const double* PD;    // [P'][T][T] dominance per-parent table of (dom, RoR, het) or NULL
+    const double* QB;    // [P'][T][T] additive table of asub (DirDom VarBV) or NULL
+    const double* X;     // [N][T][T] per-cross dominance term or NULL
+    const int* sire_slot;  // [N] index into the tables
+    const int* dam_slot;
+    const int* pair_t1;  // [npairs]
+    const int* pair_t2;
+    long long N;
+    int T, npairs, ncomp;
+    double* out;         // [N][npairs][ncomp]
+};
+cudaError_t launch_assemble(const AssembleParams& p, cudaStream_t st);
+
+// predCrossMeans: gebv[p][t] = sum_j dose_pj add_t[j]; TGV mean per cross (Falconer-MacKay 14.6).
+cudaError_t launch_gebv(const unsigned* planeA, const unsigned* planeB, long long wpp, const int* plist,
+                        long long nP, const double* emat, long long mp_total, int T, double* gebv, cudaStream_t st);
+cudaError_t launch_tgv_mean(const unsigned* planeA, const unsigned* planeB, long long wpp, const int* sire,
+                            const int* dam, long long N, const double* emat_add, const double* emat_dom,
+                            long long mp_total, int T, double* mean_tgv, cudaStream_t st);
+
+}  // namespace gms

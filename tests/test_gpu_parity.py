@@ -1,0 +1,254 @@
+"""GPU parity tests: the CUDA path, called through the C ABI (ctypes), against the CPU oracle.
+Tolerance (BASELINE.json north_star): 1e-9 relative on every variance and covariance;
+Nsegsnps bit-exact."""
+import numpy as np
+import pytest
+
+from oracle import predcrossvar_oracle as O
+from tests.util import oracle_slab, oracle_slab_blockwise, rel_err
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-9
+
+
+@pytest.fixture(scope="module")
+def gms():
+    import genomicmateselectr_b200 as g
+    return g
+
+
+def bundled_engine(gms, b, use_map=False):
+    eng = gms.CrossVarEngine(0)
+    idx = []
+    for p in b.PARENTS:
+        idx += [b.hap_rownames.index(f"{p}_HapA"), b.hap_rownames.index(f"{p}_HapB")]
+    H = b.haploMat[idx]
+    eng.set_recomb_matrix(b.recombFreqMat, b.chrom)
+    eng.set_haplotypes(H)
+    sire, dam = zip(*[(i, j) for i in range(5) for j in range(i, 5)])
+    return eng, H, np.array(sire, np.int32), np.array(dam, np.int32)
+
+
+# ---------------------------------------------------------------- configs 1-3: bundled data
+def test_bundled_A_single_trait(gms, bundled):
+    b = bundled
+    eng, H, sire, dam = bundled_engine(gms, b)
+    out, nseg = eng.predict("A", b.effA[:, :1], None, None, sire, dam)
+    want, wseg = oracle_slab("A", H, b.recombFreqMat, b.effA[:, :1], None, None, sire, dam)
+    assert out.shape == (15, 1, 1)
+    assert np.array_equal(nseg, wseg) and list(nseg[:4]) == [22, 46, 48, 53]
+    assert rel_err(out, want) < TOL
+    assert round(out[0, 0, 0]) == 707          # docs/articles/start_here.html:385
+    eng.close()
+
+
+def test_bundled_A_two_traits_matches_vignette(gms, bundled):
+    b = bundled
+    eng, H, sire, dam = bundled_engine(gms, b)
+    out, nseg = eng.predict("A", b.effA, None, None, sire, dam)
+    want, wseg = oracle_slab("A", H, b.recombFreqMat, b.effA, None, None, sire, dam)
+    assert np.array_equal(nseg, wseg)
+    assert rel_err(out, want) < TOL
+    # slab pair order (T1,T1),(T2,T2),(T1,T2): 707 1519 -350 | 1079 1813 (start_here.html:385)
+    assert [round(v) for v in out[0, :, 0]] == [707, 1519, -350]
+    assert [round(v) for v in out[1, :2, 0]] == [1079, 1813]
+    si = eng.selind("A", out, [0.75, 0.25])
+    assert [round(v) for v in si[:4, 0]] == [361, 454, 458, 536]      # start_here.html:333-342
+    eng.close()
+
+
+def test_bundled_AD_matches_vignette(gms, bundled):
+    b = bundled
+    eng, H, sire, dam = bundled_engine(gms, b)
+    out, nseg = eng.predict("AD", b.effAD_add, b.effAD_dom, None, sire, dam)
+    want, wseg = oracle_slab("AD", H, b.recombFreqMat, b.effAD_add, b.effAD_dom, None, sire, dam)
+    assert np.array_equal(nseg, wseg)
+    assert rel_err(out, want) < TOL
+    x = 14                                         # 146 x 146 is the last cross
+    assert nseg[x] == 34
+    assert [round(v) for v in out[x, :, 0]] == [1232, 1976, -820]     # non_additive_models.html:624-626
+    assert [round(v, 2) for v in out[x, :, 1]] == [9.97, 51.27, 9.04]  # :627-629 (51.3 printed)
+    si = eng.selind("AD", out, [0.75, 0.25])
+    assert round(si[x, 0]) == 509 and round(si[x, 0] + si[x, 1]) == 521   # :600-601
+    eng.close()
+
+
+def test_bundled_DirDom(gms, bundled):
+    b = bundled
+    a, d, alpha = b.dirdom_effects()
+    eng, H, sire, dam = bundled_engine(gms, b)
+    out, nseg = eng.predict("DirDom", a, d, alpha, sire, dam)
+    want, wseg = oracle_slab("DirDom", H, b.recombFreqMat, a, d, alpha, sire, dam)
+    assert out.shape == (15, 3, 3)
+    assert np.array_equal(nseg, wseg)
+    assert rel_err(out, want) < TOL
+    eng.close()
+
+
+# ---------------------------------------------------------------- synthetic, ragged shapes
+def synth(seed, m_c, P, T):
+    rng = np.random.default_rng(seed)
+    m_c = np.asarray(m_c)
+    m = int(m_c.sum())
+    cM = np.concatenate([np.sort(rng.uniform(0, 120, k)) for k in m_c])
+    chrom = np.repeat(np.arange(1, len(m_c) + 1), m_c)
+    p = rng.uniform(0.05, 0.95, m)
+    H = (rng.random((2 * P, m)) < p).astype(np.uint8)
+    add = rng.standard_normal((m, T))
+    dom = 0.5 * rng.standard_normal((m, T))
+    asub = add + dom * (1 - 2 * p)[:, None]
+    R = O.recombfreq_to_ld_decay(O.genmap2recombfreq(cM, chrom))
+    return dict(m=m, m_c=m_c, cM=cM, chrom=chrom, H=H, add=add, dom=dom, asub=asub, R=R)
+
+
+@pytest.mark.parametrize("model", ["A", "AD", "DirDom"])
+@pytest.mark.parametrize("T", [1, 2, 3, 5, 7, 16])
+def test_synthetic_map_path(gms, model, T):
+    s = synth(100 + T, [200, 131, 77, 300], P=24, T=T)
+    rng = np.random.default_rng(5)
+    sire = rng.integers(0, 24, 70).astype(np.int32)
+    dam = rng.integers(0, 24, 70).astype(np.int32)
+    sire[:6] = dam[:6]                      # selfs
+    sire[6], dam[6] = sire[7], dam[7]       # a duplicate row
+    eng = gms.CrossVarEngine(0)
+    eng.set_genmap(s["cM"], s["m_c"])
+    eng.set_haplotypes(s["H"])
+    dom = s["dom"] if model != "A" else None
+    asub = s["asub"] if model == "DirDom" else None
+    out, nseg = eng.predict(model, s["add"], dom, asub, sire, dam)
+    want, wseg = oracle_slab(model, s["H"], s["R"], s["add"], dom, asub, sire, dam)
+    assert np.array_equal(nseg, wseg)
+    assert rel_err(out, want) < TOL
+    assert np.array_equal(out[6], out[7])
+    eng.close()
+
+
+def test_blocks_path_equals_map_path_and_many_rowtiles(gms):
+    s = synth(11, [700, 390, 129], P=12, T=5)     # 6 + 4 + 2 row tiles; ragged last tiles
+    sire = np.array([0, 1, 2, 3, 4, 5, 6, 7, 3], np.int32)
+    dam = np.array([1, 1, 5, 9, 10, 11, 6, 0, 8], np.int32)
+    eng = gms.CrossVarEngine(0)
+    eng.set_genmap(s["cM"], s["m_c"])
+    eng.set_haplotypes(s["H"])
+    out1, nseg1 = eng.predict("AD", s["add"], s["dom"], None, sire, dam)
+    want, wseg = oracle_slab("AD", s["H"], s["R"], s["add"], s["dom"], None, sire, dam)
+    assert np.array_equal(nseg1, wseg) and rel_err(out1, want) < TOL
+    eng2 = gms.CrossVarEngine(0)
+    assert eng2.set_recomb_matrix(s["R"], s["chrom"]) is True
+    eng2.set_haplotypes(s["H"].astype(np.int32).copy(order="F"))   # R integer-matrix layout entry point
+    out2, nseg2 = eng2.predict("AD", s["add"], s["dom"], None, sire, dam)
+    assert np.array_equal(nseg2, wseg) and rel_err(out2, want) < TOL
+    # chromosome shards add up to the whole (multi-GPU chromosome axis)
+    acc = np.zeros_like(out1)
+    accn = np.zeros_like(nseg1)
+    for c in range(3):
+        eng.set_chromosome_shard(c, c + 1)
+        o, n = eng.predict("AD", s["add"], s["dom"], None, sire, dam)
+        acc += o
+        accn += n
+    assert np.array_equal(accn, wseg) and rel_err(acc, want) < TOL
+    eng.close()
+    eng2.close()
+
+
+def test_general_matrix_single_block(gms):
+    """recombFreqMat with non-zero off-chromosome entries -> one dense block."""
+    rng = np.random.default_rng(3)
+    m, P, T = 150, 6, 2
+    B = rng.standard_normal((m, m))
+    R = B @ B.T / m
+    chrom = np.repeat([1, 2], [80, 70])
+    H = (rng.random((2 * P, m)) < 0.5).astype(np.uint8)
+    add, dom = rng.standard_normal((m, T)), rng.standard_normal((m, T))
+    sire = np.array([0, 1, 2, 3], np.int32)
+    dam = np.array([0, 2, 4, 5], np.int32)
+    eng = gms.CrossVarEngine(0)
+    assert eng.set_recomb_matrix(R, chrom) is False
+    eng.set_haplotypes(H)
+    out, nseg = eng.predict("AD", add, dom, None, sire, dam)
+    want, wseg = oracle_slab("AD", H, R, add, dom, None, sire, dam)
+    assert np.array_equal(nseg, wseg) and rel_err(out, want) < TOL
+    eng.close()
+
+
+# ---------------------------------------------------------------- edge cases and errors
+def test_edge_cases(gms):
+    s = synth(2, [64, 40], P=4, T=2)
+    H = s["H"].copy()
+    H[0] = H[1] = H[2] = H[3] = 1            # parents 0 and 1: fixed for allele 1 everywhere
+    eng = gms.CrossVarEngine(0)
+    eng.set_genmap(s["cM"], s["m_c"])
+    eng.set_haplotypes(H)
+    out, nseg = eng.predict("AD", s["add"], s["dom"], None, [0, 0, 2], [1, 0, 3])
+    assert list(nseg[:2]) == [0, 0] and np.all(out[:2] == 0.0)     # vanishing crosses (R/predCrossVar.R:156-160)
+    want, wseg = oracle_slab("AD", H, s["R"], s["add"], s["dom"], None, [2], [3])
+    assert nseg[2] == wseg[0] and rel_err(out[2:], want) < TOL
+    out0, nseg0 = eng.predict("A", s["add"], None, None, [], [])   # empty cross list
+    assert out0.shape == (0, 3, 1) and nseg0.shape == (0,)
+    with pytest.raises(gms.GmsError, match="out of range"):
+        eng.predict("A", s["add"], None, None, [0], [9])
+    with pytest.raises(gms.GmsError, match="required"):
+        eng.predict("AD", s["add"], None, None, [0], [1])
+    bad = H.copy()
+    bad[3, 5] = 2
+    with pytest.raises(gms.GmsError, match="outside"):
+        eng.set_haplotypes(bad)
+    eng.close()
+    eng = gms.CrossVarEngine(0)
+    with pytest.raises(gms.GmsError, match="before"):
+        eng.set_haplotypes(H)
+    R = s["R"].copy()
+    R[3, 10] += 1e-3
+    with pytest.raises(gms.GmsError, match="symmetric"):
+        eng.set_recomb_matrix(R, s["chrom"])
+    eng.close()
+
+
+def test_invariances(gms):
+    """Size-independent properties of the path: sire/dam swap, HapA/HapB swap, effect scaling."""
+    s = synth(9, [300, 200], P=10, T=3)
+    sire = np.arange(10, dtype=np.int32)
+    dam = np.roll(sire, 3)
+    eng = gms.CrossVarEngine(0)
+    eng.set_genmap(s["cM"], s["m_c"])
+    eng.set_haplotypes(s["H"])
+    base, nseg = eng.predict("AD", s["add"], s["dom"], None, sire, dam)
+    swapped, nseg2 = eng.predict("AD", s["add"], s["dom"], None, dam, sire)
+    assert np.array_equal(nseg, nseg2) and np.allclose(base, swapped, rtol=1e-12, atol=0)
+    scaled, _ = eng.predict("AD", 3.0 * s["add"], -2.0 * s["dom"], None, sire, dam)
+    assert np.allclose(scaled[:, :, 0], 9.0 * base[:, :, 0], rtol=1e-12)
+    assert np.allclose(scaled[:, :, 1], 4.0 * base[:, :, 1], rtol=1e-12)
+    H2 = s["H"].copy()
+    H2[[0, 1]] = H2[[1, 0]]                  # swap the two haplotypes of parent 0
+    eng.set_haplotypes(H2)
+    flipped, nseg3 = eng.predict("AD", s["add"], s["dom"], None, sire, dam)
+    assert np.array_equal(nseg, nseg3) and np.allclose(base, flipped, rtol=1e-11, atol=0)
+    eng.close()
+
+
+# ---------------------------------------------------------------- BASELINE.json full size
+def test_cassava_scale_against_blockwise_oracle(gms):
+    """configs[3]: 1000 parents, 33k SNPs / 18 chromosomes, 5 traits, AD.  A handful of crosses is
+    checked against the oracle evaluated chromosome by chromosome; the whole batch is checked through
+    invariants (self-cross rows = twice the gametic part, duplicate rows identical)."""
+    from genomicmateselectr_b200 import synth as S
+    d = S.make("cassava", N=2000)
+    eng = gms.CrossVarEngine(0)
+    eng.set_genmap(d["cM"], d["m_c"])
+    eng.set_haplotypes(d["H"])
+    out, nseg = eng.predict("AD", d["add"], d["dom"], None, d["sire"], d["dam"])
+    assert np.all(np.isfinite(out)) and np.all(nseg > 0)
+    assert np.all(out[:, :5, :] > 0)                       # variances are positive
+    pick = [0, 1, 1999]
+    offs = np.concatenate([[0], np.cumsum(d["m_c"])])
+    blocks, ranges = [], []
+    for c in range(len(d["m_c"])):
+        a, b = int(offs[c]), int(offs[c + 1])
+        cm = d["cM"][a:b]
+        blocks.append(O.recombfreq_to_ld_decay(O.genmap2recombfreq(cm, np.ones(b - a))))
+        ranges.append((a, b))
+    want, wseg = oracle_slab_blockwise("AD", d["H"], blocks, ranges, d["add"], d["dom"], None,
+                                       d["sire"][pick], d["dam"][pick])
+    assert np.array_equal(nseg[pick], wseg)
+    assert rel_err(out[pick], want) < TOL
+    eng.close()
