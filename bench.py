@@ -1,0 +1,333 @@
+#!/usr/bin/env python
+"""Benchmark of the cross-variance hot path (BASELINE.json metric):
+cross variance-covariance predictions/sec (A+AD, 5 traits) on synthetic cassava-scale data.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cassava]
+
+A step = one pass of the hot path (modelType AD: VarA + VarD for all 15 trait pairs + Nsegsnps) over
+the whole batch of crosses.  N > 1: launched by torchrun, one rank per GPU, crosses sharded by rank
+(weak scaling: --crosses-per-gpu fixed), LD-decay tiles and haplotypes replicated, no data-path
+collective; the per-rank slabs are gathered to rank 0 in the e2e leg only.
+
+  value     crosses/s with inputs resident in HBM (gms_compute only), CUDA events, max over ranks
+  e2e       the same through gms_predict with pinned HOST buffers (H2D + kernels + D2H [+ gather])
+  roofline  FP64 tensor (DMMA) roofline of the dominant kernel (per-cross dominance contraction)
+  cpu_baseline  the oracle's C restatement of the reference algorithm on the host cores (rank 0)
+--impl reference times that CPU restatement alone (the reference is R; R is not installed here).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "cross variance-covariance predictions/sec (A+AD, 5 traits)"
+UNIT = "crosses/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cassava", choices=["cassava", "large", "mini"])
+    ap.add_argument("--crosses-per-gpu", type=int, default=None, help="default: the workload's N on every GPU")
+    ap.add_argument("--model", default="AD", choices=["A", "AD", "DirDom"])
+    ap.add_argument("--cpu-sample", type=int, default=2, help="crosses per CPU-baseline step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+# ----------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.idx)], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, pw, reasons = [], [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); pw.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def measured_peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        return {}
+
+
+def dgemm_peak_tflops(torch):
+    """FP64 ceiling on this box: cuBLAS DGEMM 8192^3, best of 5 (MEASURED_PEAKS.json has no FP64 figure)."""
+    a = torch.randn(8192, 8192, dtype=torch.float64, device="cuda")
+    b = torch.randn(8192, 8192, dtype=torch.float64, device="cuda")
+    for _ in range(2):
+        a @ b
+    torch.cuda.synchronize()
+    best = 1e30
+    for _ in range(5):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        a @ b
+        e1.record()
+        torch.cuda.synchronize()
+        best = min(best, e0.elapsed_time(e1))
+    del a, b
+    torch.cuda.empty_cache()
+    return 2.0 * 8192 ** 3 / best / 1e9
+
+
+# ----------------------------------------------------------------------------------------------
+def cpu_reference_run(d, model, sample, steps, warmup, nthreads=0):
+    """Time the oracle's C restatement of the reference algorithm (dense D per cross, one quadratic
+    form per trait pair) on the host cores: `sample` crosses per step, all threads inside a cross."""
+    from oracle import crossvar_ref as CR
+    from oracle import predcrossvar_oracle as O
+    offs = np.concatenate([[0], np.cumsum(d["m_c"])])
+    blocks = []
+    for c in range(len(d["m_c"])):
+        cm = d["cM"][offs[c]:offs[c + 1]]
+        blocks.append(O.recombfreq_to_ld_decay(O.genmap2recombfreq(cm, np.ones(cm.size))))
+    prob = CR.RefProblem(d["H"], d["add"], d["dom"] if model != "A" else None, blocks=blocks)
+    cores = nthreads or CR.max_threads()
+    rng = np.random.default_rng(12345)
+    times, nsegs = [], []
+    for it in range(warmup + steps):
+        pick = rng.integers(0, d["N"], sample)
+        t0 = time.perf_counter()
+        for x in pick:
+            _, nseg = prob.one_cross(int(d["sire"][x]), int(d["dam"][x]), "AD" if model != "A" else "A", cores)
+            nsegs.append(nseg)
+        dt = time.perf_counter() - t0
+        if it >= warmup:
+            times.append(dt)
+    total = float(np.sum(times))
+    return {"value": sample * steps / total, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{sample} random crosses per step x {steps} steps of the same workload "
+                      f"(mean Nsegsnps {int(np.mean(nsegs))}); oracle/crossvar_ref.c = the reference's algorithm "
+                      f"(dense m_seg^2 cross LD matrix, one quadratic form per trait pair) restated in C+OpenMP; "
+                      f"R itself is not installed",
+            "ms_per_step": 1e3 * total / steps}
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    from genomicmateselectr_b200 import synth
+    cfg = synth.CONFIGS[args.workload]
+    n_per = args.crosses_per_gpu or cfg["N"]
+    T = cfg["T"]
+    config = {"workload": f"synthetic {args.workload}-scale: {cfg['P']} phased parents, {sum(cfg['m_c'])} SNPs / "
+                          f"{len(cfg['m_c'])} chromosomes, {T} traits, {n_per} crosses per GPU, modelType {args.model}",
+              "model_type": args.model, "crosses_per_gpu": n_per, "parents": cfg["P"], "snps": int(sum(cfg["m_c"])),
+              "chromosomes": len(cfg["m_c"]), "traits": T, "sharding": "by cross, tiles+haplotypes replicated",
+              "l2_policy": "inputs larger than L2 (RoR tile image 283 MB at cassava scale, re-streamed every step)"}
+
+    # ------------------------------------------------------------------ reference arm (CPU)
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        d = synth.make(args.workload, N=min(cfg["N"], 50_000))
+        r = cpu_reference_run(d, args.model, args.cpu_sample, args.steps, args.warmup)
+        line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
+                "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+                "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        print(json.dumps(line))
+        return 0
+
+    # ------------------------------------------------------------------ our arm (GPU)
+    import torch
+    import torch.distributed as dist
+    from genomicmateselectr_b200 import CrossVarEngine
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the engine has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    n_total = n_per * world
+    d = synth.make(args.workload, N=n_total)
+    lo, hi = rank * n_per, (rank + 1) * n_per
+    sire, dam = d["sire"][lo:hi].copy(), d["dam"][lo:hi].copy()
+    dom = d["dom"] if args.model != "A" else None
+    asub = (d["add"] + d["dom"] * 0.1) if args.model == "DirDom" else None
+
+    eng = CrossVarEngine(local_rank)
+    stream = torch.cuda.current_stream()
+    eng.set_stream(stream.cuda_stream)
+    t0 = time.perf_counter()
+    eng.set_genmap(d["cM"], d["m_c"])
+    eng.set_haplotypes(d["H"])
+    torch.cuda.synchronize()
+    setup_s = time.perf_counter() - t0
+
+    fp64_peak = dgemm_peak_tflops(torch)
+
+    # ---- value: device-resident inputs, kernels only
+    eng.stage(args.model, d["add"], dom, asub, sire, dam)
+    for _ in range(args.warmup):
+        eng.compute(sync=True)
+    kernel_ms, stage_ms = [], []
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    launches = 0
+    for _ in range(args.steps):
+        eng.compute(sync=False)
+    e1.record(stream)
+    barrier()
+    ms = max_over_ranks(e0.elapsed_time(e1))
+    clocks = sampler.stop()
+    st = eng.stats()
+    launches = st["last_launches"] * args.steps
+    # dominant-kernel duration: CUDA events recorded around the launch on the same stream (inside the
+    # library); averaged over separate, synchronised steps so that every launch is read back
+    for _ in range(args.steps):
+        eng.compute(sync=True)
+        s = eng.stats()
+        kernel_ms.append(s["last_ms_cross_kernel"])
+        stage_ms.append((s["last_ms_parent_stage"], s["last_ms_cross_stage"], s["last_ms_assemble"], s["last_ms_total"]))
+    value = n_total * args.steps / (ms * 1e-3)
+
+    # ---- e2e: gms_predict with pinned host buffers, H2D and D2H inside the timed region
+    npairs, ncomp = T * (T + 1) // 2, {"A": 1, "AD": 2, "DirDom": 3}[args.model]
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+    add_p = pin(np.asfortranarray(d["add"]).T)           # m x T column-major == (T, m) C-order
+    dom_p = pin(np.asfortranarray(dom).T) if dom is not None else None
+    asub_p = pin(np.asfortranarray(asub).T) if asub is not None else None
+    sire_p, dam_p = pin(sire), pin(dam)
+    out_p = torch.empty((n_per, npairs, ncomp), dtype=torch.float64).pin_memory()
+    nseg_p = torch.empty(n_per, dtype=torch.int32).pin_memory()
+    gather = [torch.empty((n_per, npairs, ncomp), dtype=torch.float64, device="cuda") for _ in range(world)] \
+        if (world > 1 and rank == 0) else None
+    f = lambda t: None if t is None else t.numpy().T      # back to an F-ordered (m, T) view of the pinned memory
+
+    def e2e_step():
+        o, n = eng.predict(args.model, f(add_p), f(dom_p), f(asub_p), sire_p.numpy(), dam_p.numpy(),
+                           out=out_p.numpy(), nseg=nseg_p.numpy())
+        if world > 1:        # the "final gather of results" of the north star
+            dist.gather(out_p.cuda(non_blocking=True), gather, dst=0)
+        return float(o[0, 0, 0])
+
+    for _ in range(min(2, args.warmup)):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_step()
+    barrier()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    h2d = sum(t.numel() * t.element_size() for t in (add_p, dom_p, asub_p, sire_p, dam_p) if t is not None) \
+        + 2 * n_per * 4 + 4 * int(st["last_parents_used"])      # + sire/dam table slots + parent list
+    d2h = out_p.numel() * 8 + nseg_p.numel() * 4
+    e2e = {"value": n_total * args.steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+           "d2h_bytes_per_step": int(d2h), "ms_per_step": 1e3 * e2e_s / args.steps,
+           "api": "gms_predict (C ABI) via CrossVarEngine.predict, pinned host buffers"}
+
+    # ---- roofline of the dominant kernel (per-cross dominance contraction, FP64 DMMA)
+    k_ms = float(np.mean(kernel_ms)) if kernel_ms else 0.0
+    alg_flops = 2.0 * T * st["S2"] * n_per                  # SURVEY 8d dense count for the cross term, per launch
+    exec_flops = st["last_flops_cross"]
+    roof = None
+    if args.model != "A" and k_ms > 0:
+        achieved = alg_flops / (k_ms * 1e-3) / 1e12
+        roof = {"bound": "tensor", "kernel": "contract_kernel<MASK_XI> (FP64 mma.sync DMMA, cp.async.bulk staged)",
+                "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s", "frac": achieved / fp64_peak,
+                "traffic": None,
+                "peak_source": "cuBLAS DGEMM 8192^3 measured in this run (MEASURED_PEAKS.json has no FP64 figure); "
+                               "DMMA pipe probe tools/dmma_probe: 37.2 TFLOP/s; nominal 37-40",
+                "algorithmic_flops_per_launch": alg_flops, "executed_flops_per_launch": exec_flops,
+                "executed_tflops": exec_flops / (k_ms * 1e-3) / 1e12,
+                "executed_frac_of_peak": exec_flops / (k_ms * 1e-3) / 1e12 / fp64_peak,
+                "note": "algorithmic = dense 2*T*S2 per cross (no symmetry credit); the kernel executes only the lower "
+                        "block triangle of the symmetric RoR blocks (x0.585 incl. padding), so frac can exceed 1",
+                "kernel_ms": k_ms, "kernel_share_of_step": k_ms / float(np.mean([s[3] for s in stage_ms]))}
+
+    if rank == 0:
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            cpu = cpu_reference_run(d, args.model, args.cpu_sample, 3, 1)
+            cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        pk = measured_peaks()
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config, "clocks": clocks,
+                "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu,
+                "stages_ms": {"parent_tables": float(np.mean([s[0] for s in stage_ms])),
+                              "cross_term": float(np.mean([s[1] for s in stage_ms])),
+                              "assemble_nseg": float(np.mean([s[2] for s in stage_ms]))},
+                "setup_s": setup_s, "hbm_tile_bytes": int(st["tile_bytes"]),
+                "measured_peaks": {"hbm_gbs": pk.get("hbm_gbs"), "fp64_dgemm_tflops": fp64_peak}}
+        print(json.dumps(line))
+    eng.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())
