@@ -215,7 +215,8 @@ def main():
     asub = (d["add"] + d["dom"] * 0.1) if args.model == "DirDom" else None
 
     eng = CrossVarEngine(local_rank)
-    stream = torch.cuda.current_stream()
+    stream = torch.cuda.Stream()          # a real (non-default) stream: handle 0 would mean "engine's own stream"
+    torch.cuda.set_stream(stream)
     eng.set_stream(stream.cuda_stream)
     t0 = time.perf_counter()
     eng.set_genmap(d["cM"], d["m_c"])

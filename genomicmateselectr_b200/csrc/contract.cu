@@ -154,14 +154,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) contract_kernel(const ContractPar
                     const unsigned c0 = __shfl_sync(0xffffffffu, ng0, srcl), c1 = __shfl_sync(0xffffffffu, ng1, srcl);
                     unsigned nz = (rel >> 5) ? a1 : a0, ng = (rel >> 5) ? c1 : c0;
                     if (colu[b] < 0) nz = 0u;
-                    const double* ecol = ebase + (long long)colt[b] * p.mp_total;
+                    // integer-only select / sign flip: the FP64 pipe belongs to the DMMA warps
+                    const unsigned long long* ecol =
+                        reinterpret_cast<const unsigned long long*>(ebase + (long long)colt[b] * p.mp_total);
+                    unsigned long long* bq = reinterpret_cast<unsigned long long*>(bdst);
 #pragma unroll
                     for (int q = 0; q < 8; ++q) {
                         const int k = 4 * q + tig;
-                        double e = 0.0;
+                        unsigned long long e = 0ull;
                         if ((nz >> k) & 1u) e = __ldg(ecol + k);
-                        if ((ng >> k) & 1u) e = -e;
-                        bdst[(q * 10 + b) * 32] = e;
+                        e ^= (unsigned long long)((ng >> k) & 1u) << 63;
+                        bq[(q * 10 + b) * 32] = e;
                     }
                 }
                 __syncwarp();
@@ -225,10 +228,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) contract_kernel(const ContractPar
 #pragma unroll
                         for (int h = 0; h < 2; ++h) {
                             const int bit = 16 * mi + 8 * h + g;
-                            double v = acc[mi][ni][2 * h + j];
-                            if (!((nz >> bit) & 1u)) v = 0.0;
-                            if ((ng >> bit) & 1u) v = -v;
-                            acc[mi][ni][2 * h + j] = v;
+                            long long v = __double_as_longlong(acc[mi][ni][2 * h + j]);
+                            if (!((nz >> bit) & 1u)) v = 0ll;
+                            v ^= (long long)((ng >> bit) & 1u) << 63;
+                            acc[mi][ni][2 * h + j] = __longlong_as_double(v);
                         }
                 }
             }
