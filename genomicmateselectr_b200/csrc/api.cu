@@ -142,7 +142,11 @@ int build_worklist(gms_handle* h) {
         const int nI = h->chrom[c].mp / BM;
         for (int I = 0; I < nI; ++I) {
             h->rowtiles.push_back(RowTile{c, I});
-            h->lower_elems += (double)BM * BM * (I + 1);
+            // what contract_kernel really issues: 16-row blocks with a real row x k-chunks with a real k
+            const int rows = h->chrom[c].m - BM * I;
+            const int nact = rows >= BM ? 8 : (rows + 15) / 16;
+            const int nkc = std::min(4 * (I + 1), (h->chrom[c].m + BK - 1) / BK);
+            h->lower_elems += 16.0 * nact * BK * nkc;
         }
         h->S2 += (long long)h->chrom[c].m * h->chrom[c].m;
     }

@@ -80,21 +80,109 @@ __device__ __forceinline__ void unit_mask(const ContractParams& p, int pa, int p
     }
 }
 
+// non-blocking probe of an mbarrier phase (result consumed several hundred cycles later)
+__device__ __forceinline__ unsigned mbar_try(unsigned bar, unsigned parity) {
+    unsigned ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok;
+}
+
+struct Frag {
+    double2 a0, a1;
+    double b[5];
+};
+
+// One k4-step worth of operands for this warp: two 16-row A blocks (mb = wm and wm + 4) and five
+// 8-column B blocks. A0/A1: whether the block has any real (non-padding) row in this row-tile.
+template <bool A0, bool A1>
+__device__ __forceinline__ void load_frag(Frag& f, const double* a, const double* b, int q) {
+    if (A0) f.a0 = *reinterpret_cast<const double2*>(a + (q * 8) * 64);
+    if (A1) f.a1 = *reinterpret_cast<const double2*>(a + (q * 8 + 4) * 64);
+#pragma unroll
+    for (int ni = 0; ni < 5; ++ni) f.b[ni] = b[(q * 10 + ni) * 32];
+}
+template <bool A0, bool A1>
+__device__ __forceinline__ void mma_step(double (&acc)[2][5][4], const Frag& f) {
+#pragma unroll
+    for (int ni = 0; ni < 5; ++ni) {
+        if (A0) dmma_16x8x4(acc[0][ni], f.a0.x, f.a0.y, f.b[ni]);
+        if (A1) dmma_16x8x4(acc[1][ni], f.a1.x, f.a1.y, f.b[ni]);
+    }
+}
+
+// Main loop of one row-tile for one consumer warp, software-pipelined across k4-steps AND across
+// pipeline stages: the next stage's barrier is probed one whole stage early and its first operands
+// are fetched before the last DMMAs of the current stage issue, so the FP64 tensor pipe never
+// drains at a stage boundary.
+template <bool A0, bool A1>
+__device__ __forceinline__ void rowtile_mainloop(double (&acc)[2][5][4], const double* As, const double* Bs,
+                                                 unsigned full0, unsigned empty0, int S, int nkc, unsigned& it,
+                                                 int wm, int wn, int lane) {
+    unsigned slot = it % S, ph = (it / S) & 1u;
+    mbar_wait(full0 + 8 * slot, ph);
+    const int aoff = (wm * 32 + lane) * 2, boff = (5 * wn) * 32 + lane;
+    Frag cur, nxt;
+    load_frag<A0, A1>(cur, As + (size_t)slot * CHUNK + aoff, Bs + (size_t)slot * BCHUNK + boff, 0);
+    for (int kc = 0; kc < nkc; ++kc) {
+        const unsigned nslot = (it + 1) % S, nph = ((it + 1) / S) & 1u;
+        const bool has_next = kc + 1 < nkc;
+        unsigned ok = 1u;
+        if (has_next) ok = mbar_try(full0 + 8 * nslot, nph);
+        const double* a = As + (size_t)slot * CHUNK + aoff;
+        const double* b = Bs + (size_t)slot * BCHUNK + boff;
+#pragma unroll
+        for (int q = 0; q < 7; ++q) {
+            load_frag<A0, A1>(nxt, a, b, q + 1);
+            mma_step<A0, A1>(acc, cur);
+            cur = nxt;
+        }
+        if (has_next) {
+            if (!ok) mbar_wait(full0 + 8 * nslot, nph);
+            load_frag<A0, A1>(nxt, As + (size_t)nslot * CHUNK + aoff, Bs + (size_t)nslot * BCHUNK + boff, 0);
+        }
+        mma_step<A0, A1>(acc, cur);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(empty0 + 8 * slot);   // every read of this slot has completed
+        cur = nxt;
+        slot = nslot;
+        ++it;
+    }
+}
+
+// real (non-padding) extent of a row-tile: 16-row blocks with a real row, and k-chunks with a real k
+__device__ __forceinline__ int rowtile_nact(const ChromDesc& cd, int I) {
+    const int rows = cd.m - BM * I;
+    return rows >= BM ? 8 : (rows + 15) >> 4;
+}
+__device__ __forceinline__ int rowtile_nkc(const ChromDesc& cd, int I) {
+    const int full = 4 * (I + 1), real = (cd.m + BK - 1) / BK;
+    return full < real ? full : real;
+}
+
 __global__ void __launch_bounds__(NTHREADS, 1) contract_kernel(const ContractParams p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int S = p.stages;
     const int T = p.T;
+    const int NU = p.NU;
     double* As = reinterpret_cast<double*>(smem_raw);
     double* Bs = As + (size_t)S * CHUNK;
     double* Zacc = Bs + (size_t)S * BCHUNK;                       // [8 warps][40][T]
     unsigned long long* bars = reinterpret_cast<unsigned long long*>(Zacc + MATH_WARPS * 40 * T);
+    unsigned* emask = reinterpret_cast<unsigned*>(bars + 2 * S);  // [2 buffers][NU][4 words][nz, ng]
     const unsigned full0 = smem_u32(bars);
     const unsigned empty0 = smem_u32(bars + S);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const int g = lane >> 2, tig = lane & 3;
-    const int NU = p.NU;
     const long long u0 = (long long)blockIdx.x * NU;
     const int split = blockIdx.y;
     const int rt_begin = p.split_begin[split], rt_end = p.split_begin[split + 1];
@@ -131,7 +219,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) contract_kernel(const ContractPar
         for (int rt = rt_begin; rt < rt_end; ++rt) {
             const RowTile tile = p.rowtiles[rt];
             const ChromDesc cd = p.chrom[tile.c];
-            const int nkc = 4 * (tile.I + 1);
+            const int nkc = rowtile_nkc(cd, tile.I);
             const double* src = p.tiles + cd.tile_off + chunks_before_rowtile(tile.I) * CHUNK;
             for (int kc = 0; kc < nkc; ++kc, ++it) {
                 const unsigned slot = it % S, ph = (it / S) & 1u;
@@ -139,6 +227,21 @@ __global__ void __launch_bounds__(NTHREADS, 1) contract_kernel(const ContractPar
                 if (pw == 0 && lane == 0) {
                     mbar_arrive_expect_tx(full0 + 8 * slot, CHUNK * 8);
                     bulk_g2s(smem_u32(As + (size_t)slot * CHUNK), src + (size_t)kc * CHUNK, CHUNK * 8, full0 + 8 * slot);
+                }
+                if (kc == 0) {
+                    // masks of this row-tile's 128 rows for the consumers' epilogue (published by the
+                    // arrive on this stage's full barrier; double-buffered by row-tile parity)
+                    unsigned* em = emask + ((rt - rt_begin) & 1) * (NU * 8);
+                    const long long wbase = (cd.pad_off >> 5) + 4 * tile.I;
+                    for (int idx = pw * 32 + lane; idx < NU * 4; idx += PROD_WARPS * 32) {
+                        const int u = idx >> 2, w4 = idx & 3;
+                        int pa = -1, pb = 0;
+                        if (u0 + u < p.n_units) { pa = p.unit_a[u0 + u]; pb = (p.mode == MASK_XI) ? p.unit_b[u0 + u] : 0; }
+                        unsigned nz, ng;
+                        unit_mask(p, pa, pb, wbase + w4, nz, ng);
+                        em[idx * 2] = nz;
+                        em[idx * 2 + 1] = ng;
+                    }
                 }
                 const long long w = (cd.pad_off >> 5) + kc;
                 unsigned nz0, ng0, nz1, ng1;
@@ -173,13 +276,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) contract_kernel(const ContractPar
         }
     } else {
         // ------------------------------------------------------------------ consumers
+        // warp (wm, wn): rows of the 16-row blocks mb = wm and wm + 4 (interleaved so that the padding
+        // blocks of a chromosome's last row-tile are spread over the 4 SM sub-partitions), columns 40 wn ..
         const int wm = warp & 3, wn = warp >> 2;
         double acc[2][5][4];
         unsigned it = 0;
         for (int rt = rt_begin; rt < rt_end; ++rt) {
             const RowTile tile = p.rowtiles[rt];
             const ChromDesc cd = p.chrom[tile.c];
-            const int nkc = 4 * (tile.I + 1);
+            const int nkc = rowtile_nkc(cd, tile.I);
+            const int nact = rowtile_nact(cd, tile.I);
+            const bool act0 = wm < nact, act1 = wm + 4 < nact;
 #pragma unroll
             for (int mi = 0; mi < 2; ++mi)
 #pragma unroll
@@ -187,67 +294,62 @@ __global__ void __launch_bounds__(NTHREADS, 1) contract_kernel(const ContractPar
 #pragma unroll
                     for (int r = 0; r < 4; ++r) acc[mi][ni][r] = 0.0;
 
-            for (int kc = 0; kc < nkc; ++kc, ++it) {
-                const unsigned slot = it % S, ph = (it / S) & 1u;
-                mbar_wait(full0 + 8 * slot, ph);
-                const double* a = As + (size_t)slot * CHUNK + ((2 * wm) * 32 + lane) * 2;
-                const double* b = Bs + (size_t)slot * BCHUNK + (5 * wn) * 32 + lane;
-#pragma unroll
-                for (int q = 0; q < 8; ++q) {
-                    const double2 a0 = *reinterpret_cast<const double2*>(a + (q * 8) * 64);
-                    const double2 a1 = *reinterpret_cast<const double2*>(a + (q * 8 + 1) * 64);
-                    double bf[5];
-#pragma unroll
-                    for (int ni = 0; ni < 5; ++ni) bf[ni] = b[(q * 10 + ni) * 32];
-#pragma unroll
-                    for (int ni = 0; ni < 5; ++ni) {
-                        dmma_16x8x4(acc[0][ni], a0.x, a0.y, bf[ni]);
-                        dmma_16x8x4(acc[1][ni], a1.x, a1.y, bf[ni]);
-                    }
+            if (act1) {
+                rowtile_mainloop<true, true>(acc, As, Bs, full0, empty0, S, nkc, it, wm, wn, lane);
+            } else if (act0) {
+                rowtile_mainloop<true, false>(acc, As, Bs, full0, empty0, S, nkc, it, wm, wn, lane);
+            } else {
+                for (int kc = 0; kc < nkc; ++kc, ++it) {      // nothing to compute: keep the ring moving
+                    const unsigned slot = it % S, ph = (it / S) & 1u;
+                    mbar_wait(full0 + 8 * slot, ph);
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(empty0 + 8 * slot);
                 }
-                __syncwarp();
-                if (lane == 0) mbar_arrive(empty0 + 8 * slot);
+                continue;
             }
 
             // ---- row-tile epilogue: Zacc[col][t] += sum_rows e_t[row] * mask_u(col)[row] * acc[row][col]
-            const long long wrow = (cd.pad_off >> 5) + 4 * tile.I + wm;   // haplotype word of this warp's 32 rows
+            const unsigned* em = emask + ((rt - rt_begin) & 1) * (NU * 8);
+            const int bit0 = 16 * (wm & 1) + g;            // row 16 (wm + 4 mi) + 8 h + g -> word (wm>>1) + 2 mi, bit bit0 + 8 h
 #pragma unroll
             for (int ni = 0; ni < 5; ++ni) {
 #pragma unroll
                 for (int j = 0; j < 2; ++j) {
                     const int n = 40 * wn + 8 * ni + 2 * tig + j;
-                    int pa = -1, pb = 0;
-                    if (n < NU * T) {
-                        const long long u = u0 + n / T;
-                        if (u < p.n_units) { pa = p.unit_a[u]; pb = (p.mode == MASK_XI) ? p.unit_b[u] : 0; }
-                    }
-                    unsigned nz, ng;
-                    unit_mask(p, pa, pb, wrow, nz, ng);
+                    const bool live = n < NU * T;
+                    const int u = live ? n / T : 0;
 #pragma unroll
-                    for (int mi = 0; mi < 2; ++mi)
+                    for (int mi = 0; mi < 2; ++mi) {
+                        const uint2 mk = *reinterpret_cast<const uint2*>(em + (u * 4 + (wm >> 1) + 2 * mi) * 2);
+                        const unsigned nz = live ? mk.x : 0u, ng = mk.y;
 #pragma unroll
                         for (int h = 0; h < 2; ++h) {
-                            const int bit = 16 * mi + 8 * h + g;
+                            const int bit = bit0 + 8 * h;
                             long long v = __double_as_longlong(acc[mi][ni][2 * h + j]);
                             if (!((nz >> bit) & 1u)) v = 0ll;
                             v ^= (long long)((ng >> bit) & 1u) << 63;
                             acc[mi][ni][2 * h + j] = __longlong_as_double(v);
                         }
+                    }
                 }
             }
-            const double* erow = p.emat + cd.pad_off + BM * tile.I + 32 * wm + g;
+            const double* erow = p.emat + cd.pad_off + BM * tile.I + 16 * wm + g;   // + 8 h + 64 mi
             double* zw = Zacc + (size_t)(warp * 40) * T;
+            double e00 = __ldg(erow), e01 = __ldg(erow + 8), e10 = __ldg(erow + 64), e11 = __ldg(erow + 72);
             for (int t = 0; t < T; ++t) {
-                const double* et = erow + (long long)t * p.mp_total;
-                const double e00 = __ldg(et), e01 = __ldg(et + 8), e10 = __ldg(et + 16), e11 = __ldg(et + 24);
+                const double c00 = e00, c01 = e01, c10 = e10, c11 = e11;
+                if (t + 1 < T) {                               // prefetch the next trait's effects
+                    const double* et = erow + (long long)(t + 1) * p.mp_total;
+                    e00 = __ldg(et); e01 = __ldg(et + 8); e10 = __ldg(et + 64); e11 = __ldg(et + 72);
+                }
 #pragma unroll
                 for (int ni = 0; ni < 5; ++ni) {
 #pragma unroll
                     for (int j = 0; j < 2; ++j) {
-                        double s = e00 * acc[0][ni][j];
-                        s = fma(e01, acc[0][ni][2 + j], s);
-                        s = fma(e10, acc[1][ni][j], s);
-                        s = fma(e11, acc[1][ni][2 + j], s);
+                        double s = c00 * acc[0][ni][j];
+                        s = fma(c01, acc[0][ni][2 + j], s);
+                        s = fma(c10, acc[1][ni][j], s);
+                        s = fma(c11, acc[1][ni][2 + j], s);
                         s += __shfl_xor_sync(0xffffffffu, s, 4);
                         s += __shfl_xor_sync(0xffffffffu, s, 8);
                         s += __shfl_xor_sync(0xffffffffu, s, 16);
@@ -276,7 +378,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) contract_kernel(const ContractPar
 }
 
 size_t contract_smem_bytes(int T, int stages) {
-    return (size_t)stages * (CHUNK + BCHUNK) * 8 + (size_t)MATH_WARPS * 40 * T * 8 + (size_t)2 * stages * 8;
+    const int NU = BN / T;
+    return (size_t)stages * (CHUNK + BCHUNK) * 8 + (size_t)MATH_WARPS * 40 * T * 8 + (size_t)2 * stages * 8 +
+           (size_t)2 * NU * 8 * 4;
 }
 
 int contract_pick_stages(int T, size_t smem_limit) {
