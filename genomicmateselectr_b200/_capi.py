@@ -44,6 +44,7 @@ _SIGS = {
     "gms_set_haplotypes_i32cm": (C.c_int, [_P, C.c_int64, C.c_int64, _P]),
     "gms_set_haplotypes_u8rm": (C.c_int, [_P, C.c_int64, C.c_int64, _P]),
     "gms_set_chromosome_shard": (C.c_int, [_P, C.c_int, C.c_int]),
+    "gms_set_mode": (C.c_int, [_P, C.c_int]),
     "gms_trait_pairs": (C.c_int, [C.c_int, _P, _P]),
     "gms_predict": (C.c_int, [_P, C.c_int, C.c_int, _P, _P, _P, C.c_int64, _P, _P, _P, _P]),
     "gms_stage_inputs": (C.c_int, [_P, C.c_int, C.c_int, _P, _P, _P, C.c_int64, _P, _P]),

@@ -78,6 +78,14 @@ struct gms_handle {
     Plan plan_par, plan_x;
     int stages = 0;
 
+    // map-structured fast path
+    int mode = GMS_MODE_DENSE;
+    bool scan_ok = false;
+    DevBuf<double> scan_ab;            // [4][mp]: a(0.02), b(0.02), a(0.04), b(0.04)
+    DevBuf<double> S_add, S_dom, S_asub;
+    DevBuf<int> split_scan_par_d, split_scan_x_d;
+    std::vector<int> scan_split_par, scan_split_x;
+
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     gms_stats st{};
 };
@@ -225,6 +233,51 @@ int run_contract(gms_handle* h, const double* tiles, const double* emat, int mod
     return GMS_OK;
 }
 
+// chromosome ranges for the scan path: enough (unit x range) threads to fill the GPU, bounded partial buffer
+void make_scan_split(const gms_handle* h, long long n_units, std::vector<int>& sb) {
+    const int nchr = h->c_end - h->c_begin;
+    long long want = n_units > 0 ? (600000 + n_units - 1) / n_units : 1;
+    const long long cap = std::max<long long>(1, (1LL << 30) / std::max<long long>(1, n_units * h->T * h->T * 8));
+    int ns = (int)std::max<long long>(1, std::min<long long>(std::min<long long>(want, cap), nchr));
+    sb.assign(ns + 1, h->c_begin);
+    double total = 0, acc = 0;
+    for (int c = h->c_begin; c < h->c_end; ++c) total += h->chrom[c].m;
+    int sp = 1;
+    for (int c = h->c_begin; c < h->c_end && sp < ns; ++c) {
+        acc += h->chrom[c].m;
+        while (sp < ns && acc >= total * sp / ns && (h->c_end - (c + 1)) >= (ns - sp)) sb[sp++] = c + 1;
+    }
+    for (; sp < ns; ++sp) sb[sp] = std::max(sb[sp - 1], h->c_end - (ns - sp));
+    sb[ns] = h->c_end;
+    for (int i = 1; i <= ns; ++i) sb[i] = std::max(sb[i], sb[i - 1]);
+}
+
+int run_scan(gms_handle* h, const double* S, int mode, const int* ua, const int* ub, long long n_units,
+             const std::vector<int>& sb, const int* split_d, double* Xout, cudaEvent_t e_before = nullptr,
+             cudaEvent_t e_after = nullptr) {
+    if (n_units == 0) return GMS_OK;
+    ScanParams p{};
+    p.chrom = h->chrom_d.p;
+    p.split_begin = split_d;
+    p.S = S;
+    p.planeA = h->planeA.p;
+    p.planeB = h->planeB.p;
+    p.wpp = h->wpp;
+    p.unit_a = ua;
+    p.unit_b = ub;
+    p.n_units = n_units;
+    p.T = h->T;
+    p.mode = mode;
+    p.Xpart = h->Z.p;
+    const int ns = (int)sb.size() - 1;
+    if (e_before) CU(cudaEventRecord(e_before, h->stream));
+    CU(launch_scan(p, ns, h->stream));
+    if (e_after) CU(cudaEventRecord(e_after, h->stream));
+    CU(launch_finalize_sym(h->Z.p, ns, n_units, h->T, Xout, h->stream, false));
+    h->st.last_launches += 2;
+    return GMS_OK;
+}
+
 int upload_effects(gms_handle* h, const double* host, DevBuf<double>& emat) {
     const size_t n = (size_t)h->m * h->T;
     CU(h->eff_raw.ensure(n));
@@ -292,7 +345,8 @@ void gms_destroy(gms_handle* h) {
     h->dam_slot_d.release(); h->plist_d.release(); h->pair1_d.release(); h->pair2_d.release();
     h->split_par_d.release(); h->split_x_d.release(); h->flag_d.release(); h->Z.release(); h->QA.release();
     h->PD.release(); h->QB.release(); h->X.release(); h->out_d.release(); h->nseg_d.release();
-    h->gebv_d.release(); h->mean_d.release();
+    h->gebv_d.release(); h->mean_d.release(); h->scan_ab.release(); h->S_add.release(); h->S_dom.release();
+    h->S_asub.release(); h->split_scan_par_d.release(); h->split_scan_x_d.release();
     for (auto& ev : h->ev) if (ev) cudaEventDestroy(ev);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     delete h;
@@ -320,8 +374,42 @@ int gms_set_genmap(gms_handle* h, int C, const int64_t* m_c, const double* cM) {
         CU(launch_build_tiles_from_map(cm_d.p + h->chrom[c].snp_off, h->chrom[c], h->R.p, h->R2.p, h->stream));
     CU(cudaStreamSynchronize(h->stream));
     cm_d.release();
+    // map-structured fast path: a_j = exp(-c x_j), b_j = exp(c x_j) with x relative to the chromosome start;
+    // usable when positions are sorted within every chromosome and c * length stays far from overflow
+    h->scan_ok = true;
+    std::vector<double> ab((size_t)4 * h->mp_total, 0.0);
+    for (int c = 0; c < C && h->scan_ok; ++c) {
+        const ChromDesc& cd = h->chrom[c];
+        const double x0 = cM[cd.snp_off];
+        for (int j = 0; j < cd.m; ++j) {
+            const double x = cM[cd.snp_off + j];
+            if (j > 0 && x < cM[cd.snp_off + j - 1]) { h->scan_ok = false; break; }
+            const double d = x - x0;
+            if (4.0 * (d / 100.0) > 600.0) { h->scan_ok = false; break; }
+            const size_t pj = (size_t)cd.pad_off + j;
+            ab[0 * h->mp_total + pj] = exp(-2.0 * (d / 100.0));
+            ab[1 * h->mp_total + pj] = exp(2.0 * (d / 100.0));
+            ab[2 * h->mp_total + pj] = exp(-4.0 * (d / 100.0));
+            ab[3 * h->mp_total + pj] = exp(4.0 * (d / 100.0));
+        }
+    }
+    if (h->scan_ok) {
+        CU(h->scan_ab.ensure(ab.size()));
+        CU(cudaMemcpy(h->scan_ab.p, ab.data(), ab.size() * sizeof(double), cudaMemcpyHostToDevice));
+    }
+    h->mode = GMS_MODE_DENSE;
     h->have_tiles = true;
     return build_worklist(h);
+}
+
+int gms_set_mode(gms_handle* h, int mode) {
+    if (!h) return GMS_EINVAL;
+    if (mode != GMS_MODE_DENSE && mode != GMS_MODE_MAP_SCAN) return fail(h, GMS_EINVAL, "unknown mode");
+    if (mode == GMS_MODE_MAP_SCAN && !(h->have_tiles && h->scan_ok))
+        return fail(h, GMS_ESTATE, "the map-structured fast path needs gms_set_genmap() with positions sorted within every chromosome");
+    h->mode = mode;
+    h->staged = h->computed = false;
+    return GMS_OK;
 }
 
 int gms_set_recomb_blocks(gms_handle* h, int C, const int64_t* m_c, const double* const* blocks) {
@@ -352,6 +440,8 @@ int gms_set_recomb_blocks(gms_handle* h, int C, const int64_t* m_c, const double
         snprintf(buf, sizeof buf, "recombFreqMat block is not symmetric / finite (%d entries differ from their transpose)", asym);
         return fail(h, GMS_EINVAL, buf);
     }
+    h->scan_ok = false;
+    h->mode = GMS_MODE_DENSE;
     h->have_tiles = true;
     return build_worklist(h);
 }
@@ -479,6 +569,26 @@ int gms_stage_inputs(gms_handle* h, int model, int T, const double* add, const d
 
     // plans and workspaces
     const int NU = BN / T, TT = T * T;
+    if (h->mode == GMS_MODE_MAP_SCAN) {
+        const size_t sn = (size_t)h->mp_total * 3 * T;
+        const double* ab = h->scan_ab.p;
+        CU(h->S_add.ensure(sn));
+        CU(launch_scan_prepare(h->emat_add.p, ab, ab + h->mp_total, h->mp_total, T, h->S_add.p, h->stream));
+        if (model >= GMS_MODEL_AD) {
+            CU(h->S_dom.ensure(sn));
+            CU(launch_scan_prepare(h->emat_dom.p, ab + 2 * h->mp_total, ab + 3 * h->mp_total, h->mp_total, T, h->S_dom.p, h->stream));
+        }
+        if (model == GMS_MODEL_DIRDOM) {
+            CU(h->S_asub.ensure(sn));
+            CU(launch_scan_prepare(h->emat_asub.p, ab, ab + h->mp_total, h->mp_total, T, h->S_asub.p, h->stream));
+        }
+        make_scan_split(h, h->nP, h->scan_split_par);
+        make_scan_split(h, model >= GMS_MODEL_AD ? N : 0, h->scan_split_x);
+        CU(h->split_scan_par_d.ensure(h->scan_split_par.size()));
+        CU(h->split_scan_x_d.ensure(h->scan_split_x.size()));
+        CU(cudaMemcpyAsync(h->split_scan_par_d.p, h->scan_split_par.data(), sizeof(int) * h->scan_split_par.size(), cudaMemcpyHostToDevice, h->stream));
+        CU(cudaMemcpyAsync(h->split_scan_x_d.p, h->scan_split_x.data(), sizeof(int) * h->scan_split_x.size(), cudaMemcpyHostToDevice, h->stream));
+    }
     make_plan(h, h->nP, NU, h->plan_par);
     make_plan(h, model >= GMS_MODEL_AD ? N : 0, NU, h->plan_x);
     CU(h->split_par_d.ensure(h->plan_par.split_begin.size()));
@@ -487,8 +597,11 @@ int gms_stage_inputs(gms_handle* h, int model, int T, const double* add, const d
                        cudaMemcpyHostToDevice, h->stream));
     CU(cudaMemcpyAsync(h->split_x_d.p, h->plan_x.split_begin.data(), sizeof(int) * h->plan_x.split_begin.size(),
                        cudaMemcpyHostToDevice, h->stream));
-    const size_t zneed = std::max<size_t>((size_t)h->plan_par.nsplit * (size_t)h->nP * TT,
-                                          model >= GMS_MODEL_AD ? (size_t)h->plan_x.nsplit * (size_t)N * TT : (size_t)0);
+    size_t zneed = std::max<size_t>((size_t)h->plan_par.nsplit * (size_t)h->nP * TT,
+                                    model >= GMS_MODEL_AD ? (size_t)h->plan_x.nsplit * (size_t)N * TT : (size_t)0);
+    if (h->mode == GMS_MODE_MAP_SCAN)
+        zneed = std::max<size_t>((h->scan_split_par.size() - 1) * (size_t)h->nP * TT,
+                                 model >= GMS_MODEL_AD ? (h->scan_split_x.size() - 1) * (size_t)N * TT : (size_t)0);
     CU(h->Z.ensure(zneed));
     CU(h->QA.ensure((size_t)h->nP * TT));
     if (model >= GMS_MODEL_AD) { CU(h->PD.ensure((size_t)h->nP * TT)); CU(h->X.ensure((size_t)N * TT)); }
@@ -507,20 +620,36 @@ int gms_compute(gms_handle* h, int sync) {
     if (int rc = bind(h)) return rc;
     h->st.last_launches = 0;
     CU(cudaEventRecord(h->ev[0], h->stream));
-    // per-parent tables: Q_P = (a o delta_P)' R (a o delta_P), P_P = (d o het_P)' RoR (d o het_P)
-    if (int rc = run_contract(h, h->R.p, h->emat_add.p, MASK_DELTA, h->plist_d.p, nullptr, h->nP, h->plan_par,
-                              h->split_par_d.p, h->QA.p)) return rc;
-    if (h->model >= GMS_MODEL_AD)
-        if (int rc = run_contract(h, h->R2.p, h->emat_dom.p, MASK_HET, h->plist_d.p, nullptr, h->nP, h->plan_par,
-                                  h->split_par_d.p, h->PD.p)) return rc;
-    if (h->model == GMS_MODEL_DIRDOM)
-        if (int rc = run_contract(h, h->R.p, h->emat_asub.p, MASK_DELTA, h->plist_d.p, nullptr, h->nP, h->plan_par,
-                                  h->split_par_d.p, h->QB.p)) return rc;
-    CU(cudaEventRecord(h->ev[1], h->stream));
-    // per-cross dominance term X = (d o xi)' RoR (d o xi), xi = delta_sire o delta_dam
-    if (h->model >= GMS_MODEL_AD)
-        if (int rc = run_contract(h, h->R2.p, h->emat_dom.p, MASK_XI, h->sire_d.p, h->dam_d.p, h->N, h->plan_x,
-                                  h->split_x_d.p, h->X.p, h->ev[4], h->ev[5])) return rc;
+    if (h->mode == GMS_MODE_MAP_SCAN) {
+        // same tables through the prefix-sum recurrence (scan.cu)
+        if (int rc = run_scan(h, h->S_add.p, MASK_DELTA, h->plist_d.p, nullptr, h->nP, h->scan_split_par,
+                              h->split_scan_par_d.p, h->QA.p)) return rc;
+        if (h->model >= GMS_MODEL_AD)
+            if (int rc = run_scan(h, h->S_dom.p, MASK_HET, h->plist_d.p, nullptr, h->nP, h->scan_split_par,
+                                  h->split_scan_par_d.p, h->PD.p)) return rc;
+        if (h->model == GMS_MODEL_DIRDOM)
+            if (int rc = run_scan(h, h->S_asub.p, MASK_DELTA, h->plist_d.p, nullptr, h->nP, h->scan_split_par,
+                                  h->split_scan_par_d.p, h->QB.p)) return rc;
+        CU(cudaEventRecord(h->ev[1], h->stream));
+        if (h->model >= GMS_MODEL_AD)
+            if (int rc = run_scan(h, h->S_dom.p, MASK_XI, h->sire_d.p, h->dam_d.p, h->N, h->scan_split_x,
+                                  h->split_scan_x_d.p, h->X.p, h->ev[4], h->ev[5])) return rc;
+    } else {
+        // per-parent tables: Q_P = (a o delta_P)' R (a o delta_P), P_P = (d o het_P)' RoR (d o het_P)
+        if (int rc = run_contract(h, h->R.p, h->emat_add.p, MASK_DELTA, h->plist_d.p, nullptr, h->nP, h->plan_par,
+                                  h->split_par_d.p, h->QA.p)) return rc;
+        if (h->model >= GMS_MODEL_AD)
+            if (int rc = run_contract(h, h->R2.p, h->emat_dom.p, MASK_HET, h->plist_d.p, nullptr, h->nP, h->plan_par,
+                                      h->split_par_d.p, h->PD.p)) return rc;
+        if (h->model == GMS_MODEL_DIRDOM)
+            if (int rc = run_contract(h, h->R.p, h->emat_asub.p, MASK_DELTA, h->plist_d.p, nullptr, h->nP, h->plan_par,
+                                      h->split_par_d.p, h->QB.p)) return rc;
+        CU(cudaEventRecord(h->ev[1], h->stream));
+        // per-cross dominance term X = (d o xi)' RoR (d o xi), xi = delta_sire o delta_dam
+        if (h->model >= GMS_MODEL_AD)
+            if (int rc = run_contract(h, h->R2.p, h->emat_dom.p, MASK_XI, h->sire_d.p, h->dam_d.p, h->N, h->plan_x,
+                                      h->split_x_d.p, h->X.p, h->ev[4], h->ev[5])) return rc;
+    }
     CU(cudaEventRecord(h->ev[2], h->stream));
     const long long w0 = h->chrom[h->c_begin].pad_off / 32;
     const long long w1 = ((long long)h->chrom[h->c_end - 1].pad_off + h->chrom[h->c_end - 1].mp) / 32;

@@ -187,7 +187,7 @@ cudaError_t launch_scatter_effects(const double* eff_dev, long long m, int T, co
 
 // ------------------------------------------------------------------------------------------
 __global__ void finalize_sym_kernel(const double* __restrict__ Z, int nsplit, long long n, int T,
-                                    double* __restrict__ X) {
+                                    double* __restrict__ X, bool sym) {
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const int TT = T * T;
     if (idx >= n * TT) return;
@@ -197,14 +197,14 @@ __global__ void finalize_sym_kernel(const double* __restrict__ Z, int nsplit, lo
     double v = 0.0;
     for (int sp = 0; sp < nsplit; ++sp) {           // fixed order: bit-reproducible
         const double* z = Z + ((long long)sp * n + u) * TT;
-        v += z[t * T + s] + z[s * T + t];
+        v += sym ? z[t * T + s] + z[s * T + t] : z[t * T + s];
     }
     X[idx] = v;
 }
-cudaError_t launch_finalize_sym(const double* Z, int nsplit, long long n, int T, double* X, cudaStream_t st) {
+cudaError_t launch_finalize_sym(const double* Z, int nsplit, long long n, int T, double* X, cudaStream_t st, bool sym) {
     const long long total = n * T * T;
     if (total == 0) return cudaSuccess;
-    finalize_sym_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(Z, nsplit, n, T, X);
+    finalize_sym_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(Z, nsplit, n, T, X, sym);
     return cudaGetLastError();
 }
 

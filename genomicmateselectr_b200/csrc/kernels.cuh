@@ -21,8 +21,28 @@ cudaError_t launch_pack_u8rm(const uint8_t* hap_dev, long long P, long long m, c
 cudaError_t launch_scatter_effects(const double* eff_dev, long long m, int T, const ChromDesc* chrom, int C,
                                    double* emat, long long mp_total, cudaStream_t st);
 
-// X[n][t][s] = sum_split Z[split][n][t][s] + Z[split][n][s][t]
-cudaError_t launch_finalize_sym(const double* Z, int nsplit, long long n, int T, double* X, cudaStream_t st);
+// X[n][t][s] = sum_split Z[split][n][t][s] + Z[split][n][s][t]   (sym)   or   sum_split Z[split][n][t][s]
+cudaError_t launch_finalize_sym(const double* Z, int nsplit, long long n, int T, double* X, cudaStream_t st,
+                                bool sym = true);
+
+// ---- map-structured fast path (scan.cu) ----
+struct ScanParams {
+    const ChromDesc* chrom;
+    const int* split_begin;      // [nsplit + 1] ranges of chromosomes
+    const double* S;             // [mp][3][T]: e, a e, b e
+    const unsigned* planeA;
+    const unsigned* planeB;
+    long long wpp;
+    const int* unit_a;
+    const int* unit_b;
+    long long n_units;
+    int T;
+    int mode;
+    double* Xpart;               // [nsplit][n_units][T*T], symmetric
+};
+cudaError_t launch_scan_prepare(const double* emat, const double* apos, const double* bpos, long long mp_total, int T,
+                                double* S, cudaStream_t st);
+cudaError_t launch_scan(const ScanParams& p, int nsplit, cudaStream_t st);
 
 // Nsegsnps per cross over words [w_begin, w_end) of the padded axis.
 cudaError_t launch_nseg(const unsigned* planeA, const unsigned* planeB, long long wpp, long long w_begin,

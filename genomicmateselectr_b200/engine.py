@@ -110,6 +110,12 @@ class CrossVarEngine:
             self.set_recomb_blocks([R])
         return mask_ok
 
+    def set_mode(self, mode):
+        """"dense" (default: FP64 tensor contraction, any symmetric recombFreqMat) or "map_scan"
+        (map-structured prefix-sum fast path; needs set_genmap() with sorted positions)."""
+        code = {"dense": 0, "map_scan": 1}[mode] if isinstance(mode, str) else int(mode)
+        self._ck(self._lib.gms_set_mode(self._h, code))
+
     def set_chromosome_shard(self, c_begin, c_end):
         self._ck(self._lib.gms_set_chromosome_shard(self._h, int(c_begin), int(c_end)))
 

@@ -83,6 +83,15 @@ GMS_API int gms_set_recomb_blocks(gms_handle* h, int C, const int64_t* m_c, cons
 GMS_API int gms_set_haplotypes_i32cm(gms_handle* h, int64_t P, int64_t m, const int32_t* hap);
 GMS_API int gms_set_haplotypes_u8rm(gms_handle* h, int64_t P, int64_t m, const uint8_t* hap);
 
+/* Optional: evaluation mode. GMS_MODE_DENSE (default) is the dense FP64 tensor contraction against the
+ * stored R / RoR blocks - valid for any symmetric recombFreqMat. GMS_MODE_MAP_SCAN is the map-structured
+ * fast path: when the blocks came from gms_set_genmap() with positions sorted within each
+ * chromosome, R[j,k] = exp(-2|x_j-x_k|/100) factorises and every quadratic form becomes a prefix-sum
+ * scan over the non-zero SNPs of a unit (O(m T^2) per cross instead of O(m^2 T)); same results to ~1e-13.
+ * Returns GMS_ESTATE if the handle's blocks did not come from a sorted map. */
+enum { GMS_MODE_DENSE = 0, GMS_MODE_MAP_SCAN = 1 };
+GMS_API int gms_set_mode(gms_handle* h, int mode);
+
 /* Optional chromosome shard: this handle only sums over chromosomes [c_begin, c_end).  Outputs of
  * gms_predict are then PARTIAL sums (variances and Nsegsnps are additive over chromosomes); the
  * host adds the partial slabs of the shards (NCCL all-reduce in the multi-GPU driver).

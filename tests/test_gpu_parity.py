@@ -252,3 +252,64 @@ def test_cassava_scale_against_blockwise_oracle(gms):
     assert np.array_equal(nseg[pick], wseg)
     assert rel_err(out[pick], want) < TOL
     eng.close()
+
+
+# ---------------------------------------------------------------- map-structured fast path
+@pytest.mark.parametrize("model", ["A", "AD", "DirDom"])
+@pytest.mark.parametrize("T", [1, 2, 5, 6, 7, 11])
+def test_map_scan_mode_matches_oracle_and_dense(gms, model, T):
+    s = synth(300 + T, [200, 131, 77, 300], P=24, T=T)
+    rng = np.random.default_rng(6)
+    sire = rng.integers(0, 24, 90).astype(np.int32)
+    dam = rng.integers(0, 24, 90).astype(np.int32)
+    sire[:5] = dam[:5]
+    dom = s["dom"] if model != "A" else None
+    asub = s["asub"] if model == "DirDom" else None
+    eng = gms.CrossVarEngine(0)
+    eng.set_genmap(s["cM"], s["m_c"])
+    eng.set_haplotypes(s["H"])
+    dense, nseg_d = eng.predict(model, s["add"], dom, asub, sire, dam)
+    eng.set_mode("map_scan")
+    out, nseg = eng.predict(model, s["add"], dom, asub, sire, dam)
+    want, wseg = oracle_slab(model, s["H"], s["R"], s["add"], dom, asub, sire, dam)
+    assert np.array_equal(nseg, wseg) and np.array_equal(nseg_d, wseg)
+    assert rel_err(out, want) < TOL
+    assert rel_err(out, dense) < TOL
+    eng.set_mode("dense")
+    again, _ = eng.predict(model, s["add"], dom, asub, sire, dam)
+    assert np.array_equal(again, dense)                     # the dense path is bit-reproducible
+    eng.close()
+
+
+def test_map_scan_needs_a_sorted_map(gms):
+    s = synth(4, [90, 60], P=4, T=2)
+    eng = gms.CrossVarEngine(0)
+    eng.set_recomb_matrix(s["R"], s["chrom"])
+    eng.set_haplotypes(s["H"])
+    with pytest.raises(gms.GmsError, match="sorted"):
+        eng.set_mode("map_scan")
+    cM = s["cM"].copy()
+    cM[[3, 4]] = cM[[4, 3]]                               # unsorted map: dense still fine, scan refused
+    eng.set_genmap(cM, s["m_c"])
+    eng.set_haplotypes(s["H"])
+    with pytest.raises(gms.GmsError, match="sorted"):
+        eng.set_mode("map_scan")
+    R = O.recombfreq_to_ld_decay(O.genmap2recombfreq(cM, s["chrom"]))
+    out, nseg = eng.predict("AD", s["add"], s["dom"], None, [0, 1], [2, 3])
+    want, wseg = oracle_slab("AD", s["H"], R, s["add"], s["dom"], None, [0, 1], [2, 3])
+    assert np.array_equal(nseg, wseg) and rel_err(out, want) < TOL
+    eng.close()
+
+
+def test_map_scan_cassava_scale_equals_dense(gms):
+    from genomicmateselectr_b200 import synth as S
+    d = S.make("cassava", N=3000)
+    eng = gms.CrossVarEngine(0)
+    eng.set_genmap(d["cM"], d["m_c"])
+    eng.set_haplotypes(d["H"])
+    dense, nseg = eng.predict("AD", d["add"], d["dom"], None, d["sire"], d["dam"])
+    eng.set_mode("map_scan")
+    fast, nseg2 = eng.predict("AD", d["add"], d["dom"], None, d["sire"], d["dam"])
+    assert np.array_equal(nseg, nseg2)
+    assert rel_err(fast, dense) < TOL
+    eng.close()
