@@ -47,6 +47,7 @@ _SIGS = {
     "gms_set_mode": (C.c_int, [_P, C.c_int]),
     "gms_trait_pairs": (C.c_int, [C.c_int, _P, _P]),
     "gms_predict": (C.c_int, [_P, C.c_int, C.c_int, _P, _P, _P, C.c_int64, _P, _P, _P, _P]),
+    "gms_predict_sharded": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, _P, _P, _P, C.c_int64, _P, _P, _P, _P]),
     "gms_stage_inputs": (C.c_int, [_P, C.c_int, C.c_int, _P, _P, _P, C.c_int64, _P, _P]),
     "gms_compute": (C.c_int, [_P, C.c_int]),
     "gms_fetch_outputs": (C.c_int, [_P, _P, _P]),

@@ -7,6 +7,7 @@
 #include <mutex>
 #include <new>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/gms_b200.h"
@@ -686,6 +687,32 @@ int gms_predict(gms_handle* h, int model, int T, const double* add, const double
     if (int rc = gms_stage_inputs(h, model, T, add, dom, asub, N, sire, dam)) return rc;
     if (int rc = gms_compute(h, 0)) return rc;
     return gms_fetch_outputs(h, out, nseg);
+}
+
+int gms_predict_sharded(gms_handle* const* hs, int nh, int model, int T, const double* add, const double* dom,
+                        const double* asub, int64_t N, const int32_t* sire, const int32_t* dam, double* out,
+                        int32_t* nseg) {
+    if (!hs || nh < 1 || !hs[0]) return GMS_EINVAL;
+    for (int i = 0; i < nh; ++i) if (!hs[i]) return fail(hs[0], GMS_EINVAL, "NULL handle in gms_predict_sharded");
+    if (model < GMS_MODEL_A || model > GMS_MODEL_DIRDOM || T < 1) return fail(hs[0], GMS_EINVAL, "bad model / T");
+    if (N < 0 || (N > 0 && (!sire || !dam || !out || !nseg))) return fail(hs[0], GMS_EINVAL, "bad cross list / outputs");
+    const int64_t stride = (int64_t)(T * (T + 1) / 2) * (model + 1);
+    std::vector<int> rc((size_t)nh, GMS_OK);
+    std::vector<std::thread> th;
+    auto work = [&](int i) {
+        const int64_t base = N / nh, extra = N % nh;
+        const int64_t lo = i * base + std::min<int64_t>(i, extra), n = base + (i < extra ? 1 : 0);
+        rc[i] = gms_predict(hs[i], model, T, add, dom, asub, n, sire + lo, dam + lo, out + lo * stride, nseg + lo);
+    };
+    for (int i = 1; i < nh; ++i) th.emplace_back(work, i);
+    work(0);
+    for (auto& t : th) t.join();
+    for (int i = 0; i < nh; ++i)
+        if (rc[i] != GMS_OK) {
+            if (i != 0) hs[0]->err = "shard " + std::to_string(i) + ": " + hs[i]->err;
+            return rc[i];
+        }
+    return GMS_OK;
 }
 
 int gms_selind(int model, int T, int64_t N, const double* out, const double* w, double* si) {

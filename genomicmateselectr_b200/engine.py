@@ -203,6 +203,26 @@ class CrossVarEngine:
                                        _ptr(sire), _ptr(dam), _ptr(out), _ptr(nseg)))
         return out, nseg
 
+    @staticmethod
+    def predict_sharded(engines, model, add, dom=None, asub=None, sire=None, dam=None):
+        """gms_predict_sharded: several engines (one per GPU, same map + haplotypes) in ONE process; the
+        cross list is cut into contiguous shards, results land in one host slab."""
+        e0 = engines[0]
+        model = MODEL[model] if isinstance(model, str) else int(model)
+        add, T = e0._eff(add, e0.m)
+        dom, _ = e0._eff(dom, e0.m)
+        asub, _ = e0._eff(asub, e0.m)
+        sire = np.ascontiguousarray(sire, dtype=np.int32)
+        dam = np.ascontiguousarray(dam, dtype=np.int32)
+        N, npairs, ncomp = sire.size, T * (T + 1) // 2, model + 1
+        out = np.empty((N, npairs, ncomp), np.float64)
+        nseg = np.empty(N, np.int32)
+        hs = (C.c_void_p * len(engines))(*[e._h for e in engines])
+        rc = e0._lib.gms_predict_sharded(C.cast(hs, C.c_void_p), len(engines), model, T, _ptr(add), _ptr(dom), _ptr(asub),
+                                         N, _ptr(sire), _ptr(dam), _ptr(out), _ptr(nseg))
+        e0._ck(rc)
+        return out, nseg
+
     # ------------------------------------------------------------------ "next" rows
     def cross_means(self, add, dom=None, sire=None, dam=None):
         """predCrossMeans: returns (gebv[P,T], mean_bv[N,T], mean_tgv[N,T] or None)."""

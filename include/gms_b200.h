@@ -122,6 +122,16 @@ GMS_API int gms_predict(gms_handle* h, int model, int T,
                 int64_t N, const int32_t* sire, const int32_t* dam,
                 double* out, int32_t* nseg);
 
+/* Multi-GPU from ONE host process (what a single R session needs): `hs[0..nh)` are handles on different
+ * devices that were given the same map / blocks and haplotypes. The cross list is cut into nh contiguous
+ * shards, one host thread per handle runs gms_predict on its shard and writes straight into the caller's
+ * `out` / `nseg` slices - no collective, only this implicit gather. Returns the first non-zero status
+ * (its text is copied to hs[0]'s gms_last_error). */
+GMS_API int gms_predict_sharded(gms_handle* const* hs, int nh, int model, int T,
+                                const double* add, const double* dom, const double* asub,
+                                int64_t N, const int32_t* sire, const int32_t* dam,
+                                double* out, int32_t* nseg);
+
 /* The same work split in three so that a benchmark can time the device part alone with inputs
  * resident in HBM: gms_stage_inputs (host->device), gms_compute (kernels only, asynchronous on
  * the handle's stream unless `sync` != 0), gms_fetch_outputs (device->host, synchronises). */

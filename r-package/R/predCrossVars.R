@@ -25,7 +25,16 @@ Ops.gms_twoc <- function(e1, e2) {
 }
 
 # Device-resident session: tiles + haplotypes of `parents`; reuse it across calls (CV folds).
-gms_session <- function(haploMat, recombFreqMat, parents = NULL, device = 0L) {
+# `devices`: integer vector of CUDA devices; with more than one, every device gets the tiles + haplotypes
+# and predCrossVars() shards the cross list over them (gms_predict_sharded), all from this one R process.
+# `map_scan = TRUE` switches on the map-structured fast path when recombFreqMat is a lazy map object.
+gms_session <- function(haploMat, recombFreqMat, parents = NULL, devices = 0L, map_scan = FALSE) {
+  if (length(devices) > 1) {
+    ss <- lapply(devices, function(d) gms_session(haploMat, recombFreqMat, parents, d, map_scan))
+    return(structure(list(handle = ss[[1]]$handle, handles = lapply(ss, `[[`, "handle"),
+                          snps = ss[[1]]$snps, parents = ss[[1]]$parents), class = "gms_session"))
+  }
+  device <- devices
   snps <- colnames(haploMat)
   chr <- .gms_chrom(snps)
   ord <- order(match(chr, unique(chr)))                          # group by chromosome, stable
@@ -48,7 +57,8 @@ gms_session <- function(haploMat, recombFreqMat, parents = NULL, device = 0L) {
   H <- haploMat[rows, snps, drop = FALSE]                         # errors if a parent is missing, like :46
   storage.mode(H) <- "integer"
   .Call("gmsr_set_haplotypes", h, H)
-  structure(list(handle = h, snps = snps, parents = as.character(parents)), class = "gms_session")
+  if (map_scan && inherits(recombFreqMat, "gms_lddecay")) .Call("gmsr_set_mode", h, 1L)
+  structure(list(handle = h, handles = list(h), snps = snps, parents = as.character(parents)), class = "gms_session")
 }
 
 .gms_effmat <- function(EffectList, snps) {
@@ -63,6 +73,8 @@ gms_session <- function(haploMat, recombFreqMat, parents = NULL, device = 0L) {
   sire <- match(as.character(CrossesToPredict$sireID), session$parents) - 1L
   dam <- match(as.character(CrossesToPredict$damID), session$parents) - 1L
   if (anyNA(sire) || anyNA(dam)) stop("subscript out of bounds: parent not in haploMat")
+  if (length(session$handles) > 1)
+    return(.Call("gmsr_predict_sharded", session$handles, model, add, dom, asub, sire, dam))
   .Call("gmsr_predict", session$handle, model, add, dom, asub, sire, dam)
 }
 
@@ -75,7 +87,7 @@ predCrossVars <- function(CrossesToPredict, modelType, AddEffectList, DomEffectL
   if (is.null(session)) {
     parents <- union(CrossesToPredict$sireID, CrossesToPredict$damID)          # :44-46
     session <- gms_session(haploMat, recombFreqMat, parents)
-    on.exit(.Call("gmsr_close", session$handle))
+    on.exit(lapply(session$handles, function(h) .Call("gmsr_close", h)))
   }
   res <- .gms_run(session, CrossesToPredict, model, AddEffectList, DomEffectList)
   traits <- names(AddEffectList)

@@ -106,6 +106,43 @@ SEXP gmsr_predict(SEXP ptr, SEXP model, SEXP add, SEXP dom, SEXP asub, SEXP sire
     return res;
 }
 
+/* same as gmsr_predict on a LIST of handles (one per GPU, same map + haplotypes): gms_predict_sharded cuts
+ * the cross list into contiguous shards, one host thread per GPU, all joined before returning to R */
+SEXP gmsr_predict_sharded(SEXP ptrs, SEXP model, SEXP add, SEXP dom, SEXP asub, SEXP sire, SEXP dam) {
+    const int nh = LENGTH(ptrs);
+    if (nh < 1) Rf_error("gms_b200: no engine handles");
+    gms_handle** hs = (gms_handle**)R_alloc(nh, sizeof(gms_handle*));
+    for (int i = 0; i < nh; ++i) hs[i] = gmsr_get(VECTOR_ELT(ptrs, i));
+    const int mdl = Rf_asInteger(model), T = Rf_ncols(add);
+    const R_xlen_t N = XLENGTH(sire);
+    const int npairs = T * (T + 1) / 2, ncomp = mdl + 1;
+    if (XLENGTH(dam) != N) Rf_error("gms_b200: sire and dam differ in length");
+    SEXP out = PROTECT(Rf_allocVector(REALSXP, (R_xlen_t)ncomp * npairs * N));
+    SEXP nseg = PROTECT(Rf_allocVector(INTSXP, N));
+    int rc = gms_predict_sharded(hs, nh, mdl, T, REAL(add), Rf_isNull(dom) ? NULL : REAL(dom),
+                                 Rf_isNull(asub) ? NULL : REAL(asub), (int64_t)N, INTEGER(sire), INTEGER(dam),
+                                 REAL(out), INTEGER(nseg));
+    if (rc != GMS_OK) { UNPROTECT(2); Rf_error("gms_b200: %s", gms_last_error(hs[0])); }
+    SEXP dim = PROTECT(Rf_allocVector(INTSXP, 3));
+    INTEGER(dim)[0] = ncomp; INTEGER(dim)[1] = npairs; INTEGER(dim)[2] = (int)N;
+    Rf_setAttrib(out, R_DimSymbol, dim);
+    SEXP res = PROTECT(Rf_allocVector(VECSXP, 2));
+    SET_VECTOR_ELT(res, 0, out);
+    SET_VECTOR_ELT(res, 1, nseg);
+    SEXP nm = PROTECT(Rf_allocVector(STRSXP, 2));
+    SET_STRING_ELT(nm, 0, Rf_mkChar("out"));
+    SET_STRING_ELT(nm, 1, Rf_mkChar("nseg"));
+    Rf_setAttrib(res, R_NamesSymbol, nm);
+    UNPROTECT(5);
+    return res;
+}
+
+SEXP gmsr_set_mode(SEXP ptr, SEXP mode) {
+    gms_handle* h = gmsr_get(ptr);
+    gmsr_check(h, gms_set_mode(h, Rf_asInteger(mode)));
+    return R_NilValue;
+}
+
 static const R_CallMethodDef gmsr_calls[] = {
     {"gmsr_create", (DL_FUNC)&gmsr_create, 1},
     {"gmsr_close", (DL_FUNC)&gmsr_close, 1},
@@ -113,6 +150,8 @@ static const R_CallMethodDef gmsr_calls[] = {
     {"gmsr_set_recomb_blocks", (DL_FUNC)&gmsr_set_recomb_blocks, 2},
     {"gmsr_set_haplotypes", (DL_FUNC)&gmsr_set_haplotypes, 2},
     {"gmsr_predict", (DL_FUNC)&gmsr_predict, 7},
+    {"gmsr_predict_sharded", (DL_FUNC)&gmsr_predict_sharded, 7},
+    {"gmsr_set_mode", (DL_FUNC)&gmsr_set_mode, 2},
     {NULL, NULL, 0}};
 
 void R_init_genomicMateSelectRb200(DllInfo* dll) {

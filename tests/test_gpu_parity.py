@@ -313,3 +313,26 @@ def test_map_scan_cassava_scale_equals_dense(gms):
     assert np.array_equal(nseg, nseg2)
     assert rel_err(fast, dense) < TOL
     eng.close()
+
+
+def test_predict_sharded_one_process(gms):
+    """gms_predict_sharded: one host process, one handle per visible GPU (2 handles on the same GPU
+    when only one is visible - the threads then just serialise on the device)."""
+    import torch
+    s = synth(21, [150, 140], P=10, T=3)
+    rng = np.random.default_rng(1)
+    sire = rng.integers(0, 10, 41).astype(np.int32)
+    dam = rng.integers(0, 10, 41).astype(np.int32)
+    ndev = max(1, torch.cuda.device_count())
+    engines = [gms.CrossVarEngine(i % ndev) for i in range(max(2, min(ndev, 4)))]
+    for e in engines:
+        e.set_genmap(s["cM"], s["m_c"])
+        e.set_haplotypes(s["H"])
+    out, nseg = gms.CrossVarEngine.predict_sharded(engines, "AD", s["add"], s["dom"], None, sire, dam)
+    ref, rseg = engines[0].predict("AD", s["add"], s["dom"], None, sire, dam)
+    assert np.array_equal(nseg, rseg) and np.array_equal(out, ref)
+    with pytest.raises(gms.GmsError, match="out of range"):
+        bad = dam.copy(); bad[-1] = 99
+        gms.CrossVarEngine.predict_sharded(engines, "AD", s["add"], s["dom"], None, sire, bad)
+    for e in engines:
+        e.close()
