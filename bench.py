@@ -155,8 +155,26 @@ def cpu_reference_run(d, model, sample, steps, warmup, nthreads=0):
             "ms_per_step": 1e3 * total / steps}
 
 
+_REAL_STDOUT = None
+
+
+def claim_stdout():
+    """stdout must carry exactly ONE JSON line: route everything else (NCCL's version banner, library
+    chatter) to stderr and keep the real stdout for emit()."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
+
+
+def emit(line):
+    sys.stdout.flush()
+    os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, (json.dumps(line) + "\n").encode())
+
+
 def main():
     args = parse()
+    claim_stdout()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -182,7 +200,7 @@ def main():
                 "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
                 "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
-        print(json.dumps(line))
+        emit(line)
         return 0
 
     # ------------------------------------------------------------------ our arm (GPU)
@@ -351,7 +369,7 @@ def main():
                               "assemble_nseg": float(np.mean([s[2] for s in stage_ms]))},
                 "map_scan": map_scan, "setup_s": setup_s, "hbm_tile_bytes": int(st["tile_bytes"]),
                 "measured_peaks": {"hbm_gbs": pk.get("hbm_gbs"), "fp64_dgemm_tflops": fp64_peak}}
-        print(json.dumps(line))
+        emit(line)
     eng.close()
     if world > 1:
         dist.destroy_process_group()
