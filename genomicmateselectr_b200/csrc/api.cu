@@ -79,6 +79,17 @@ struct gms_handle {
     Plan plan_par, plan_x;
     int stages = 0;
 
+    // int8 tensor path (per-cross term)
+    std::vector<RowTile> jtiles;
+    DevBuf<RowTile> jtiles_d;
+    std::vector<long long> gbase;
+    DevBuf<long long> gbase_d;
+    DevBuf<signed char> xi_d, G_d;
+    DevBuf<double> scale_d;
+    DevBuf<int> split_i8_d;
+    Plan plan_i8;
+    bool use_i8 = false;
+
     // map-structured fast path
     int mode = GMS_MODE_DENSE;
     bool scan_ok = false;
@@ -348,6 +359,7 @@ void gms_destroy(gms_handle* h) {
     h->PD.release(); h->QB.release(); h->X.release(); h->out_d.release(); h->nseg_d.release();
     h->gebv_d.release(); h->mean_d.release(); h->scan_ab.release(); h->S_add.release(); h->S_dom.release();
     h->S_asub.release(); h->split_scan_par_d.release(); h->split_scan_x_d.release();
+    h->jtiles_d.release(); h->gbase_d.release(); h->xi_d.release(); h->G_d.release(); h->scale_d.release(); h->split_i8_d.release();
     for (auto& ev : h->ev) if (ev) cudaEventDestroy(ev);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     delete h;
@@ -405,7 +417,9 @@ int gms_set_genmap(gms_handle* h, int C, const int64_t* m_c, const double* cM) {
 
 int gms_set_mode(gms_handle* h, int mode) {
     if (!h) return GMS_EINVAL;
-    if (mode != GMS_MODE_DENSE && mode != GMS_MODE_MAP_SCAN) return fail(h, GMS_EINVAL, "unknown mode");
+    if (mode != GMS_MODE_DENSE && mode != GMS_MODE_MAP_SCAN && mode != GMS_MODE_INT8_TENSOR)
+        return fail(h, GMS_EINVAL, "unknown mode");
+    if (mode == GMS_MODE_INT8_TENSOR && !h->have_tiles) return fail(h, GMS_ESTATE, "set the map / recombination blocks first");
     if (mode == GMS_MODE_MAP_SCAN && !(h->have_tiles && h->scan_ok))
         return fail(h, GMS_ESTATE, "the map-structured fast path needs gms_set_genmap() with positions sorted within every chromosome");
     h->mode = mode;
@@ -598,11 +612,69 @@ int gms_stage_inputs(gms_handle* h, int model, int T, const double* add, const d
                        cudaMemcpyHostToDevice, h->stream));
     CU(cudaMemcpyAsync(h->split_x_d.p, h->plan_x.split_begin.data(), sizeof(int) * h->plan_x.split_begin.size(),
                        cudaMemcpyHostToDevice, h->stream));
+    h->use_i8 = (h->mode == GMS_MODE_INT8_TENSOR && model >= GMS_MODEL_AD && T <= 6 && N > 0 &&
+                 (double)((N + 127) / 128 * 128) * (double)h->mp_total < 24e9);
+    if (h->use_i8) {
+        // 64-row tiles of the lower block triangle + digit image offsets for the chromosome shard
+        h->jtiles.clear();
+        h->gbase.assign(h->C, 0);
+        long long gb = 0;
+        for (int c = h->c_begin; c < h->c_end; ++c) {
+            const int nJ = (h->chrom[c].m + 63) / 64;
+            h->gbase[c] = gb;
+            gb += (long long)nJ * (nJ + 1) / 2 * T * 7 * 4096;
+            for (int J = 0; J < nJ; ++J) h->jtiles.push_back(RowTile{c, J});
+        }
+        CU(h->jtiles_d.ensure(h->jtiles.size()));
+        CU(h->gbase_d.ensure(h->C));
+        CU(cudaMemcpyAsync(h->jtiles_d.p, h->jtiles.data(), sizeof(RowTile) * h->jtiles.size(), cudaMemcpyHostToDevice, h->stream));
+        CU(cudaMemcpyAsync(h->gbase_d.p, h->gbase.data(), sizeof(long long) * h->C, cudaMemcpyHostToDevice, h->stream));
+        CU(h->G_d.ensure((size_t)gb));
+        CU(h->scale_d.ensure((size_t)h->mp_total * T));
+        CU(cudaMemsetAsync(h->scale_d.p, 0, sizeof(double) * h->mp_total * T, h->stream));
+        for (int c = h->c_begin; c < h->c_end; ++c)
+            CU(launch_i8_build_digits(h->R2.p, h->chrom_d.p, h->chrom[c], c, h->emat_dom.p, h->mp_total, T, h->scale_d.p,
+                                      h->gbase[c], h->G_d.p, h->stream));
+        const long long npad = (N + 127) / 128 * 128;
+        CU(h->xi_d.ensure((size_t)npad * h->mp_total));
+        CU(launch_i8_build_xi(h->planeA.p, h->planeB.p, h->wpp, h->sire_d.p, h->dam_d.p, N, MASK_XI, h->mp_total / 64,
+                              h->xi_d.p, h->stream));
+        // plan: contiguous ranges of jtiles of equal work (weight J + 1)
+        Plan& pl = h->plan_i8;
+        pl.ntiles = (int)(npad / 128);
+        const int njt = (int)h->jtiles.size();
+        int ns = 1;
+        if (pl.ntiles < 2 * h->num_sms) ns = (2 * h->num_sms + pl.ntiles - 1) / pl.ntiles;
+        else {
+            double best = 1e30;
+            for (int cand = 1; cand <= 8; ++cand) {
+                const double ctas = (double)pl.ntiles * cand, waves = std::ceil(ctas / h->num_sms);
+                const double cost = waves * h->num_sms / ctas * (1.0 + 0.01 * (cand - 1));
+                if (cost < best - 1e-12) { best = cost; ns = cand; }
+            }
+        }
+        ns = std::max(1, std::min(ns, njt));
+        pl.nsplit = ns;
+        pl.split_begin.assign(ns + 1, 0);
+        double total = 0, acc = 0;
+        for (const RowTile& r : h->jtiles) total += r.I + 1;
+        int sp = 1;
+        for (int i = 0; i < njt && sp < ns; ++i) {
+            acc += h->jtiles[i].I + 1;
+            while (sp < ns && acc >= total * sp / ns && (njt - (i + 1)) >= (ns - sp)) pl.split_begin[sp++] = i + 1;
+        }
+        for (; sp < ns; ++sp) pl.split_begin[sp] = std::max(pl.split_begin[sp - 1], njt - (ns - sp));
+        pl.split_begin[ns] = njt;
+        for (int i = 1; i <= ns; ++i) pl.split_begin[i] = std::max(pl.split_begin[i], pl.split_begin[i - 1]);
+        CU(h->split_i8_d.ensure(pl.split_begin.size()));
+        CU(cudaMemcpyAsync(h->split_i8_d.p, pl.split_begin.data(), sizeof(int) * pl.split_begin.size(), cudaMemcpyHostToDevice, h->stream));
+    }
     size_t zneed = std::max<size_t>((size_t)h->plan_par.nsplit * (size_t)h->nP * TT,
                                     model >= GMS_MODEL_AD ? (size_t)h->plan_x.nsplit * (size_t)N * TT : (size_t)0);
     if (h->mode == GMS_MODE_MAP_SCAN)
         zneed = std::max<size_t>((h->scan_split_par.size() - 1) * (size_t)h->nP * TT,
                                  model >= GMS_MODEL_AD ? (h->scan_split_x.size() - 1) * (size_t)N * TT : (size_t)0);
+    if (h->use_i8) zneed = std::max<size_t>(zneed, (size_t)h->plan_i8.nsplit * (size_t)N * TT);
     CU(h->Z.ensure(zneed));
     CU(h->QA.ensure((size_t)h->nP * TT));
     if (model >= GMS_MODEL_AD) { CU(h->PD.ensure((size_t)h->nP * TT)); CU(h->X.ensure((size_t)N * TT)); }
@@ -647,7 +719,20 @@ int gms_compute(gms_handle* h, int sync) {
                                       h->split_par_d.p, h->QB.p)) return rc;
         CU(cudaEventRecord(h->ev[1], h->stream));
         // per-cross dominance term X = (d o xi)' RoR (d o xi), xi = delta_sire o delta_dam
-        if (h->model >= GMS_MODEL_AD)
+        if (h->use_i8) {
+            I8Params ip{};
+            ip.chrom = h->chrom_d.p; ip.jtiles = h->jtiles_d.p; ip.split_begin = h->split_i8_d.p;
+            ip.xi = h->xi_d.p; ip.nkb_total = h->mp_total / 64; ip.G = h->G_d.p; ip.gbase = h->gbase_d.p;
+            ip.scale = h->scale_d.p; ip.emat = h->emat_dom.p; ip.mp_total = h->mp_total;
+            ip.planeA = h->planeA.p; ip.planeB = h->planeB.p; ip.wpp = h->wpp;
+            ip.unit_a = h->sire_d.p; ip.unit_b = h->dam_d.p; ip.n_units = h->N; ip.T = h->T; ip.mode = MASK_XI;
+            ip.Zpart = h->Z.p;
+            CU(cudaEventRecord(h->ev[4], h->stream));
+            CU(launch_i8_contract(ip, h->plan_i8.ntiles, h->plan_i8.nsplit, h->stream));
+            CU(cudaEventRecord(h->ev[5], h->stream));
+            CU(launch_finalize_sym(h->Z.p, h->plan_i8.nsplit, h->N, h->T, h->X.p, h->stream, true));
+            h->st.last_launches += 2;
+        } else if (h->model >= GMS_MODEL_AD)
             if (int rc = run_contract(h, h->R2.p, h->emat_dom.p, MASK_XI, h->sire_d.p, h->dam_d.p, h->N, h->plan_x,
                                       h->split_x_d.p, h->X.p, h->ev[4], h->ev[5])) return rc;
     }

@@ -1,0 +1,427 @@
+// Exact int8 tensor-core evaluation of the per-cross dominance term (opt-in: GMS_MODE_INT8_TENSOR).
+//
+// FP64 has no tcgen05 kind, but this contraction has a special shape: one operand is TERNARY.
+//     C_s[j,x] = sum_k G_s[j,k] xi_x[k],   G_s[j,k] = L'[j,k] d_s[k]  (FP64),   xi in {-1,0,+1}
+// xi is exact in int8. G_s is split row-wise into 7 signed radix-128 digits with a shared power-of-two
+// row scale 2^E(j,s):  G = 2^E sum_i g_i 128^-(i+1) + r,  |r| <= 2^(E-49)  (exact FP64 operations).
+// Each digit plane times xi is an int8 x int8 -> int32 product whose sum over k <= 1920 terms is EXACT in
+// int32 (|sum| < 2^18), so the 5th-generation tensor cores (tcgen05.mma kind::i8, accumulators in TMEM)
+// do the O(m^2) work at int8 rate and the result differs from exact arithmetic only by the 2^-49 digit
+// truncation - tighter than a rounded FP64 dot product. The epilogue recombines the digits in FP64,
+// applies xi_x[j] d_t[j] and accumulates the T x T quadratic forms per cross in registers
+// (TMEM lane = cross, so the reduction over SNPs j is thread-local: no shuffles, no atomics).
+//
+// Orientation: D[M = 128 crosses (TMEM lanes)][N = 64 SNP rows j] += Xi[128 x K] * Gdigit_i[64 x K]^T,
+// both operands K-major, no swizzle, pre-tiled in HBM in the UMMA canonical "interleaved" layout
+// (8 rows x 16 bytes core matrices) so that one cp.async.bulk lands them ready for the descriptors.
+// Warp roles: 0-3 epilogue (tcgen05.ld, one TMEM lane quarter each), 4 bulk-copy producer, 5 MMA issuer.
+#include "kernels.cuh"
+
+namespace gms {
+
+constexpr int I8_M = 128;        // crosses per tile (TMEM lanes)
+constexpr int I8_N = 64;         // SNP rows j per accumulator
+constexpr int I8_KB = 64;        // k per pipeline stage (bytes of int8)
+constexpr int I8_DIG = 7;        // radix-128 digits
+constexpr int I8_A_BYTES = I8_M * I8_KB;            // 8 KiB
+constexpr int I8_B_BYTES = I8_N * I8_KB;            // 4 KiB per digit
+constexpr int I8_STAGE_BYTES = I8_A_BYTES + I8_DIG * I8_B_BYTES;   // 36 KiB
+constexpr int I8_STAGES = 5;
+constexpr int I8_THREADS = 192;
+
+// ------------------------------------------------------------------------------------------ prep: xi images
+// image (X tile, global k-block) : [chunk cc (4)][r1 (16)][r0 (8)][16 bytes], row r = 8 r1 + r0, k = 16 cc + b
+__global__ void i8_build_xi_kernel(const unsigned* __restrict__ planeA, const unsigned* __restrict__ planeB,
+                                   long long wpp, const int* __restrict__ sire, const int* __restrict__ dam,
+                                   long long n_units, int mode, long long nkb_total, signed char* __restrict__ xi) {
+    // one thread = one (unit, 16-byte chunk): 16 consecutive k of one cross
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long chunks_per_unit = nkb_total * 4;
+    const long long npad = (n_units + I8_M - 1) / I8_M * I8_M;
+    if (gid >= npad * chunks_per_unit) return;
+    // consecutive threads -> consecutive rows (so that the 16-byte stores of a warp are contiguous)
+    const long long tile_chunk = gid / I8_M;            // (X, kbglobal, cc)
+    const int r = (int)(gid - tile_chunk * I8_M);
+    const long long X = tile_chunk / chunks_per_unit;
+    const long long rem = tile_chunk - X * chunks_per_unit;
+    const long long kbg = rem >> 2;
+    const int cc = (int)(rem & 3);
+    const long long unit = X * I8_M + r;
+    unsigned nz = 0, ng = 0;
+    if (unit < n_units) {
+        const long long w = kbg * 2 + (cc >> 1);
+        const int pa = sire[unit];
+        const unsigned A = planeA[(long long)pa * wpp + w], B = planeB[(long long)pa * wpp + w];
+        if (mode == MASK_XI) {
+            const int pb = dam[unit];
+            const unsigned A2 = planeA[(long long)pb * wpp + w], B2 = planeB[(long long)pb * wpp + w];
+            nz = (A ^ B) & (A2 ^ B2);
+            ng = ((~A & B) ^ (~A2 & B2)) & nz;
+        } else {
+            nz = A ^ B;
+            ng = (mode == MASK_DELTA) ? (~A & B) : 0u;
+        }
+        nz >>= 16 * (cc & 1);
+        ng >>= 16 * (cc & 1);
+    }
+    unsigned out[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        unsigned v = 0;
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            const int bit = 4 * q + b;
+            const unsigned byte = ((nz >> bit) & 1u) ? (((ng >> bit) & 1u) ? 0xFFu : 0x01u) : 0u;
+            v |= byte << (8 * b);
+        }
+        out[q] = v;
+    }
+    const int r1 = r >> 3, r0 = r & 7;
+    signed char* dst = xi + ((X * nkb_total + kbg) * (long long)I8_A_BYTES) + ((cc * 16 + r1) * 8 + r0) * 16;
+    *reinterpret_cast<uint4*>(dst) = make_uint4(out[0], out[1], out[2], out[3]);
+}
+
+// ------------------------------------------------------------------------------------------ prep: G digits
+// element (row, col) of the chromosome's L' (lower block triangle at 64 granularity, diagonal 64 x 64
+// blocks halved) read from the FP64 tile image, whose own convention is 128-granular (common.cuh)
+__device__ __forceinline__ double lprime64(const double* __restrict__ tiles, const ChromDesc& cd, int row, int col) {
+    const int I = row >> 7, kc = col >> 5;
+    const long long ch = chunks_before_rowtile(I) + kc;
+    const int mb = (row & 127) >> 4, hi = (row & 15) >> 3, lane = ((row & 7) << 2) | (col & 3), q = (col & 31) >> 2;
+    double v = tiles[cd.tile_off + ch * CHUNK + (((q * 8 + mb) * 32 + lane) << 1) + hi];
+    if ((col >> 7) == I) v *= 2.0;                     // undo the 128-granular halving
+    if ((col >> 6) == (row >> 6)) v *= 0.5;            // apply the 64-granular one
+    return v;
+}
+
+// scale[s][pj] = 2^E with |G_s[j,k]| < 2^E for every k of row j's lower-triangle range (1 if the row is zero)
+__global__ void i8_rowscale_kernel(const double* __restrict__ tiles, const ChromDesc* __restrict__ chrom, int c,
+                                   const double* __restrict__ emat, long long mp_total, int T,
+                                   double* __restrict__ scale) {
+    const ChromDesc cd = chrom[c];
+    const int row = blockIdx.x;                        // local row (< roundup(m,64))
+    const int s = blockIdx.y;
+    const int kend = min(cd.m, ((row >> 6) + 1) << 6);
+    double mx = 0.0;
+    if (row < cd.m)
+        for (int k = threadIdx.x; k < kend; k += blockDim.x)
+            mx = fmax(mx, fabs(lprime64(tiles, cd, row, k) * emat[(long long)s * mp_total + cd.pad_off + k]));
+    __shared__ double sh[32];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = mx;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int i = 1; i < (int)(blockDim.x >> 5); ++i) mx = fmax(mx, sh[i]);
+        int e = 0;
+        if (mx > 0.0) { (void)frexp(mx, &e); }          // mx = f * 2^e, f in [0.5, 1)  =>  mx < 2^e
+        scale[(long long)s * mp_total + cd.pad_off + row] = ldexp(1.0, e);
+    }
+}
+
+// digit images: (c, J, kb <= J, s, digit i): [cc (4)][r1 (8)][r0 (8)][16 bytes]; one thread = 16 consecutive k of a row
+__global__ void i8_build_digits_kernel(const double* __restrict__ tiles, const ChromDesc* __restrict__ chrom, int c,
+                                       const double* __restrict__ emat, long long mp_total, int T,
+                                       const double* __restrict__ scale, long long gbase, signed char* __restrict__ G) {
+    const ChromDesc cd = chrom[c];
+    const int blk = blockIdx.x;                       // index of (J, kb) in the lower block triangle
+    int J = (int)((sqrt(8.0 * blk + 1.0) - 1.0) * 0.5);
+    while ((J + 1) * (J + 2) / 2 <= blk) ++J;
+    while (J * (J + 1) / 2 > blk) --J;
+    const int kb = blk - J * (J + 1) / 2;
+    const int s = blockIdx.y;
+    const int r = threadIdx.x & 63, cc = threadIdx.x >> 6;      // 256 threads: 64 rows x 4 chunks
+    const int row = J * 64 + r;
+    signed char d[I8_DIG][16];
+    const double inv = 1.0 / scale[(long long)s * mp_total + cd.pad_off + row];     // exact: a power of two
+#pragma unroll
+    for (int b = 0; b < 16; ++b) {
+        const int col = kb * 64 + cc * 16 + b;
+        double g = 0.0;
+        if (row < cd.m && col < cd.m)
+            g = lprime64(tiles, cd, row, col) * emat[(long long)s * mp_total + cd.pad_off + col];
+        double rr = g * inv;                           // |rr| < 1, exact
+#pragma unroll
+        for (int i = 0; i < I8_DIG; ++i) {
+            rr *= 128.0;                               // exact
+            const double t = trunc(rr);                // |t| <= 127
+            d[i][b] = (signed char)(int)t;
+            rr -= t;                                   // exact
+        }
+    }
+    const int r1 = r >> 3, r0 = r & 7;
+#pragma unroll
+    for (int i = 0; i < I8_DIG; ++i) {
+        signed char* dst = G + gbase + ((((long long)blk * T + s) * I8_DIG + i) * (long long)I8_B_BYTES) +
+                           ((cc * 8 + r1) * 8 + r0) * 16;
+        *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(d[i]);
+    }
+}
+
+// ------------------------------------------------------------------------------------------ main kernel
+__device__ __forceinline__ unsigned i8_smem_u32(const void* p) { return static_cast<unsigned>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void i8_mbar_init(unsigned bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void i8_mbar_arrive(unsigned bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void i8_mbar_expect_tx(unsigned bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void i8_mbar_wait(unsigned bar, unsigned parity) {
+    unsigned ok;
+    do {
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+                     : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void i8_bulk_g2s(unsigned dst, const void* src, unsigned bytes, unsigned bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+// K-major, no swizzle: uint128 offset of (row r0 + 8 r1, chunk c) = r0 + r1*SBO + c*LBO   (cute mma_traits_sm100.hpp)
+__device__ __forceinline__ unsigned long long i8_desc(unsigned smem_addr, unsigned lbo_bytes, unsigned sbo_bytes) {
+    unsigned long long d = 0;
+    d |= (unsigned long long)((smem_addr >> 4) & 0x3FFFu);
+    d |= (unsigned long long)((lbo_bytes >> 4) & 0x3FFFu) << 16;
+    d |= (unsigned long long)((sbo_bytes >> 4) & 0x3FFFu) << 32;
+    d |= 1ull << 46;                                  // descriptor version (Blackwell)
+    return d;                                         // base_offset 0, lbo_mode 0, layout_type 0 = SWIZZLE_NONE
+}
+__device__ __forceinline__ void i8_mma(unsigned tmem_d, unsigned long long da, unsigned long long db, unsigned idesc,
+                                       unsigned accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n"
+        "}\n"
+        ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate), "r"(0u)
+        : "memory");
+}
+__device__ __forceinline__ void i8_commit(unsigned bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void i8_tmem_ld8(unsigned taddr, int (&v)[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                 : "r"(taddr) : "memory");
+}
+
+template <int T>
+__global__ void __launch_bounds__(I8_THREADS, 1) i8_contract_kernel(const I8Params p) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    unsigned char* stage0 = smem;
+    unsigned long long* bars = reinterpret_cast<unsigned long long*>(smem + I8_STAGES * I8_STAGE_BYTES);
+    unsigned* tmem_slot = reinterpret_cast<unsigned*>(bars + 2 * I8_STAGES + 2);
+    const unsigned full0 = i8_smem_u32(bars), empty0 = i8_smem_u32(bars + I8_STAGES);
+    const unsigned accfull = i8_smem_u32(bars + 2 * I8_STAGES), accempty = i8_smem_u32(bars + 2 * I8_STAGES + 1);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long X = blockIdx.x;
+    const int split = blockIdx.y;
+    const int jt_begin = p.split_begin[split], jt_end = p.split_begin[split + 1];
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < I8_STAGES; ++s) { i8_mbar_init(full0 + 8 * s, 1); i8_mbar_init(empty0 + 8 * s, 1); }
+        i8_mbar_init(accfull, 1);
+        i8_mbar_init(accempty, 4);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 4) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(i8_smem_u32(tmem_slot)), "r"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const unsigned tmem_base = *tmem_slot;
+
+    if (warp == 4) {
+        // ------------------------------------------------------------------ producer (one lane)
+        if (lane == 0) {
+            unsigned it = 0;
+            for (int jt = jt_begin; jt < jt_end; ++jt) {
+                const RowTile tile = p.jtiles[jt];
+                const ChromDesc cd = p.chrom[tile.c];
+                const int J = tile.I;
+                const int nkb = min(J + 1, (cd.m + I8_KB - 1) / I8_KB);
+                const signed char* abase = p.xi + (X * p.nkb_total + (cd.pad_off >> 6)) * (long long)I8_A_BYTES;
+                const signed char* gb = p.G + p.gbase[tile.c] + ((long long)(J * (J + 1) / 2) * T) * (I8_DIG * (long long)I8_B_BYTES);
+                for (int s = 0; s < T; ++s)
+                    for (int kb = 0; kb < nkb; ++kb, ++it) {
+                        const unsigned slot = it % I8_STAGES, ph = (it / I8_STAGES) & 1u;
+                        i8_mbar_wait(empty0 + 8 * slot, ph ^ 1u);
+                        const unsigned dst = i8_smem_u32(stage0 + slot * I8_STAGE_BYTES);
+                        i8_mbar_expect_tx(full0 + 8 * slot, I8_STAGE_BYTES);
+                        i8_bulk_g2s(dst, abase + (long long)kb * I8_A_BYTES, I8_A_BYTES, full0 + 8 * slot);
+                        i8_bulk_g2s(dst + I8_A_BYTES, gb + ((long long)kb * T + s) * (I8_DIG * (long long)I8_B_BYTES),
+                                    I8_DIG * I8_B_BYTES, full0 + 8 * slot);
+                    }
+            }
+        }
+    } else if (warp == 5) {
+        // ------------------------------------------------------------------ MMA issuer (one lane)
+        if (lane == 0) {
+            // instruction descriptor: D = S32, A = B = signed 8 bit, K-major both, N = 64, M = 128
+            const unsigned idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((unsigned)(I8_N >> 3) << 17) | ((unsigned)(I8_M >> 4) << 24);
+            unsigned it = 0, acc_it = 0;
+            for (int jt = jt_begin; jt < jt_end; ++jt) {
+                const RowTile tile = p.jtiles[jt];
+                const ChromDesc cd = p.chrom[tile.c];
+                const int nkb = min(tile.I + 1, (cd.m + I8_KB - 1) / I8_KB);
+                for (int s = 0; s < T; ++s, ++acc_it) {
+                    i8_mbar_wait(accempty, (acc_it & 1u) ^ 1u);           // epilogue has drained the accumulators
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    for (int kb = 0; kb < nkb; ++kb, ++it) {
+                        const unsigned slot = it % I8_STAGES, ph = (it / I8_STAGES) & 1u;
+                        i8_mbar_wait(full0 + 8 * slot, ph);
+                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                        const unsigned a0 = i8_smem_u32(stage0 + slot * I8_STAGE_BYTES);
+                        const unsigned b0 = a0 + I8_A_BYTES;
+#pragma unroll
+                        for (int kk = 0; kk < I8_KB / 32; ++kk) {
+                            const unsigned long long da = i8_desc(a0 + kk * 2 * (I8_M * 16), I8_M * 16, 128);
+#pragma unroll
+                            for (int i = 0; i < I8_DIG; ++i) {
+                                const unsigned long long db = i8_desc(b0 + i * I8_B_BYTES + kk * 2 * (I8_N * 16), I8_N * 16, 128);
+                                i8_mma(tmem_base + i * I8_N, da, db, idesc, (kb | kk) != 0);
+                            }
+                        }
+                        i8_commit(empty0 + 8 * slot);                     // frees the smem slot when these MMAs retire
+                    }
+                    i8_commit(accfull);                                    // accumulators of trait s are complete
+                }
+            }
+        }
+    } else {
+        // ------------------------------------------------------------------ epilogue: thread = one cross
+        const long long unit = X * I8_M + warp * 32 + lane;
+        const bool live = unit < p.n_units;
+        int pa = 0, pb = 0;
+        if (live) { pa = p.unit_a[unit]; pb = (p.mode == MASK_XI) ? p.unit_b[unit] : 0; }
+        double Z[T][T];
+#pragma unroll
+        for (int t = 0; t < T; ++t)
+#pragma unroll
+            for (int s = 0; s < T; ++s) Z[t][s] = 0.0;
+        const unsigned tlane = tmem_base + ((unsigned)(warp * 32) << 16);
+        unsigned acc_it = 0;
+        for (int jt = jt_begin; jt < jt_end; ++jt) {
+            const RowTile tile = p.jtiles[jt];
+            const ChromDesc cd = p.chrom[tile.c];
+            const long long prow = (long long)cd.pad_off + 64 * tile.I;      // padded index of the tile's first row
+            unsigned nz[2] = {0u, 0u}, ng[2] = {0u, 0u};
+            if (live) {
+#pragma unroll
+                for (int w = 0; w < 2; ++w) {
+                    const long long wi = (prow >> 5) + w;
+                    const unsigned A = __ldg(p.planeA + (long long)pa * p.wpp + wi), B = __ldg(p.planeB + (long long)pa * p.wpp + wi);
+                    if (p.mode == MASK_XI) {
+                        const unsigned A2 = __ldg(p.planeA + (long long)pb * p.wpp + wi), B2 = __ldg(p.planeB + (long long)pb * p.wpp + wi);
+                        nz[w] = (A ^ B) & (A2 ^ B2);
+                        ng[w] = ((~A & B) ^ (~A2 & B2)) & nz[w];
+                    } else {
+                        nz[w] = A ^ B;
+                        ng[w] = (p.mode == MASK_DELTA) ? (~A & B) : 0u;
+                    }
+                }
+            }
+#pragma unroll
+            for (int s = 0; s < T; ++s, ++acc_it) {               // unrolled: Z[t][s] must stay in registers
+                i8_mbar_wait(accfull, acc_it & 1u);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll 1
+                for (int cb = 0; cb < I8_N / 8; ++cb) {                      // 8 SNP rows at a time
+                    int dig[I8_DIG][8];
+#pragma unroll
+                    for (int i = 0; i < I8_DIG; ++i) i8_tmem_ld8(tlane + i * I8_N + cb * 8, dig[i]);
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    if (cb == I8_N / 8 - 1) {                               // TMEM fully read: let the next trait's MMAs start
+                        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                        __syncwarp();
+                        if (lane == 0) i8_mbar_arrive(accempty);
+                    }
+                    const unsigned nzw = nz[cb >> 2] >> (8 * (cb & 3)), ngw = ng[cb >> 2] >> (8 * (cb & 3));
+                    const double* erow = p.emat + prow + cb * 8;
+                    const double* srow = p.scale + (long long)s * p.mp_total + prow + cb * 8;
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) {
+                        // sum_i S_i 128^-(i+1): pairs of digits combined exactly in int32, then 4 exact int->fp64 terms
+                        const int w0 = dig[0][c] * 128 + dig[1][c], w1 = dig[2][c] * 128 + dig[3][c];
+                        const int w2 = dig[4][c] * 128 + dig[5][c], w3 = dig[6][c];
+                        double v = (double)w3 * 0x1p-49;
+                        v = fma((double)w2, 0x1p-42, v);
+                        v = fma((double)w1, 0x1p-28, v);
+                        v = fma((double)w0, 0x1p-14, v);
+                        v *= __ldg(srow + c);                          // exact power-of-two row scale
+                        long long bits = __double_as_longlong(v);
+                        if (!((nzw >> c) & 1u)) bits = 0ll;
+                        bits ^= (long long)((ngw >> c) & 1u) << 63;
+                        v = __longlong_as_double(bits);
+#pragma unroll
+                        for (int t = 0; t < T; ++t) Z[t][s] = fma(__ldg(erow + (long long)t * p.mp_total + c), v, Z[t][s]);
+                    }
+                }
+            }
+        }
+        if (live) {
+            double* out = p.Zpart + ((long long)split * p.n_units + unit) * (T * T);
+#pragma unroll
+            for (int t = 0; t < T; ++t)
+#pragma unroll
+                for (int s = 0; s < T; ++s) out[t * T + s] = Z[t][s];
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 4) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+    }
+}
+
+size_t i8_smem_bytes() { return (size_t)I8_STAGES * I8_STAGE_BYTES + (2 * I8_STAGES + 2) * 8 + 16; }
+
+cudaError_t launch_i8_build_xi(const unsigned* planeA, const unsigned* planeB, long long wpp, const int* sire,
+                               const int* dam, long long n_units, int mode, long long nkb_total, signed char* xi,
+                               cudaStream_t st) {
+    const long long npad = (n_units + I8_M - 1) / I8_M * I8_M;
+    const long long total = npad * nkb_total * 4;
+    if (total == 0) return cudaSuccess;
+    i8_build_xi_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(planeA, planeB, wpp, sire, dam, n_units, mode,
+                                                                         nkb_total, xi);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_i8_build_digits(const double* tiles, const ChromDesc* chrom_d, const ChromDesc& cd, int c,
+                                   const double* emat, long long mp_total, int T, double* scale, long long gbase,
+                                   signed char* G, cudaStream_t st) {
+    const int nJ = (cd.m + 63) / 64;
+    dim3 g1(nJ * 64, T);
+    i8_rowscale_kernel<<<g1, 128, 0, st>>>(tiles, chrom_d, c, emat, mp_total, T, scale);
+    dim3 g2(nJ * (nJ + 1) / 2, T);
+    i8_build_digits_kernel<<<g2, 256, 0, st>>>(tiles, chrom_d, c, emat, mp_total, T, scale, gbase, G);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_i8_contract(const I8Params& p, int ntiles, int nsplit, cudaStream_t st) {
+    if (ntiles == 0) return cudaSuccess;
+    const size_t smem = i8_smem_bytes();
+    dim3 grid(ntiles, nsplit);
+    cudaError_t e = cudaSuccess;
+#define GMS_I8(TV)                                                                                                  \
+    case TV:                                                                                                        \
+        e = cudaFuncSetAttribute(i8_contract_kernel<TV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);   \
+        if (e != cudaSuccess) return e;                                                                             \
+        i8_contract_kernel<TV><<<grid, I8_THREADS, smem, st>>>(p);                                                  \
+        break;
+    switch (p.T) {
+        GMS_I8(1) GMS_I8(2) GMS_I8(3) GMS_I8(4) GMS_I8(5) GMS_I8(6)
+        default: return cudaErrorInvalidValue;
+    }
+#undef GMS_I8
+    return cudaGetLastError();
+}
+
+}  // namespace gms

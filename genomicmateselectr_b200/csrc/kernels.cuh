@@ -44,6 +44,37 @@ cudaError_t launch_scan_prepare(const double* emat, const double* apos, const do
                                 double* S, cudaStream_t st);
 cudaError_t launch_scan(const ScanParams& p, int nsplit, cudaStream_t st);
 
+// ---- exact int8 tensor-core path for the per-cross term (i8path.cu) ----
+struct I8Params {
+    const ChromDesc* chrom;
+    const RowTile* jtiles;       // (c, J): 64-row tiles of the lower block triangle, ordered by (c, J)
+    const int* split_begin;      // [nsplit + 1] ranges of jtiles
+    const signed char* xi;       // [X tile][global 64-k block][8 KiB image]
+    long long nkb_total;         // mp_total / 64
+    const signed char* G;        // digit images
+    const long long* gbase;      // [C] byte offset of each chromosome's digit images
+    const double* scale;         // [T][mp_total] power-of-two row scales
+    const double* emat;          // [T][mp_total] effects that multiply the rows (d_t[j])
+    long long mp_total;
+    const unsigned* planeA;
+    const unsigned* planeB;
+    long long wpp;
+    const int* unit_a;
+    const int* unit_b;
+    long long n_units;
+    int T;
+    int mode;
+    double* Zpart;               // [nsplit][n_units][T*T]
+};
+size_t i8_smem_bytes();
+cudaError_t launch_i8_build_xi(const unsigned* planeA, const unsigned* planeB, long long wpp, const int* sire,
+                               const int* dam, long long n_units, int mode, long long nkb_total, signed char* xi,
+                               cudaStream_t st);
+cudaError_t launch_i8_build_digits(const double* tiles, const ChromDesc* chrom_d, const ChromDesc& cd, int c,
+                                   const double* emat, long long mp_total, int T, double* scale, long long gbase,
+                                   signed char* G, cudaStream_t st);
+cudaError_t launch_i8_contract(const I8Params& p, int ntiles, int nsplit, cudaStream_t st);
+
 // Nsegsnps per cross over words [w_begin, w_end) of the padded axis.
 cudaError_t launch_nseg(const unsigned* planeA, const unsigned* planeB, long long wpp, long long w_begin,
                         long long w_end, const int* sire, const int* dam, long long N, int* nseg, cudaStream_t st);

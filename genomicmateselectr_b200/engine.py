@@ -113,7 +113,7 @@ class CrossVarEngine:
     def set_mode(self, mode):
         """"dense" (default: FP64 tensor contraction, any symmetric recombFreqMat) or "map_scan"
         (map-structured prefix-sum fast path; needs set_genmap() with sorted positions)."""
-        code = {"dense": 0, "map_scan": 1}[mode] if isinstance(mode, str) else int(mode)
+        code = {"dense": 0, "map_scan": 1, "int8_tensor": 2}[mode] if isinstance(mode, str) else int(mode)
         self._ck(self._lib.gms_set_mode(self._h, code))
 
     def set_chromosome_shard(self, c_begin, c_end):

@@ -88,8 +88,12 @@ GMS_API int gms_set_haplotypes_u8rm(gms_handle* h, int64_t P, int64_t m, const u
  * fast path: when the blocks came from gms_set_genmap() with positions sorted within each
  * chromosome, R[j,k] = exp(-2|x_j-x_k|/100) factorises and every quadratic form becomes a prefix-sum
  * scan over the non-zero SNPs of a unit (O(m T^2) per cross instead of O(m^2 T)); same results to ~1e-13.
- * Returns GMS_ESTATE if the handle's blocks did not come from a sorted map. */
-enum { GMS_MODE_DENSE = 0, GMS_MODE_MAP_SCAN = 1 };
+ * Returns GMS_ESTATE if the handle's blocks did not come from a sorted map.
+ * GMS_MODE_INT8_TENSOR (any symmetric matrix, AD / DirDom, T <= 6): the per-cross dominance contraction runs
+ * on the int8 tcgen05 tensor cores - RoR.d is split into 7 exact radix-128 int8 digit planes, xi is ternary,
+ * int32 accumulation in TMEM is exact, digits are recombined in FP64 (error <= 2^-49 of the row maximum).
+ * The per-parent tables still use the FP64 contraction. Falls back to GMS_MODE_DENSE for T > 6. */
+enum { GMS_MODE_DENSE = 0, GMS_MODE_MAP_SCAN = 1, GMS_MODE_INT8_TENSOR = 2 };
 GMS_API int gms_set_mode(gms_handle* h, int mode);
 
 /* Optional chromosome shard: this handle only sums over chromosomes [c_begin, c_end).  Outputs of

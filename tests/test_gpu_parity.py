@@ -336,3 +336,46 @@ def test_predict_sharded_one_process(gms):
         gms.CrossVarEngine.predict_sharded(engines, "AD", s["add"], s["dom"], None, sire, bad)
     for e in engines:
         e.close()
+
+
+# ---------------------------------------------------------------- exact int8 tensor-core path (tcgen05)
+@pytest.mark.parametrize("model,T", [("AD", 1), ("AD", 2), ("AD", 5), ("DirDom", 3), ("AD", 6)])
+def test_int8_tensor_mode_matches_oracle_and_dense(gms, model, T):
+    s = synth(500 + T, [200, 131, 77, 300], P=24, T=T)
+    rng = np.random.default_rng(8)
+    sire = rng.integers(0, 24, 150).astype(np.int32)
+    dam = rng.integers(0, 24, 150).astype(np.int32)
+    sire[:5] = dam[:5]
+    asub = s["asub"] if model == "DirDom" else None
+    eng = gms.CrossVarEngine(0)
+    eng.set_genmap(s["cM"], s["m_c"])
+    eng.set_haplotypes(s["H"])
+    dense, nseg_d = eng.predict(model, s["add"], s["dom"], asub, sire, dam)
+    eng.set_mode("int8_tensor")
+    out, nseg = eng.predict(model, s["add"], s["dom"], asub, sire, dam)
+    want, wseg = oracle_slab(model, s["H"], s["R"], s["add"], s["dom"], asub, sire, dam)
+    assert np.array_equal(nseg, wseg)
+    assert rel_err(dense, want) < TOL
+    assert rel_err(out, want) < TOL
+    assert rel_err(out, dense) < TOL
+    eng.close()
+
+
+def test_int8_tensor_general_matrix_and_many_tiles(gms):
+    """A non-map (one block) matrix and > 128 crosses x several 64-row tiles."""
+    rng = np.random.default_rng(13)
+    m, P, T = 330, 30, 4
+    B = rng.standard_normal((m, 40))
+    R = B @ B.T / 40
+    H = (rng.random((2 * P, m)) < 0.4).astype(np.uint8)
+    add, dom = rng.standard_normal((m, T)), rng.standard_normal((m, T)) * np.exp(rng.normal(0, 2, (m, 1)))
+    sire = rng.integers(0, P, 300).astype(np.int32)
+    dam = rng.integers(0, P, 300).astype(np.int32)
+    eng = gms.CrossVarEngine(0)
+    eng.set_recomb_matrix(R, np.ones(m, int))
+    eng.set_haplotypes(H)
+    eng.set_mode("int8_tensor")
+    out, nseg = eng.predict("AD", add, dom, None, sire, dam)
+    want, wseg = oracle_slab("AD", H, R, add, dom, None, sire, dam)
+    assert np.array_equal(nseg, wseg) and rel_err(out, want) < TOL
+    eng.close()
