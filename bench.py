@@ -326,33 +326,44 @@ def main():
                         "block triangle of the symmetric RoR blocks (x0.585 incl. padding), so frac can exceed 1",
                 "kernel_ms": k_ms, "kernel_share_of_step": k_ms / float(np.mean([s[3] for s in stage_ms]))}
 
-    # ---- optional map-structured fast path: same inputs, same outputs, prefix-sum scan
-    map_scan = None
-    try:
-        eng.set_mode("map_scan")
-        eng.stage(args.model, d["add"], dom, asub, sire, dam)
-        for _ in range(args.warmup):
-            eng.compute(sync=True)
-        barrier()
-        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        f0.record(stream)
-        for _ in range(args.steps):
-            eng.compute(sync=False)
-        f1.record(stream)
-        barrier()
-        ms_scan = max_over_ranks(f0.elapsed_time(f1))
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(args.steps):
-            e2e_step()
-        barrier()
-        scan_e2e_s = max_over_ranks(time.perf_counter() - t0)
-        map_scan = {"value": n_total * args.steps / (ms_scan * 1e-3), "unit": UNIT, "ms_per_step": ms_scan / args.steps,
-                    "e2e": n_total * args.steps / scan_e2e_s,
-                    "note": "gms_set_mode(GMS_MODE_MAP_SCAN): valid only for map-derived recombFreqMat; not the headline"}
+    # ---- optional modes on the same inputs / outputs (not the headline):
+    #   int8_tensor: exact int8 tcgen05 evaluation of the per-cross term, any symmetric matrix
+    #   map_scan   : map-structured prefix-sum fast path, map-derived matrices only
+    def run_mode(mode, note):
+        try:
+            eng.set_mode(mode)
+            eng.stage(args.model, d["add"], dom, asub, sire, dam)
+            for _ in range(args.warmup):
+                eng.compute(sync=True)
+            barrier()
+            f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            f0.record(stream)
+            for _ in range(args.steps):
+                eng.compute(sync=False)
+            f1.record(stream)
+            barrier()
+            ms_m = max_over_ranks(f0.elapsed_time(f1))
+            kms = []
+            for _ in range(args.steps):
+                eng.compute(sync=True)
+                kms.append(eng.stats()["last_ms_cross_kernel"])
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(args.steps):
+                e2e_step()
+            barrier()
+            e2e_m = max_over_ranks(time.perf_counter() - t0)
+            res = {"value": n_total * args.steps / (ms_m * 1e-3), "unit": UNIT, "ms_per_step": ms_m / args.steps,
+                   "cross_kernel_ms": float(np.mean(kms)), "e2e": n_total * args.steps / e2e_m, "note": note}
+        except Exception as exc:   # the headline path must not depend on the optional ones
+            res = {"error": str(exc)}
         eng.set_mode("dense")
-    except Exception as exc:   # the headline path must not depend on the optional one
-        map_scan = {"error": str(exc)}
+        return res
+
+    int8_tensor = run_mode("int8_tensor", "gms_set_mode(GMS_MODE_INT8_TENSOR): tcgen05 kind::i8, exact digit planes; "
+                           "e2e includes building the digit / xi images every call; not the headline") \
+        if args.model != "A" else None
+    map_scan = run_mode("map_scan", "gms_set_mode(GMS_MODE_MAP_SCAN): valid only for map-derived recombFreqMat; not the headline")
 
     if rank == 0:
         cpu = None
@@ -367,7 +378,7 @@ def main():
                 "stages_ms": {"parent_tables": float(np.mean([s[0] for s in stage_ms])),
                               "cross_term": float(np.mean([s[1] for s in stage_ms])),
                               "assemble_nseg": float(np.mean([s[2] for s in stage_ms]))},
-                "map_scan": map_scan, "setup_s": setup_s, "hbm_tile_bytes": int(st["tile_bytes"]),
+                "int8_tensor": int8_tensor, "map_scan": map_scan, "setup_s": setup_s, "hbm_tile_bytes": int(st["tile_bytes"]),
                 "measured_peaks": {"hbm_gbs": pk.get("hbm_gbs"), "fp64_dgemm_tflops": fp64_peak}}
         emit(line)
     eng.close()

@@ -84,10 +84,10 @@ struct gms_handle {
     DevBuf<RowTile> jtiles_d;
     std::vector<long long> gbase;
     DevBuf<long long> gbase_d;
-    DevBuf<signed char> xi_d, G_d;
-    DevBuf<double> scale_d;
-    DevBuf<int> split_i8_d;
-    Plan plan_i8;
+    DevBuf<signed char> xi_d, xi_het_d, xi_delta_d, G_d, G_add_d, G_asub_d;
+    DevBuf<double> scale_d, scale_add_d, scale_asub_d;
+    DevBuf<int> split_i8_d, split_i8_par_d;
+    Plan plan_i8, plan_i8_par;
     bool use_i8 = false;
 
     // map-structured fast path
@@ -360,6 +360,8 @@ void gms_destroy(gms_handle* h) {
     h->gebv_d.release(); h->mean_d.release(); h->scan_ab.release(); h->S_add.release(); h->S_dom.release();
     h->S_asub.release(); h->split_scan_par_d.release(); h->split_scan_x_d.release();
     h->jtiles_d.release(); h->gbase_d.release(); h->xi_d.release(); h->G_d.release(); h->scale_d.release(); h->split_i8_d.release();
+    h->xi_het_d.release(); h->xi_delta_d.release(); h->G_add_d.release(); h->G_asub_d.release(); h->scale_add_d.release();
+    h->scale_asub_d.release(); h->split_i8_par_d.release();
     for (auto& ev : h->ev) if (ev) cudaEventDestroy(ev);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     delete h;
@@ -629,52 +631,66 @@ int gms_stage_inputs(gms_handle* h, int model, int T, const double* add, const d
         CU(h->gbase_d.ensure(h->C));
         CU(cudaMemcpyAsync(h->jtiles_d.p, h->jtiles.data(), sizeof(RowTile) * h->jtiles.size(), cudaMemcpyHostToDevice, h->stream));
         CU(cudaMemcpyAsync(h->gbase_d.p, h->gbase.data(), sizeof(long long) * h->C, cudaMemcpyHostToDevice, h->stream));
-        CU(h->G_d.ensure((size_t)gb));
-        CU(h->scale_d.ensure((size_t)h->mp_total * T));
-        CU(cudaMemsetAsync(h->scale_d.p, 0, sizeof(double) * h->mp_total * T, h->stream));
-        for (int c = h->c_begin; c < h->c_end; ++c)
-            CU(launch_i8_build_digits(h->R2.p, h->chrom_d.p, h->chrom[c], c, h->emat_dom.p, h->mp_total, T, h->scale_d.p,
-                                      h->gbase[c], h->G_d.p, h->stream));
-        const long long npad = (N + 127) / 128 * 128;
+        // digit planes: (RoR, dom) for the dominance terms, (R, add) [and (R, asub)] for the additive tables
+        auto digits = [&](const double* tiles, const double* emat, DevBuf<signed char>& G, DevBuf<double>& sc) -> int {
+            CU(G.ensure((size_t)gb));
+            CU(sc.ensure((size_t)h->mp_total * T));
+            CU(cudaMemsetAsync(sc.p, 0, sizeof(double) * h->mp_total * T, h->stream));
+            for (int c = h->c_begin; c < h->c_end; ++c)
+                CU(launch_i8_build_digits(tiles, h->chrom_d.p, h->chrom[c], c, emat, h->mp_total, T, sc.p, h->gbase[c], G.p, h->stream));
+            return GMS_OK;
+        };
+        if (int rc = digits(h->R2.p, h->emat_dom.p, h->G_d, h->scale_d)) return rc;
+        if (int rc = digits(h->R.p, h->emat_add.p, h->G_add_d, h->scale_add_d)) return rc;
+        if (model == GMS_MODEL_DIRDOM) if (int rc = digits(h->R.p, h->emat_asub.p, h->G_asub_d, h->scale_asub_d)) return rc;
+        // mask images: crosses (xi), parents (het and delta)
+        const long long npad = (N + 127) / 128 * 128, ppad = (h->nP + 127) / 128 * 128;
         CU(h->xi_d.ensure((size_t)npad * h->mp_total));
-        CU(launch_i8_build_xi(h->planeA.p, h->planeB.p, h->wpp, h->sire_d.p, h->dam_d.p, N, MASK_XI, h->mp_total / 64,
-                              h->xi_d.p, h->stream));
-        // plan: contiguous ranges of jtiles of equal work (weight J + 1)
-        Plan& pl = h->plan_i8;
-        pl.ntiles = (int)(npad / 128);
-        const int njt = (int)h->jtiles.size();
-        int ns = 1;
-        if (pl.ntiles < 2 * h->num_sms) ns = (2 * h->num_sms + pl.ntiles - 1) / pl.ntiles;
-        else {
-            double best = 1e30;
-            for (int cand = 1; cand <= 8; ++cand) {
-                const double ctas = (double)pl.ntiles * cand, waves = std::ceil(ctas / h->num_sms);
-                const double cost = waves * h->num_sms / ctas * (1.0 + 0.01 * (cand - 1));
-                if (cost < best - 1e-12) { best = cost; ns = cand; }
+        CU(h->xi_het_d.ensure((size_t)ppad * h->mp_total));
+        CU(h->xi_delta_d.ensure((size_t)ppad * h->mp_total));
+        CU(launch_i8_build_xi(h->planeA.p, h->planeB.p, h->wpp, h->sire_d.p, h->dam_d.p, N, MASK_XI, h->mp_total / 64, h->xi_d.p, h->stream));
+        CU(launch_i8_build_xi(h->planeA.p, h->planeB.p, h->wpp, h->plist_d.p, nullptr, h->nP, MASK_HET, h->mp_total / 64, h->xi_het_d.p, h->stream));
+        CU(launch_i8_build_xi(h->planeA.p, h->planeB.p, h->wpp, h->plist_d.p, nullptr, h->nP, MASK_DELTA, h->mp_total / 64, h->xi_delta_d.p, h->stream));
+        // plans: contiguous ranges of jtiles of equal work (weight J + 1)
+        auto i8plan = [&](long long units, Plan& pl, DevBuf<int>& dev) -> int {
+            pl.ntiles = (int)((units + 127) / 128);
+            const int njt = (int)h->jtiles.size();
+            int ns = 1;
+            if (pl.ntiles < 2 * h->num_sms) ns = (2 * h->num_sms + pl.ntiles - 1) / std::max(1, pl.ntiles);
+            else {
+                double best = 1e30;
+                for (int cand = 1; cand <= 8; ++cand) {
+                    const double ctas = (double)pl.ntiles * cand, waves = std::ceil(ctas / h->num_sms);
+                    const double cost = waves * h->num_sms / ctas * (1.0 + 0.01 * (cand - 1));
+                    if (cost < best - 1e-12) { best = cost; ns = cand; }
+                }
             }
-        }
-        ns = std::max(1, std::min(ns, njt));
-        pl.nsplit = ns;
-        pl.split_begin.assign(ns + 1, 0);
-        double total = 0, acc = 0;
-        for (const RowTile& r : h->jtiles) total += r.I + 1;
-        int sp = 1;
-        for (int i = 0; i < njt && sp < ns; ++i) {
-            acc += h->jtiles[i].I + 1;
-            while (sp < ns && acc >= total * sp / ns && (njt - (i + 1)) >= (ns - sp)) pl.split_begin[sp++] = i + 1;
-        }
-        for (; sp < ns; ++sp) pl.split_begin[sp] = std::max(pl.split_begin[sp - 1], njt - (ns - sp));
-        pl.split_begin[ns] = njt;
-        for (int i = 1; i <= ns; ++i) pl.split_begin[i] = std::max(pl.split_begin[i], pl.split_begin[i - 1]);
-        CU(h->split_i8_d.ensure(pl.split_begin.size()));
-        CU(cudaMemcpyAsync(h->split_i8_d.p, pl.split_begin.data(), sizeof(int) * pl.split_begin.size(), cudaMemcpyHostToDevice, h->stream));
+            ns = std::max(1, std::min(ns, njt));
+            pl.nsplit = ns;
+            pl.split_begin.assign(ns + 1, 0);
+            double total = 0, acc = 0;
+            for (const RowTile& r : h->jtiles) total += r.I + 1;
+            int sp = 1;
+            for (int i = 0; i < njt && sp < ns; ++i) {
+                acc += h->jtiles[i].I + 1;
+                while (sp < ns && acc >= total * sp / ns && (njt - (i + 1)) >= (ns - sp)) pl.split_begin[sp++] = i + 1;
+            }
+            for (; sp < ns; ++sp) pl.split_begin[sp] = std::max(pl.split_begin[sp - 1], njt - (ns - sp));
+            pl.split_begin[ns] = njt;
+            for (int i = 1; i <= ns; ++i) pl.split_begin[i] = std::max(pl.split_begin[i], pl.split_begin[i - 1]);
+            CU(dev.ensure(pl.split_begin.size()));
+            CU(cudaMemcpyAsync(dev.p, pl.split_begin.data(), sizeof(int) * pl.split_begin.size(), cudaMemcpyHostToDevice, h->stream));
+            return GMS_OK;
+        };
+        if (int rc = i8plan(N, h->plan_i8, h->split_i8_d)) return rc;
+        if (int rc = i8plan(h->nP, h->plan_i8_par, h->split_i8_par_d)) return rc;
     }
     size_t zneed = std::max<size_t>((size_t)h->plan_par.nsplit * (size_t)h->nP * TT,
                                     model >= GMS_MODEL_AD ? (size_t)h->plan_x.nsplit * (size_t)N * TT : (size_t)0);
     if (h->mode == GMS_MODE_MAP_SCAN)
         zneed = std::max<size_t>((h->scan_split_par.size() - 1) * (size_t)h->nP * TT,
                                  model >= GMS_MODEL_AD ? (h->scan_split_x.size() - 1) * (size_t)N * TT : (size_t)0);
-    if (h->use_i8) zneed = std::max<size_t>(zneed, (size_t)h->plan_i8.nsplit * (size_t)N * TT);
+    if (h->use_i8) zneed = std::max<size_t>(zneed, std::max<size_t>((size_t)2 * h->plan_i8.nsplit * (size_t)N * TT, (size_t)2 * h->plan_i8_par.nsplit * (size_t)h->nP * TT));
     CU(h->Z.ensure(zneed));
     CU(h->QA.ensure((size_t)h->nP * TT));
     if (model >= GMS_MODEL_AD) { CU(h->PD.ensure((size_t)h->nP * TT)); CU(h->X.ensure((size_t)N * TT)); }
@@ -707,6 +723,36 @@ int gms_compute(gms_handle* h, int sync) {
         if (h->model >= GMS_MODEL_AD)
             if (int rc = run_scan(h, h->S_dom.p, MASK_XI, h->sire_d.p, h->dam_d.p, h->N, h->scan_split_x,
                                   h->split_scan_x_d.p, h->X.p, h->ev[4], h->ev[5])) return rc;
+    } else if (h->use_i8) {
+        // exact int8 tcgen05 evaluation of all four tables (i8path.cu)
+        auto run_i8 = [&](const signed char* G, const double* scale, const signed char* xi, const double* emat, int mode,
+                          const int* ua, const int* ub, long long n_units, const Plan& pl, const int* split_d, double* Xout,
+                          cudaEvent_t e0, cudaEvent_t e1) -> int {
+            if (n_units == 0) return GMS_OK;
+            I8Params ip{};
+            ip.chrom = h->chrom_d.p; ip.jtiles = h->jtiles_d.p; ip.split_begin = split_d;
+            ip.xi = xi; ip.nkb_total = h->mp_total / 64; ip.G = G; ip.gbase = h->gbase_d.p;
+            ip.scale = scale; ip.emat = emat; ip.mp_total = h->mp_total;
+            ip.planeA = h->planeA.p; ip.planeB = h->planeB.p; ip.wpp = h->wpp;
+            ip.unit_a = ua; ip.unit_b = ub; ip.n_units = n_units; ip.T = h->T; ip.mode = mode;
+            ip.Zpart = h->Z.p;
+            if (e0) CU(cudaEventRecord(e0, h->stream));
+            CU(launch_i8_contract(ip, pl.ntiles, pl.nsplit, h->stream));
+            if (e1) CU(cudaEventRecord(e1, h->stream));
+            CU(launch_finalize_sym(h->Z.p, 2 * pl.nsplit, n_units, h->T, Xout, h->stream, true));
+            h->st.last_launches += 2;
+            return GMS_OK;
+        };
+        if (int rc = run_i8(h->G_add_d.p, h->scale_add_d.p, h->xi_delta_d.p, h->emat_add.p, MASK_DELTA, h->plist_d.p, nullptr,
+                            h->nP, h->plan_i8_par, h->split_i8_par_d.p, h->QA.p, nullptr, nullptr)) return rc;
+        if (int rc = run_i8(h->G_d.p, h->scale_d.p, h->xi_het_d.p, h->emat_dom.p, MASK_HET, h->plist_d.p, nullptr,
+                            h->nP, h->plan_i8_par, h->split_i8_par_d.p, h->PD.p, nullptr, nullptr)) return rc;
+        if (h->model == GMS_MODEL_DIRDOM)
+            if (int rc = run_i8(h->G_asub_d.p, h->scale_asub_d.p, h->xi_delta_d.p, h->emat_asub.p, MASK_DELTA, h->plist_d.p, nullptr,
+                                h->nP, h->plan_i8_par, h->split_i8_par_d.p, h->QB.p, nullptr, nullptr)) return rc;
+        CU(cudaEventRecord(h->ev[1], h->stream));
+        if (int rc = run_i8(h->G_d.p, h->scale_d.p, h->xi_d.p, h->emat_dom.p, MASK_XI, h->sire_d.p, h->dam_d.p,
+                            h->N, h->plan_i8, h->split_i8_d.p, h->X.p, h->ev[4], h->ev[5])) return rc;
     } else {
         // per-parent tables: Q_P = (a o delta_P)' R (a o delta_P), P_P = (d o het_P)' RoR (d o het_P)
         if (int rc = run_contract(h, h->R.p, h->emat_add.p, MASK_DELTA, h->plist_d.p, nullptr, h->nP, h->plan_par,
@@ -719,20 +765,7 @@ int gms_compute(gms_handle* h, int sync) {
                                       h->split_par_d.p, h->QB.p)) return rc;
         CU(cudaEventRecord(h->ev[1], h->stream));
         // per-cross dominance term X = (d o xi)' RoR (d o xi), xi = delta_sire o delta_dam
-        if (h->use_i8) {
-            I8Params ip{};
-            ip.chrom = h->chrom_d.p; ip.jtiles = h->jtiles_d.p; ip.split_begin = h->split_i8_d.p;
-            ip.xi = h->xi_d.p; ip.nkb_total = h->mp_total / 64; ip.G = h->G_d.p; ip.gbase = h->gbase_d.p;
-            ip.scale = h->scale_d.p; ip.emat = h->emat_dom.p; ip.mp_total = h->mp_total;
-            ip.planeA = h->planeA.p; ip.planeB = h->planeB.p; ip.wpp = h->wpp;
-            ip.unit_a = h->sire_d.p; ip.unit_b = h->dam_d.p; ip.n_units = h->N; ip.T = h->T; ip.mode = MASK_XI;
-            ip.Zpart = h->Z.p;
-            CU(cudaEventRecord(h->ev[4], h->stream));
-            CU(launch_i8_contract(ip, h->plan_i8.ntiles, h->plan_i8.nsplit, h->stream));
-            CU(cudaEventRecord(h->ev[5], h->stream));
-            CU(launch_finalize_sym(h->Z.p, h->plan_i8.nsplit, h->N, h->T, h->X.p, h->stream, true));
-            h->st.last_launches += 2;
-        } else if (h->model >= GMS_MODEL_AD)
+        if (h->model >= GMS_MODEL_AD)
             if (int rc = run_contract(h, h->R2.p, h->emat_dom.p, MASK_XI, h->sire_d.p, h->dam_d.p, h->N, h->plan_x,
                                       h->split_x_d.p, h->X.p, h->ev[4], h->ev[5])) return rc;
     }

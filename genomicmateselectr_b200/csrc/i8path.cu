@@ -14,7 +14,8 @@
 // Orientation: D[M = 128 crosses (TMEM lanes)][N = 64 SNP rows j] += Xi[128 x K] * Gdigit_i[64 x K]^T,
 // both operands K-major, no swizzle, pre-tiled in HBM in the UMMA canonical "interleaved" layout
 // (8 rows x 16 bytes core matrices) so that one cp.async.bulk lands them ready for the descriptors.
-// Warp roles: 0-3 epilogue (tcgen05.ld, one TMEM lane quarter each), 4 bulk-copy producer, 5 MMA issuer.
+// Warp roles: 0-7 epilogue (tcgen05.ld; two warps per TMEM lane quarter, 32 accumulator columns each),
+// 8 bulk-copy producer, 9 MMA issuer.
 #include "kernels.cuh"
 
 namespace gms {
@@ -27,7 +28,8 @@ constexpr int I8_A_BYTES = I8_M * I8_KB;            // 8 KiB
 constexpr int I8_B_BYTES = I8_N * I8_KB;            // 4 KiB per digit
 constexpr int I8_STAGE_BYTES = I8_A_BYTES + I8_DIG * I8_B_BYTES;   // 36 KiB
 constexpr int I8_STAGES = 5;
-constexpr int I8_THREADS = 192;
+constexpr int I8_EPI_WARPS = 8;     // two per TMEM lane quarter: each takes 32 of the 64 accumulator columns
+constexpr int I8_THREADS = 32 * (I8_EPI_WARPS + 2);
 
 // ------------------------------------------------------------------------------------------ prep: xi images
 // image (X tile, global k-block) : [chunk cc (4)][r1 (16)][r0 (8)][16 bytes], row r = 8 r1 + r0, k = 16 cc + b
@@ -149,11 +151,14 @@ __global__ void i8_build_digits_kernel(const double* __restrict__ tiles, const C
             rr -= t;                                   // exact
         }
     }
+    // the 7 digit planes of one (block, trait) form ONE K-major operand of 7 x 64 = 448 rows:
+    // [chunk cc (4)][row group R1 = 8 i + r1 (56)][r0 (8)][16 bytes]  ->  LBO = 56 * 128 B, SBO = 128 B,
+    // so a k32-step needs two MMAs (N = 256: digits 0-3, N = 192: digits 4-6) instead of seven N = 64 ones
     const int r1 = r >> 3, r0 = r & 7;
 #pragma unroll
     for (int i = 0; i < I8_DIG; ++i) {
-        signed char* dst = G + gbase + ((((long long)blk * T + s) * I8_DIG + i) * (long long)I8_B_BYTES) +
-                           ((cc * 8 + r1) * 8 + r0) * 16;
+        signed char* dst = G + gbase + (((long long)blk * T + s) * (I8_DIG * (long long)I8_B_BYTES)) +
+                           ((cc * (I8_DIG * 8) + (i * 8 + r1)) * 8 + r0) * 16;
         *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(d[i]);
     }
 }
@@ -203,10 +208,9 @@ __device__ __forceinline__ void i8_mma(unsigned tmem_d, unsigned long long da, u
 __device__ __forceinline__ void i8_commit(unsigned bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
-__device__ __forceinline__ void i8_tmem_ld8(unsigned taddr, int (&v)[8]) {
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
-                 : "r"(taddr) : "memory");
+__device__ __forceinline__ void i8_tmem_ld4(unsigned taddr, int (&v)[4]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]) : "r"(taddr) : "memory");
 }
 
 template <int T>
@@ -215,6 +219,7 @@ __global__ void __launch_bounds__(I8_THREADS, 1) i8_contract_kernel(const I8Para
     unsigned char* stage0 = smem;
     unsigned long long* bars = reinterpret_cast<unsigned long long*>(smem + I8_STAGES * I8_STAGE_BYTES);
     unsigned* tmem_slot = reinterpret_cast<unsigned*>(bars + 2 * I8_STAGES + 2);
+    double* rowbuf = reinterpret_cast<double*>(bars + 2 * I8_STAGES + 4);   // [2 buffers][2 T][64]: d_t[j], scale_s[j]
     const unsigned full0 = i8_smem_u32(bars), empty0 = i8_smem_u32(bars + I8_STAGES);
     const unsigned accfull = i8_smem_u32(bars + 2 * I8_STAGES), accempty = i8_smem_u32(bars + 2 * I8_STAGES + 1);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -225,10 +230,10 @@ __global__ void __launch_bounds__(I8_THREADS, 1) i8_contract_kernel(const I8Para
     if (threadIdx.x == 0) {
         for (int s = 0; s < I8_STAGES; ++s) { i8_mbar_init(full0 + 8 * s, 1); i8_mbar_init(empty0 + 8 * s, 1); }
         i8_mbar_init(accfull, 1);
-        i8_mbar_init(accempty, 4);
+        i8_mbar_init(accempty, I8_EPI_WARPS);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 4) {
+    if (warp == I8_EPI_WARPS) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(i8_smem_u32(tmem_slot)), "r"(512) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
@@ -237,7 +242,7 @@ __global__ void __launch_bounds__(I8_THREADS, 1) i8_contract_kernel(const I8Para
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const unsigned tmem_base = *tmem_slot;
 
-    if (warp == 4) {
+    if (warp == I8_EPI_WARPS) {
         // ------------------------------------------------------------------ producer (one lane)
         if (lane == 0) {
             unsigned it = 0;
@@ -260,11 +265,14 @@ __global__ void __launch_bounds__(I8_THREADS, 1) i8_contract_kernel(const I8Para
                     }
             }
         }
-    } else if (warp == 5) {
+    } else if (warp == I8_EPI_WARPS + 1) {
         // ------------------------------------------------------------------ MMA issuer (one lane)
         if (lane == 0) {
             // instruction descriptor: D = S32, A = B = signed 8 bit, K-major both, N = 64, M = 128
-            const unsigned idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((unsigned)(I8_N >> 3) << 17) | ((unsigned)(I8_M >> 4) << 24);
+            const unsigned idesc0 = (2u << 4) | (1u << 7) | (1u << 10) | ((unsigned)(I8_M >> 4) << 24);
+            const unsigned idescA = idesc0 | ((unsigned)((4 * I8_N) >> 3) << 17);      // N = 256: digits 0-3
+            const unsigned idescB = idesc0 | ((unsigned)((3 * I8_N) >> 3) << 17);      // N = 192: digits 4-6
+            constexpr unsigned B_LBO = I8_DIG * 8 * 128;                              // chunk stride of the 448-row operand
             unsigned it = 0, acc_it = 0;
             for (int jt = jt_begin; jt < jt_end; ++jt) {
                 const RowTile tile = p.jtiles[jt];
@@ -282,11 +290,10 @@ __global__ void __launch_bounds__(I8_THREADS, 1) i8_contract_kernel(const I8Para
 #pragma unroll
                         for (int kk = 0; kk < I8_KB / 32; ++kk) {
                             const unsigned long long da = i8_desc(a0 + kk * 2 * (I8_M * 16), I8_M * 16, 128);
-#pragma unroll
-                            for (int i = 0; i < I8_DIG; ++i) {
-                                const unsigned long long db = i8_desc(b0 + i * I8_B_BYTES + kk * 2 * (I8_N * 16), I8_N * 16, 128);
-                                i8_mma(tmem_base + i * I8_N, da, db, idesc, (kb | kk) != 0);
-                            }
+                            const unsigned long long db0 = i8_desc(b0 + kk * 2 * B_LBO, B_LBO, 128);
+                            const unsigned long long db1 = i8_desc(b0 + 32 * 128 + kk * 2 * B_LBO, B_LBO, 128);
+                            i8_mma(tmem_base, da, db0, idescA, (kb | kk) != 0);
+                            i8_mma(tmem_base + 4 * I8_N, da, db1, idescB, (kb | kk) != 0);
                         }
                         i8_commit(empty0 + 8 * slot);                     // frees the smem slot when these MMAs retire
                     }
@@ -295,8 +302,10 @@ __global__ void __launch_bounds__(I8_THREADS, 1) i8_contract_kernel(const I8Para
             }
         }
     } else {
-        // ------------------------------------------------------------------ epilogue: thread = one cross
-        const long long unit = X * I8_M + warp * 32 + lane;
+        // ------------------------------------------------------------------ epilogue: thread = one cross x one half of the columns
+        const int quarter = warp & 3, half = warp >> 2;       // TMEM lane quarter is fixed by warp id % 4
+        const int etid = threadIdx.x;                          // 0 .. 255
+        const long long unit = X * I8_M + quarter * 32 + lane;
         const bool live = unit < p.n_units;
         int pa = 0, pb = 0;
         if (live) { pa = p.unit_a[unit]; pb = (p.mode == MASK_XI) ? p.unit_b[unit] : 0; }
@@ -305,48 +314,52 @@ __global__ void __launch_bounds__(I8_THREADS, 1) i8_contract_kernel(const I8Para
         for (int t = 0; t < T; ++t)
 #pragma unroll
             for (int s = 0; s < T; ++s) Z[t][s] = 0.0;
-        const unsigned tlane = tmem_base + ((unsigned)(warp * 32) << 16);
+        const unsigned tlane = tmem_base + ((unsigned)(quarter * 32) << 16) + half * 32;
         unsigned acc_it = 0;
         for (int jt = jt_begin; jt < jt_end; ++jt) {
             const RowTile tile = p.jtiles[jt];
             const ChromDesc cd = p.chrom[tile.c];
             const long long prow = (long long)cd.pad_off + 64 * tile.I;      // padded index of the tile's first row
-            unsigned nz[2] = {0u, 0u}, ng[2] = {0u, 0u};
+            // stage d_t[j] and scale_s[j] of the 64 rows in shared memory (double-buffered by tile parity)
+            double* rb = rowbuf + ((jt - jt_begin) & 1) * (2 * T * 64);
+            for (int i = etid; i < 2 * T * 64; i += 32 * I8_EPI_WARPS) {
+                const int which = i / (T * 64), rem = i - which * (T * 64), t = rem >> 6, j = rem & 63;
+                rb[i] = __ldg((which ? p.scale : p.emat) + (long long)t * p.mp_total + prow + j);
+            }
+            unsigned nz = 0u, ng = 0u;                                       // this thread's 32 rows = one word
             if (live) {
-#pragma unroll
-                for (int w = 0; w < 2; ++w) {
-                    const long long wi = (prow >> 5) + w;
-                    const unsigned A = __ldg(p.planeA + (long long)pa * p.wpp + wi), B = __ldg(p.planeB + (long long)pa * p.wpp + wi);
-                    if (p.mode == MASK_XI) {
-                        const unsigned A2 = __ldg(p.planeA + (long long)pb * p.wpp + wi), B2 = __ldg(p.planeB + (long long)pb * p.wpp + wi);
-                        nz[w] = (A ^ B) & (A2 ^ B2);
-                        ng[w] = ((~A & B) ^ (~A2 & B2)) & nz[w];
-                    } else {
-                        nz[w] = A ^ B;
-                        ng[w] = (p.mode == MASK_DELTA) ? (~A & B) : 0u;
-                    }
+                const long long wi = (prow >> 5) + half;
+                const unsigned A = __ldg(p.planeA + (long long)pa * p.wpp + wi), B = __ldg(p.planeB + (long long)pa * p.wpp + wi);
+                if (p.mode == MASK_XI) {
+                    const unsigned A2 = __ldg(p.planeA + (long long)pb * p.wpp + wi), B2 = __ldg(p.planeB + (long long)pb * p.wpp + wi);
+                    nz = (A ^ B) & (A2 ^ B2);
+                    ng = ((~A & B) ^ (~A2 & B2)) & nz;
+                } else {
+                    nz = A ^ B;
+                    ng = (p.mode == MASK_DELTA) ? (~A & B) : 0u;
                 }
             }
+            asm volatile("bar.sync 1, %0;" ::"n"(32 * I8_EPI_WARPS) : "memory");
+            const double* erow = rb + half * 32;                 // d_t[j]:     erow[t * 64 + c]
+            const double* srow = rb + T * 64 + half * 32;        // scale_s[j]: srow[s * 64 + c]
 #pragma unroll
             for (int s = 0; s < T; ++s, ++acc_it) {               // unrolled: Z[t][s] must stay in registers
                 i8_mbar_wait(accfull, acc_it & 1u);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll 1
-                for (int cb = 0; cb < I8_N / 8; ++cb) {                      // 8 SNP rows at a time
-                    int dig[I8_DIG][8];
+                for (int cb = 0; cb < 8; ++cb) {                                 // 4 SNP rows at a time
+                    int dig[I8_DIG][4];
 #pragma unroll
-                    for (int i = 0; i < I8_DIG; ++i) i8_tmem_ld8(tlane + i * I8_N + cb * 8, dig[i]);
+                    for (int i = 0; i < I8_DIG; ++i) i8_tmem_ld4(tlane + i * I8_N + cb * 4, dig[i]);
                     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                    if (cb == I8_N / 8 - 1) {                               // TMEM fully read: let the next trait's MMAs start
+                    if (cb == 7) {                                               // TMEM fully read: next trait's MMAs may start
                         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                         __syncwarp();
                         if (lane == 0) i8_mbar_arrive(accempty);
                     }
-                    const unsigned nzw = nz[cb >> 2] >> (8 * (cb & 3)), ngw = ng[cb >> 2] >> (8 * (cb & 3));
-                    const double* erow = p.emat + prow + cb * 8;
-                    const double* srow = p.scale + (long long)s * p.mp_total + prow + cb * 8;
+                    const unsigned nzw = nz >> (4 * cb), ngw = ng >> (4 * cb);
 #pragma unroll
-                    for (int c = 0; c < 8; ++c) {
+                    for (int c = 0; c < 4; ++c) {
                         // sum_i S_i 128^-(i+1): pairs of digits combined exactly in int32, then 4 exact int->fp64 terms
                         const int w0 = dig[0][c] * 128 + dig[1][c], w1 = dig[2][c] * 128 + dig[3][c];
                         const int w2 = dig[4][c] * 128 + dig[5][c], w3 = dig[6][c];
@@ -354,19 +367,20 @@ __global__ void __launch_bounds__(I8_THREADS, 1) i8_contract_kernel(const I8Para
                         v = fma((double)w2, 0x1p-42, v);
                         v = fma((double)w1, 0x1p-28, v);
                         v = fma((double)w0, 0x1p-14, v);
-                        v *= __ldg(srow + c);                          // exact power-of-two row scale
+                        v *= srow[s * 64 + cb * 4 + c];                // exact power-of-two row scale
                         long long bits = __double_as_longlong(v);
                         if (!((nzw >> c) & 1u)) bits = 0ll;
                         bits ^= (long long)((ngw >> c) & 1u) << 63;
                         v = __longlong_as_double(bits);
 #pragma unroll
-                        for (int t = 0; t < T; ++t) Z[t][s] = fma(__ldg(erow + (long long)t * p.mp_total + c), v, Z[t][s]);
+                        for (int t = 0; t < T; ++t) Z[t][s] = fma(erow[t * 64 + cb * 4 + c], v, Z[t][s]);
                     }
                 }
             }
         }
         if (live) {
-            double* out = p.Zpart + ((long long)split * p.n_units + unit) * (T * T);
+            // the two column halves of a cross go to two partial slabs (summed by finalize_sym)
+            double* out = p.Zpart + ((long long)(split * 2 + half) * p.n_units + unit) * (T * T);
 #pragma unroll
             for (int t = 0; t < T; ++t)
 #pragma unroll
@@ -375,13 +389,13 @@ __global__ void __launch_bounds__(I8_THREADS, 1) i8_contract_kernel(const I8Para
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    if (warp == 4) {
+    if (warp == I8_EPI_WARPS) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
     }
 }
 
-size_t i8_smem_bytes() { return (size_t)I8_STAGES * I8_STAGE_BYTES + (2 * I8_STAGES + 2) * 8 + 16; }
+size_t i8_smem_bytes(int T) { return (size_t)I8_STAGES * I8_STAGE_BYTES + (2 * I8_STAGES + 4) * 8 + (size_t)2 * 2 * T * 64 * 8; }
 
 cudaError_t launch_i8_build_xi(const unsigned* planeA, const unsigned* planeB, long long wpp, const int* sire,
                                const int* dam, long long n_units, int mode, long long nkb_total, signed char* xi,
@@ -407,7 +421,7 @@ cudaError_t launch_i8_build_digits(const double* tiles, const ChromDesc* chrom_d
 
 cudaError_t launch_i8_contract(const I8Params& p, int ntiles, int nsplit, cudaStream_t st) {
     if (ntiles == 0) return cudaSuccess;
-    const size_t smem = i8_smem_bytes();
+    const size_t smem = i8_smem_bytes(p.T);
     dim3 grid(ntiles, nsplit);
     cudaError_t e = cudaSuccess;
 #define GMS_I8(TV)                                                                                                  \

@@ -66,7 +66,7 @@ struct I8Params {
     int mode;
     double* Zpart;               // [nsplit][n_units][T*T]
 };
-size_t i8_smem_bytes();
+size_t i8_smem_bytes(int T);
 cudaError_t launch_i8_build_xi(const unsigned* planeA, const unsigned* planeB, long long wpp, const int* sire,
                                const int* dam, long long n_units, int mode, long long nkb_total, signed char* xi,
                                cudaStream_t st);
