@@ -312,11 +312,18 @@ def main():
     alg_flops = 2.0 * T * st["S2"] * n_per                  # SURVEY 8d dense count for the cross term, per launch
     exec_flops = st["last_flops_cross"]
     roof = None
+    traffic = None          # DRAM bytes per launch of the dominant kernel, from the committed ncu capture of this config
+    try:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
+        if (tr["workload"], tr["crosses_per_gpu"], tr["model"]) == (args.workload, n_per, args.model):
+            traffic = tr["dram_bytes_read"] + tr["dram_bytes_write"]
+    except Exception:
+        pass
     if args.model != "A" and k_ms > 0:
         achieved = alg_flops / (k_ms * 1e-3) / 1e12
         roof = {"bound": "tensor", "kernel": "contract_kernel<MASK_XI> (FP64 mma.sync DMMA, cp.async.bulk staged)",
                 "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s", "frac": achieved / fp64_peak,
-                "traffic": None,
+                "traffic": traffic,
                 "peak_source": "cuBLAS DGEMM 8192^3 measured in this run (MEASURED_PEAKS.json has no FP64 figure); "
                                "DMMA pipe probe tools/dmma_probe: 37.2 TFLOP/s; nominal 37-40",
                 "algorithmic_flops_per_launch": alg_flops, "executed_flops_per_launch": exec_flops,

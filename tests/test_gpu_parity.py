@@ -379,3 +379,21 @@ def test_int8_tensor_general_matrix_and_many_tiles(gms):
     want, wseg = oracle_slab("AD", H, R, add, dom, None, sire, dam)
     assert np.array_equal(nseg, wseg) and rel_err(out, want) < TOL
     eng.close()
+
+
+def test_trait_count_limits(gms):
+    s = synth(31, [150, 90], P=6, T=32)
+    eng = gms.CrossVarEngine(0)
+    eng.set_genmap(s["cM"], s["m_c"])
+    eng.set_haplotypes(s["H"])
+    sire, dam = np.array([0, 1, 2], np.int32), np.array([3, 1, 5], np.int32)
+    out, nseg = eng.predict("AD", s["add"], s["dom"], None, sire, dam)            # T = 32: 2 units per tile
+    want, wseg = oracle_slab("AD", s["H"], s["R"], s["add"], s["dom"], None, sire, dam)
+    assert out.shape == (3, 528, 2) and np.array_equal(nseg, wseg) and rel_err(out, want) < TOL
+    eng.set_mode("int8_tensor")                                                   # T > 6: falls back to the FP64 path
+    again, _ = eng.predict("AD", s["add"], s["dom"], None, sire, dam)
+    assert np.array_equal(again, out)
+    big = np.zeros((s["m"], 33))
+    with pytest.raises(gms.GmsError, match="1..32"):
+        eng.predict("A", big, None, None, sire, dam)
+    eng.close()
