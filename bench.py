@@ -61,7 +61,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "200", "-i", str(self.idx)], stdout=subprocess.PIPE, text=True)
+                                          "-lms", "50", "-i", str(self.idx)], stdout=subprocess.PIPE, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except Exception:
@@ -120,6 +120,29 @@ def dgemm_peak_tflops(torch):
     del a, b
     torch.cuda.empty_cache()
     return 2.0 * 8192 ** 3 / best / 1e9
+
+
+def int8_peak_tops(torch):
+    """int8 tensor ceiling on this box: cuBLASLt int8 GEMM 8192^3 through torch._int_mm, best of 5."""
+    try:
+        a = torch.randint(-100, 100, (8192, 8192), dtype=torch.int8, device="cuda")
+        b = torch.randint(-100, 100, (8192, 8192), dtype=torch.int8, device="cuda").t().contiguous().t()
+        for _ in range(2):
+            torch._int_mm(a, b)
+        torch.cuda.synchronize()
+        best = 1e30
+        for _ in range(5):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            torch._int_mm(a, b)
+            e1.record()
+            torch.cuda.synchronize()
+            best = min(best, e0.elapsed_time(e1))
+        del a, b
+        torch.cuda.empty_cache()
+        return 2.0 * 8192 ** 3 / best / 1e9
+    except Exception:
+        return 4500.0      # nominal dense int8, if the library call is unavailable
 
 
 # ----------------------------------------------------------------------------------------------
@@ -243,36 +266,9 @@ def main():
     setup_s = time.perf_counter() - t0
 
     fp64_peak = dgemm_peak_tflops(torch)
+    int8_peak = int8_peak_tops(torch)
 
-    # ---- value: device-resident inputs, kernels only
-    eng.stage(args.model, d["add"], dom, asub, sire, dam)
-    for _ in range(args.warmup):
-        eng.compute(sync=True)
-    kernel_ms, stage_ms = [], []
-    sampler = ClockSampler(local_rank)
-    barrier()
-    sampler.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(stream)
-    launches = 0
-    for _ in range(args.steps):
-        eng.compute(sync=False)
-    e1.record(stream)
-    barrier()
-    ms = max_over_ranks(e0.elapsed_time(e1))
-    clocks = sampler.stop()
-    st = eng.stats()
-    launches = st["last_launches"] * args.steps
-    # dominant-kernel duration: CUDA events recorded around the launch on the same stream (inside the
-    # library); averaged over separate, synchronised steps so that every launch is read back
-    for _ in range(args.steps):
-        eng.compute(sync=True)
-        s = eng.stats()
-        kernel_ms.append(s["last_ms_cross_kernel"])
-        stage_ms.append((s["last_ms_parent_stage"], s["last_ms_cross_stage"], s["last_ms_assemble"], s["last_ms_total"]))
-    value = n_total * args.steps / (ms * 1e-3)
-
-    # ---- e2e: gms_predict with pinned host buffers, H2D and D2H inside the timed region
+    # pinned host buffers for the e2e legs
     npairs, ncomp = T * (T + 1) // 2, {"A": 1, "AD": 2, "DirDom": 3}[args.model]
     pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
     add_p = pin(np.asfortranarray(d["add"]).T)           # m x T column-major == (T, m) C-order
@@ -292,85 +288,123 @@ def main():
             dist.gather(out_p.cuda(non_blocking=True), gather, dst=0)
         return float(o[0, 0, 0])
 
-    for _ in range(min(2, args.warmup)):
-        e2e_step()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        e2e_step()
-    barrier()
-    e2e_s = max_over_ranks(time.perf_counter() - t0)
-    h2d = sum(t.numel() * t.element_size() for t in (add_p, dom_p, asub_p, sire_p, dam_p) if t is not None) \
-        + 2 * n_per * 4 + 4 * int(st["last_parents_used"])      # + sire/dam table slots + parent list
-    d2h = out_p.numel() * 8 + nseg_p.numel() * 4
-    e2e = {"value": n_total * args.steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
-           "d2h_bytes_per_step": int(d2h), "ms_per_step": 1e3 * e2e_s / args.steps,
-           "api": "gms_predict (C ABI) via CrossVarEngine.predict, pinned host buffers"}
+    def measure(mode, with_clocks=False):
+        """One evaluation mode on the same staged inputs: device-resident throughput (gms_compute only: every
+        kernel incl. the device-side operand preparation), per-kernel times, and end-to-end through gms_predict."""
+        eng.set_mode(mode)
+        eng.stage(args.model, d["add"], dom, asub, sire, dam)
+        for _ in range(args.warmup):
+            eng.compute(sync=True)
+        sampler = ClockSampler(local_rank) if with_clocks else None
+        barrier()
+        if sampler:
+            sampler.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(args.steps):
+            eng.compute(sync=False)
+        e1.record(stream)
+        barrier()
+        ms = max_over_ranks(e0.elapsed_time(e1))
+        clocks = sampler.stop() if sampler else None
+        # dominant-kernel duration: CUDA events recorded around the launch on the same stream (inside the
+        # library); averaged over separate, synchronised steps so that every launch is read back
+        kernel_ms, stage_ms = [], []
+        for _ in range(args.steps):
+            eng.compute(sync=True)
+            s_ = eng.stats()
+            kernel_ms.append(s_["last_ms_cross_kernel"])
+            stage_ms.append((s_["last_ms_parent_stage"], s_["last_ms_cross_stage"], s_["last_ms_assemble"], s_["last_ms_total"]))
+        st_ = eng.stats()
+        for _ in range(min(2, args.warmup)):
+            e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            e2e_step()
+        barrier()
+        e2e_s = max_over_ranks(time.perf_counter() - t0)
+        return {"mode": mode, "resolved_mode": {0: "fp64_dmma", 1: "map_scan", 2: "int8_tensor"}[st_["last_mode"]],
+                "value": n_total * args.steps / (ms * 1e-3), "ms_per_step": ms / args.steps,
+                "kernel_ms": float(np.mean(kernel_ms)), "step_ms_sync": float(np.mean([s_[3] for s_ in stage_ms])),
+                "stages_ms": {"prep_and_parent_tables": float(np.mean([s_[0] for s_ in stage_ms])),
+                              "cross_term": float(np.mean([s_[1] for s_ in stage_ms])),
+                              "assemble_nseg": float(np.mean([s_[2] for s_ in stage_ms]))},
+                "launches": st_["last_launches"] * args.steps, "e2e_value": n_total * args.steps / e2e_s,
+                "e2e_ms_per_step": 1e3 * e2e_s / args.steps, "clocks": clocks, "stats": st_}
 
-    # ---- roofline of the dominant kernel (per-cross dominance contraction, FP64 DMMA)
-    k_ms = float(np.mean(kernel_ms)) if kernel_ms else 0.0
-    alg_flops = 2.0 * T * st["S2"] * n_per                  # SURVEY 8d dense count for the cross term, per launch
-    exec_flops = st["last_flops_cross"]
-    roof = None
-    traffic = None          # DRAM bytes per launch of the dominant kernel, from the committed ncu capture of this config
+    def fp64_roofline(r):
+        """FP64 tensor (DMMA) roofline of contract_kernel<MASK_XI>."""
+        if args.model == "A" or r["kernel_ms"] <= 0:
+            return None
+        alg = 2.0 * T * r["stats"]["S2"] * n_per            # SURVEY 8d dense count for the cross term, per launch
+        exe = r["stats"]["last_flops_cross"]
+        ach = alg / (r["kernel_ms"] * 1e-3) / 1e12
+        return {"bound": "tensor", "kernel": "contract_kernel<MASK_XI> (FP64 mma.sync DMMA, cp.async.bulk staged)",
+                "achieved": ach, "peak": fp64_peak, "unit": "TFLOP/s", "frac": ach / fp64_peak, "traffic": traffic,
+                "peak_source": "cuBLAS DGEMM 8192^3 measured in this run (MEASURED_PEAKS.json has no FP64 figure); "
+                               "DMMA pipe probe tools/dmma_probe: 37.2 TFLOP/s; nominal 37-40",
+                "algorithmic_flops_per_launch": alg, "executed_flops_per_launch": exe,
+                "executed_tflops": exe / (r["kernel_ms"] * 1e-3) / 1e12,
+                "executed_frac_of_peak": exe / (r["kernel_ms"] * 1e-3) / 1e12 / fp64_peak,
+                "note": "algorithmic = dense 2*T*S2 per cross (no symmetry credit); the kernel executes only the lower "
+                        "block triangle of the symmetric RoR blocks, so frac can exceed 1",
+                "kernel_ms": r["kernel_ms"], "kernel_share_of_step": r["kernel_ms"] / r["step_ms_sync"]}
+
+    def int8_roofline(r):
+        """int8 tensor (tcgen05) roofline of i8_contract_kernel: 7 exact digit planes x ternary xi."""
+        if args.model == "A" or r["kernel_ms"] <= 0:
+            return None
+        mc = np.asarray(d["m_c"], dtype=np.float64)
+        nJ = np.ceil(mc / 64.0)
+        alg = 2.0 * 7 * T * n_per * float(np.sum(mc * (mc + 1) / 2))                    # lower triangle incl. diagonal, 7 digits
+        exe = 2.0 * 7 * T * (np.ceil(n_per / 128.0) * 128) * float(np.sum(64 * 64 * nJ * (nJ + 1) / 2))
+        ach = alg / (r["kernel_ms"] * 1e-3) / 1e12
+        return {"bound": "tensor", "kernel": "i8_contract_kernel (tcgen05.mma kind::i8, int32 accumulators in TMEM, cp.async.bulk staged)",
+                "achieved": ach, "peak": int8_peak, "unit": "TFLOP/s", "op_type": "int8 multiply-add = 2 ops",
+                "frac": ach / int8_peak, "traffic": None,
+                "peak_source": "cuBLASLt int8 GEMM 8192^3 (torch._int_mm) measured in this run; nominal dense int8 4500",
+                "algorithmic_flops_per_launch": alg, "executed_flops_per_launch": exe,
+                "executed_tflops": exe / (r["kernel_ms"] * 1e-3) / 1e12,
+                "executed_frac_of_peak": exe / (r["kernel_ms"] * 1e-3) / 1e12 / int8_peak,
+                "fp64_dense_equivalent_tflops": 2.0 * T * r["stats"]["S2"] * n_per / (r["kernel_ms"] * 1e-3) / 1e12,
+                "note": "algorithmic = 7 radix-128 digit planes x the exact lower triangle (incl. diagonal) of every chromosome "
+                        "block x T traits x crosses; executed adds 64-granular block and 128-cross tile padding",
+                "kernel_ms": r["kernel_ms"], "kernel_share_of_step": r["kernel_ms"] / r["step_ms_sync"]}
+
+    traffic = None          # DRAM bytes per launch of the FP64 kernel, from the committed ncu capture of this config
     try:
         tr = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
         if (tr["workload"], tr["crosses_per_gpu"], tr["model"]) == (args.workload, n_per, args.model):
             traffic = tr["dram_bytes_read"] + tr["dram_bytes_write"]
     except Exception:
         pass
-    if args.model != "A" and k_ms > 0:
-        achieved = alg_flops / (k_ms * 1e-3) / 1e12
-        roof = {"bound": "tensor", "kernel": "contract_kernel<MASK_XI> (FP64 mma.sync DMMA, cp.async.bulk staged)",
-                "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s", "frac": achieved / fp64_peak,
-                "traffic": traffic,
-                "peak_source": "cuBLAS DGEMM 8192^3 measured in this run (MEASURED_PEAKS.json has no FP64 figure); "
-                               "DMMA pipe probe tools/dmma_probe: 37.2 TFLOP/s; nominal 37-40",
-                "algorithmic_flops_per_launch": alg_flops, "executed_flops_per_launch": exec_flops,
-                "executed_tflops": exec_flops / (k_ms * 1e-3) / 1e12,
-                "executed_frac_of_peak": exec_flops / (k_ms * 1e-3) / 1e12 / fp64_peak,
-                "note": "algorithmic = dense 2*T*S2 per cross (no symmetry credit); the kernel executes only the lower "
-                        "block triangle of the symmetric RoR blocks (x0.585 incl. padding), so frac can exceed 1",
-                "kernel_ms": k_ms, "kernel_share_of_step": k_ms / float(np.mean([s[3] for s in stage_ms]))}
 
-    # ---- optional modes on the same inputs / outputs (not the headline):
-    #   int8_tensor: exact int8 tcgen05 evaluation of the per-cross term, any symmetric matrix
-    #   map_scan   : map-structured prefix-sum fast path, map-derived matrices only
-    def run_mode(mode, note):
+    head = measure("auto", with_clocks=True)                 # the default path of the library = the headline
+    ms, value, launches, clocks, st = head["ms_per_step"] * args.steps, head["value"], head["launches"], head["clocks"], head["stats"]
+    roof = int8_roofline(head) if head["resolved_mode"] == "int8_tensor" else fp64_roofline(head)
+    h2d = sum(t.numel() * t.element_size() for t in (add_p, dom_p, asub_p, sire_p, dam_p) if t is not None) \
+        + 2 * n_per * 4 + 4 * int(st["last_parents_used"])      # + sire/dam table slots + parent list
+    d2h = out_p.numel() * 8 + nseg_p.numel() * 4
+    e2e = {"value": head["e2e_value"], "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+           "ms_per_step": head["e2e_ms_per_step"],
+           "api": "gms_predict (C ABI) via CrossVarEngine.predict, pinned host buffers, default mode"}
+
+    def leg(mode, note, roofline_fn=None):
         try:
-            eng.set_mode(mode)
-            eng.stage(args.model, d["add"], dom, asub, sire, dam)
-            for _ in range(args.warmup):
-                eng.compute(sync=True)
-            barrier()
-            f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            f0.record(stream)
-            for _ in range(args.steps):
-                eng.compute(sync=False)
-            f1.record(stream)
-            barrier()
-            ms_m = max_over_ranks(f0.elapsed_time(f1))
-            kms = []
-            for _ in range(args.steps):
-                eng.compute(sync=True)
-                kms.append(eng.stats()["last_ms_cross_kernel"])
-            barrier()
-            t0 = time.perf_counter()
-            for _ in range(args.steps):
-                e2e_step()
-            barrier()
-            e2e_m = max_over_ranks(time.perf_counter() - t0)
-            res = {"value": n_total * args.steps / (ms_m * 1e-3), "unit": UNIT, "ms_per_step": ms_m / args.steps,
-                   "cross_kernel_ms": float(np.mean(kms)), "e2e": n_total * args.steps / e2e_m, "note": note}
-        except Exception as exc:   # the headline path must not depend on the optional ones
-            res = {"error": str(exc)}
-        eng.set_mode("dense")
-        return res
+            r = measure(mode)
+            out = {"value": r["value"], "unit": UNIT, "ms_per_step": r["ms_per_step"], "cross_kernel_ms": r["kernel_ms"],
+                   "e2e": r["e2e_value"], "stages_ms": r["stages_ms"], "note": note}
+            if roofline_fn:
+                out["roofline"] = roofline_fn(r)
+            return out
+        except Exception as exc:   # the headline path must not depend on the other legs
+            return {"error": str(exc)}
 
-    int8_tensor = run_mode("int8_tensor", "gms_set_mode(GMS_MODE_INT8_TENSOR): tcgen05 kind::i8, exact digit planes; "
-                           "e2e includes building the digit / xi images every call; not the headline") \
-        if args.model != "A" else None
-    map_scan = run_mode("map_scan", "gms_set_mode(GMS_MODE_MAP_SCAN): valid only for map-derived recombFreqMat; not the headline")
+    fp64_leg = leg("fp64", "gms_set_mode(GMS_MODE_DENSE): the FP64 DMMA contraction north_star describes; any symmetric matrix",
+                   fp64_roofline) if head["resolved_mode"] != "fp64_dmma" else None
+    map_scan = leg("map_scan", "gms_set_mode(GMS_MODE_MAP_SCAN): map-structured prefix-sum path, map-derived recombFreqMat only; opt-in")
+    eng.set_mode("auto")
 
     if rank == 0:
         cpu = None
@@ -380,13 +414,13 @@ def main():
         pk = measured_peaks()
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
-                "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config, "clocks": clocks,
+                "vs_baseline": None,
+                "dtype": "f64 results; " + ("exact int8 digit planes on tcgen05 + f64 recombination" if head["resolved_mode"] == "int8_tensor" else "f64 DMMA"),
+                "data": "synthetic", "config": dict(config, mode=head["resolved_mode"]), "clocks": clocks,
                 "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu,
-                "stages_ms": {"parent_tables": float(np.mean([s[0] for s in stage_ms])),
-                              "cross_term": float(np.mean([s[1] for s in stage_ms])),
-                              "assemble_nseg": float(np.mean([s[2] for s in stage_ms]))},
-                "int8_tensor": int8_tensor, "map_scan": map_scan, "setup_s": setup_s, "hbm_tile_bytes": int(st["tile_bytes"]),
-                "measured_peaks": {"hbm_gbs": pk.get("hbm_gbs"), "fp64_dgemm_tflops": fp64_peak}}
+                "stages_ms": head["stages_ms"], "fp64_dmma": fp64_leg, "map_scan": map_scan,
+                "setup_s": setup_s, "hbm_tile_bytes": int(st["tile_bytes"]),
+                "measured_peaks": {"hbm_gbs": pk.get("hbm_gbs"), "fp64_dgemm_tflops": fp64_peak, "int8_gemm_tops": int8_peak}}
         emit(line)
     eng.close()
     if world > 1:

@@ -22,7 +22,7 @@ class GmsError(RuntimeError):
 class Stats(C.Structure):
     _fields_ = [("m", C.c_int64), ("m_padded", C.c_int64), ("S2", C.c_int64), ("tile_bytes", C.c_int64),
                 ("C", C.c_int32), ("P", C.c_int32), ("last_T", C.c_int32), ("last_model", C.c_int32),
-                ("last_N", C.c_int64), ("last_parents_used", C.c_int64), ("last_launches", C.c_int32),
+                ("last_N", C.c_int64), ("last_parents_used", C.c_int64), ("last_launches", C.c_int32), ("last_mode", C.c_int32),
                 ("last_ms_parent_stage", C.c_float), ("last_ms_cross_stage", C.c_float),
                 ("last_ms_cross_kernel", C.c_float), ("last_ms_assemble", C.c_float),
                 ("last_ms_total", C.c_float), ("last_flops_cross", C.c_double),

@@ -111,9 +111,10 @@ class CrossVarEngine:
         return mask_ok
 
     def set_mode(self, mode):
-        """"dense" (default: FP64 tensor contraction, any symmetric recombFreqMat) or "map_scan"
-        (map-structured prefix-sum fast path; needs set_genmap() with sorted positions)."""
-        code = {"dense": 0, "map_scan": 1, "int8_tensor": 2}[mode] if isinstance(mode, str) else int(mode)
+        """"auto" (default: "int8_tensor" when T <= 6, else "fp64"), "fp64" / "dense" (FP64 DMMA contraction),
+        "int8_tensor" (exact int8 digit planes on tcgen05), "map_scan" (map-structured prefix-sum fast
+        path; needs set_genmap() with sorted positions)."""
+        code = {"dense": 0, "fp64": 0, "map_scan": 1, "int8_tensor": 2, "auto": 3}[mode] if isinstance(mode, str) else int(mode)
         self._ck(self._lib.gms_set_mode(self._h, code))
 
     def set_chromosome_shard(self, c_begin, c_end):

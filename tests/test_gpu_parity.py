@@ -17,8 +17,15 @@ def gms():
     return g
 
 
-def bundled_engine(gms, b, use_map=False):
+@pytest.fixture(params=["auto", "fp64"])
+def mode(request):
+    """"auto" = the default (exact int8 tcgen05 path when T <= 6), "fp64" = the FP64 DMMA contraction."""
+    return request.param
+
+
+def bundled_engine(gms, b, mode="auto"):
     eng = gms.CrossVarEngine(0)
+    eng.set_mode(mode)
     idx = []
     for p in b.PARENTS:
         idx += [b.hap_rownames.index(f"{p}_HapA"), b.hap_rownames.index(f"{p}_HapB")]
@@ -30,9 +37,9 @@ def bundled_engine(gms, b, use_map=False):
 
 
 # ---------------------------------------------------------------- configs 1-3: bundled data
-def test_bundled_A_single_trait(gms, bundled):
+def test_bundled_A_single_trait(gms, bundled, mode):
     b = bundled
-    eng, H, sire, dam = bundled_engine(gms, b)
+    eng, H, sire, dam = bundled_engine(gms, b, mode)
     out, nseg = eng.predict("A", b.effA[:, :1], None, None, sire, dam)
     want, wseg = oracle_slab("A", H, b.recombFreqMat, b.effA[:, :1], None, None, sire, dam)
     assert out.shape == (15, 1, 1)
@@ -42,9 +49,9 @@ def test_bundled_A_single_trait(gms, bundled):
     eng.close()
 
 
-def test_bundled_A_two_traits_matches_vignette(gms, bundled):
+def test_bundled_A_two_traits_matches_vignette(gms, bundled, mode):
     b = bundled
-    eng, H, sire, dam = bundled_engine(gms, b)
+    eng, H, sire, dam = bundled_engine(gms, b, mode)
     out, nseg = eng.predict("A", b.effA, None, None, sire, dam)
     want, wseg = oracle_slab("A", H, b.recombFreqMat, b.effA, None, None, sire, dam)
     assert np.array_equal(nseg, wseg)
@@ -57,9 +64,9 @@ def test_bundled_A_two_traits_matches_vignette(gms, bundled):
     eng.close()
 
 
-def test_bundled_AD_matches_vignette(gms, bundled):
+def test_bundled_AD_matches_vignette(gms, bundled, mode):
     b = bundled
-    eng, H, sire, dam = bundled_engine(gms, b)
+    eng, H, sire, dam = bundled_engine(gms, b, mode)
     out, nseg = eng.predict("AD", b.effAD_add, b.effAD_dom, None, sire, dam)
     want, wseg = oracle_slab("AD", H, b.recombFreqMat, b.effAD_add, b.effAD_dom, None, sire, dam)
     assert np.array_equal(nseg, wseg)
@@ -73,10 +80,10 @@ def test_bundled_AD_matches_vignette(gms, bundled):
     eng.close()
 
 
-def test_bundled_DirDom(gms, bundled):
+def test_bundled_DirDom(gms, bundled, mode):
     b = bundled
     a, d, alpha = b.dirdom_effects()
-    eng, H, sire, dam = bundled_engine(gms, b)
+    eng, H, sire, dam = bundled_engine(gms, b, mode)
     out, nseg = eng.predict("DirDom", a, d, alpha, sire, dam)
     want, wseg = oracle_slab("DirDom", H, b.recombFreqMat, a, d, alpha, sire, dam)
     assert out.shape == (15, 3, 3)
@@ -103,7 +110,7 @@ def synth(seed, m_c, P, T):
 
 @pytest.mark.parametrize("model", ["A", "AD", "DirDom"])
 @pytest.mark.parametrize("T", [1, 2, 3, 5, 7, 16])
-def test_synthetic_map_path(gms, model, T):
+def test_synthetic_map_path(gms, model, T, mode):
     s = synth(100 + T, [200, 131, 77, 300], P=24, T=T)
     rng = np.random.default_rng(5)
     sire = rng.integers(0, 24, 70).astype(np.int32)
@@ -111,6 +118,7 @@ def test_synthetic_map_path(gms, model, T):
     sire[:6] = dam[:6]                      # selfs
     sire[6], dam[6] = sire[7], dam[7]       # a duplicate row
     eng = gms.CrossVarEngine(0)
+    eng.set_mode(mode)
     eng.set_genmap(s["cM"], s["m_c"])
     eng.set_haplotypes(s["H"])
     dom = s["dom"] if model != "A" else None
@@ -123,17 +131,19 @@ def test_synthetic_map_path(gms, model, T):
     eng.close()
 
 
-def test_blocks_path_equals_map_path_and_many_rowtiles(gms):
+def test_blocks_path_equals_map_path_and_many_rowtiles(gms, mode):
     s = synth(11, [700, 390, 129], P=12, T=5)     # 6 + 4 + 2 row tiles; ragged last tiles
     sire = np.array([0, 1, 2, 3, 4, 5, 6, 7, 3], np.int32)
     dam = np.array([1, 1, 5, 9, 10, 11, 6, 0, 8], np.int32)
     eng = gms.CrossVarEngine(0)
+    eng.set_mode(mode)
     eng.set_genmap(s["cM"], s["m_c"])
     eng.set_haplotypes(s["H"])
     out1, nseg1 = eng.predict("AD", s["add"], s["dom"], None, sire, dam)
     want, wseg = oracle_slab("AD", s["H"], s["R"], s["add"], s["dom"], None, sire, dam)
     assert np.array_equal(nseg1, wseg) and rel_err(out1, want) < TOL
     eng2 = gms.CrossVarEngine(0)
+    eng2.set_mode(mode)
     assert eng2.set_recomb_matrix(s["R"], s["chrom"]) is True
     eng2.set_haplotypes(s["H"].astype(np.int32).copy(order="F"))   # R integer-matrix layout entry point
     out2, nseg2 = eng2.predict("AD", s["add"], s["dom"], None, sire, dam)
@@ -151,7 +161,7 @@ def test_blocks_path_equals_map_path_and_many_rowtiles(gms):
     eng2.close()
 
 
-def test_general_matrix_single_block(gms):
+def test_general_matrix_single_block(gms, mode):
     """recombFreqMat with non-zero off-chromosome entries -> one dense block."""
     rng = np.random.default_rng(3)
     m, P, T = 150, 6, 2
@@ -163,6 +173,7 @@ def test_general_matrix_single_block(gms):
     sire = np.array([0, 1, 2, 3], np.int32)
     dam = np.array([0, 2, 4, 5], np.int32)
     eng = gms.CrossVarEngine(0)
+    eng.set_mode(mode)
     assert eng.set_recomb_matrix(R, chrom) is False
     eng.set_haplotypes(H)
     out, nseg = eng.predict("AD", add, dom, None, sire, dam)
@@ -172,11 +183,12 @@ def test_general_matrix_single_block(gms):
 
 
 # ---------------------------------------------------------------- edge cases and errors
-def test_edge_cases(gms):
+def test_edge_cases(gms, mode):
     s = synth(2, [64, 40], P=4, T=2)
     H = s["H"].copy()
     H[0] = H[1] = H[2] = H[3] = 1            # parents 0 and 1: fixed for allele 1 everywhere
     eng = gms.CrossVarEngine(0)
+    eng.set_mode(mode)
     eng.set_genmap(s["cM"], s["m_c"])
     eng.set_haplotypes(H)
     out, nseg = eng.predict("AD", s["add"], s["dom"], None, [0, 0, 2], [1, 0, 3])
@@ -204,12 +216,13 @@ def test_edge_cases(gms):
     eng.close()
 
 
-def test_invariances(gms):
+def test_invariances(gms, mode):
     """Size-independent properties of the path: sire/dam swap, HapA/HapB swap, effect scaling."""
     s = synth(9, [300, 200], P=10, T=3)
     sire = np.arange(10, dtype=np.int32)
     dam = np.roll(sire, 3)
     eng = gms.CrossVarEngine(0)
+    eng.set_mode(mode)
     eng.set_genmap(s["cM"], s["m_c"])
     eng.set_haplotypes(s["H"])
     base, nseg = eng.predict("AD", s["add"], s["dom"], None, sire, dam)
@@ -227,13 +240,14 @@ def test_invariances(gms):
 
 
 # ---------------------------------------------------------------- BASELINE.json full size
-def test_cassava_scale_against_blockwise_oracle(gms):
+def test_cassava_scale_against_blockwise_oracle(gms, mode):
     """configs[3]: 1000 parents, 33k SNPs / 18 chromosomes, 5 traits, AD.  A handful of crosses is
     checked against the oracle evaluated chromosome by chromosome; the whole batch is checked through
     invariants (self-cross rows = twice the gametic part, duplicate rows identical)."""
     from genomicmateselectr_b200 import synth as S
     d = S.make("cassava", N=2000)
     eng = gms.CrossVarEngine(0)
+    eng.set_mode(mode)
     eng.set_genmap(d["cM"], d["m_c"])
     eng.set_haplotypes(d["H"])
     out, nseg = eng.predict("AD", d["add"], d["dom"], None, d["sire"], d["dam"])
@@ -268,6 +282,7 @@ def test_map_scan_mode_matches_oracle_and_dense(gms, model, T):
     eng = gms.CrossVarEngine(0)
     eng.set_genmap(s["cM"], s["m_c"])
     eng.set_haplotypes(s["H"])
+    eng.set_mode("fp64")
     dense, nseg_d = eng.predict(model, s["add"], dom, asub, sire, dam)
     eng.set_mode("map_scan")
     out, nseg = eng.predict(model, s["add"], dom, asub, sire, dam)
@@ -275,9 +290,9 @@ def test_map_scan_mode_matches_oracle_and_dense(gms, model, T):
     assert np.array_equal(nseg, wseg) and np.array_equal(nseg_d, wseg)
     assert rel_err(out, want) < TOL
     assert rel_err(out, dense) < TOL
-    eng.set_mode("dense")
+    eng.set_mode("fp64")
     again, _ = eng.predict(model, s["add"], dom, asub, sire, dam)
-    assert np.array_equal(again, dense)                     # the dense path is bit-reproducible
+    assert np.array_equal(again, dense)                     # the FP64 path is bit-reproducible
     eng.close()
 
 
@@ -307,6 +322,7 @@ def test_map_scan_cassava_scale_equals_dense(gms):
     eng = gms.CrossVarEngine(0)
     eng.set_genmap(d["cM"], d["m_c"])
     eng.set_haplotypes(d["H"])
+    eng.set_mode("fp64")
     dense, nseg = eng.predict("AD", d["add"], d["dom"], None, d["sire"], d["dam"])
     eng.set_mode("map_scan")
     fast, nseg2 = eng.predict("AD", d["add"], d["dom"], None, d["sire"], d["dam"])
@@ -350,6 +366,7 @@ def test_int8_tensor_mode_matches_oracle_and_dense(gms, model, T):
     eng = gms.CrossVarEngine(0)
     eng.set_genmap(s["cM"], s["m_c"])
     eng.set_haplotypes(s["H"])
+    eng.set_mode("fp64")
     dense, nseg_d = eng.predict(model, s["add"], s["dom"], asub, sire, dam)
     eng.set_mode("int8_tensor")
     out, nseg = eng.predict(model, s["add"], s["dom"], asub, sire, dam)
@@ -390,6 +407,7 @@ def test_trait_count_limits(gms):
     out, nseg = eng.predict("AD", s["add"], s["dom"], None, sire, dam)            # T = 32: 2 units per tile
     want, wseg = oracle_slab("AD", s["H"], s["R"], s["add"], s["dom"], None, sire, dam)
     assert out.shape == (3, 528, 2) and np.array_equal(nseg, wseg) and rel_err(out, want) < TOL
+    assert eng.stats()["last_mode"] == 0                                           # auto resolved to the FP64 path (T > 6)
     eng.set_mode("int8_tensor")                                                   # T > 6: falls back to the FP64 path
     again, _ = eng.predict("AD", s["add"], s["dom"], None, sire, dam)
     assert np.array_equal(again, out)

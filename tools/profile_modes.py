@@ -11,7 +11,7 @@ eng = CrossVarEngine(0)
 eng.set_genmap(d["cM"], d["m_c"])
 eng.set_haplotypes(d["H"])
 ref = None
-for mode in ["dense"] + modes if "dense" not in modes else modes:
+for mode in (["fp64"] + modes if "fp64" not in modes else modes):
     eng.set_mode(mode)
     eng.stage("AD", d["add"], d["dom"], None, d["sire"], d["dam"])
     eng.compute(sync=True)
