@@ -157,7 +157,12 @@ def cpu_reference_run(d, model, sample, steps, warmup, nthreads=0):
         cm = d["cM"][offs[c]:offs[c + 1]]
         blocks.append(O.recombfreq_to_ld_decay(O.genmap2recombfreq(cm, np.ones(cm.size))))
     prob = CR.RefProblem(d["H"], d["add"], d["dom"] if model != "A" else None, blocks=blocks)
-    cores = nthreads or CR.max_threads()
+    # all host cores, whatever OMP_NUM_THREADS says (torchrun exports OMP_NUM_THREADS=1)
+    try:
+        avail = len(os.sched_getaffinity(0))
+    except Exception:
+        avail = os.cpu_count() or 1
+    cores = nthreads or max(avail, CR.max_threads())
     rng = np.random.default_rng(12345)
     times, nsegs = [], []
     for it in range(warmup + steps):
