@@ -598,7 +598,13 @@ int gms_stage_inputs(gms_handle* h, int model, int T, const double* add, const d
     // resolve the evaluation mode
     const int NU = BN / T, TT = T * T;
     const long long npad = (N + 127) / 128 * 128, ppad = (h->nP + 127) / 128 * 128;
-    const bool i8_ok = T <= 6 && N > 0 && (double)(npad + 2 * ppad) * (double)h->mp_total < 24e9;
+    // int8 path: mask images (npad + 2 ppad) x mp bytes and up to 3 digit-plane sets must fit comfortably
+    double dig_bytes = 0;
+    for (int c = h->c_begin; c < h->c_end; ++c) {
+        const double nJ = (h->chrom[c].m + 63) / 64;
+        dig_bytes += nJ * (nJ + 1) / 2 * T * 7 * 4096.0;
+    }
+    const bool i8_ok = N > 0 && (double)(npad + 2 * ppad) * (double)h->mp_total < 24e9 && dig_bytes * (model + 1) < 60e9;
     h->eff_mode = h->mode;
     if (h->mode == GMS_MODE_AUTO) h->eff_mode = i8_ok ? GMS_MODE_INT8_TENSOR : GMS_MODE_DENSE;
     if (h->eff_mode == GMS_MODE_INT8_TENSOR && !i8_ok) h->eff_mode = GMS_MODE_DENSE;

@@ -213,19 +213,26 @@ __device__ __forceinline__ void i8_tmem_ld4(unsigned taddr, int (&v)[4]) {
                  : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]) : "r"(taddr) : "memory");
 }
 
-template <int T>
+// TT = T (SOUTER = false, T <= 6: loop "64-row tile outer, trait s inner", the cross's whole T x T table in registers)
+// or TT >= T (SOUTER = true, any T <= 32: loop "trait s outer, tile inner", one column Z[:, s] in registers).
+template <int TT, bool SOUTER>
 __global__ void __launch_bounds__(I8_THREADS, 1) i8_contract_kernel(const I8Params p) {
+    const int T = SOUTER ? p.T : TT;
     extern __shared__ __align__(1024) unsigned char smem[];
     unsigned char* stage0 = smem;
     unsigned long long* bars = reinterpret_cast<unsigned long long*>(smem + I8_STAGES * I8_STAGE_BYTES);
     unsigned* tmem_slot = reinterpret_cast<unsigned*>(bars + 2 * I8_STAGES + 2);
-    double* rowbuf = reinterpret_cast<double*>(bars + 2 * I8_STAGES + 4);   // [2 buffers][2 T][64]: d_t[j], scale_s[j]
+    double* rowbuf = reinterpret_cast<double*>(bars + 2 * I8_STAGES + 4);   // [2 buffers][2 T (or T + 1)][64]: d_t[j], scale_s[j]
     const unsigned full0 = i8_smem_u32(bars), empty0 = i8_smem_u32(bars + I8_STAGES);
     const unsigned accfull = i8_smem_u32(bars + 2 * I8_STAGES), accempty = i8_smem_u32(bars + 2 * I8_STAGES + 1);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const long long X = blockIdx.x;
     const int split = blockIdx.y;
     const int jt_begin = p.split_begin[split], jt_end = p.split_begin[split + 1];
+    const int njt = jt_end - jt_begin, nunits = njt * T;       // a unit = one (tile, trait) accumulator pass
+    // unit u -> (tile, trait) in this kernel's loop order
+    auto unit_jt = [&](int u) { return jt_begin + (SOUTER ? u % njt : u / T); };
+    auto unit_s = [&](int u) { return SOUTER ? u / njt : u % T; };
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < I8_STAGES; ++s) { i8_mbar_init(full0 + 8 * s, 1); i8_mbar_init(empty0 + 8 * s, 1); }
@@ -246,23 +253,23 @@ __global__ void __launch_bounds__(I8_THREADS, 1) i8_contract_kernel(const I8Para
         // ------------------------------------------------------------------ producer (one lane)
         if (lane == 0) {
             unsigned it = 0;
-            for (int jt = jt_begin; jt < jt_end; ++jt) {
-                const RowTile tile = p.jtiles[jt];
+            for (int u = 0; u < nunits; ++u) {
+                const RowTile tile = p.jtiles[unit_jt(u)];
+                const int s = unit_s(u);
                 const ChromDesc cd = p.chrom[tile.c];
                 const int J = tile.I;
                 const int nkb = min(J + 1, (cd.m + I8_KB - 1) / I8_KB);
                 const signed char* abase = p.xi + (X * p.nkb_total + (cd.pad_off >> 6)) * (long long)I8_A_BYTES;
                 const signed char* gb = p.G + p.gbase[tile.c] + ((long long)(J * (J + 1) / 2) * T) * (I8_DIG * (long long)I8_B_BYTES);
-                for (int s = 0; s < T; ++s)
-                    for (int kb = 0; kb < nkb; ++kb, ++it) {
-                        const unsigned slot = it % I8_STAGES, ph = (it / I8_STAGES) & 1u;
-                        i8_mbar_wait(empty0 + 8 * slot, ph ^ 1u);
-                        const unsigned dst = i8_smem_u32(stage0 + slot * I8_STAGE_BYTES);
-                        i8_mbar_expect_tx(full0 + 8 * slot, I8_STAGE_BYTES);
-                        i8_bulk_g2s(dst, abase + (long long)kb * I8_A_BYTES, I8_A_BYTES, full0 + 8 * slot);
-                        i8_bulk_g2s(dst + I8_A_BYTES, gb + ((long long)kb * T + s) * (I8_DIG * (long long)I8_B_BYTES),
-                                    I8_DIG * I8_B_BYTES, full0 + 8 * slot);
-                    }
+                for (int kb = 0; kb < nkb; ++kb, ++it) {
+                    const unsigned slot = it % I8_STAGES, ph = (it / I8_STAGES) & 1u;
+                    i8_mbar_wait(empty0 + 8 * slot, ph ^ 1u);
+                    const unsigned dst = i8_smem_u32(stage0 + slot * I8_STAGE_BYTES);
+                    i8_mbar_expect_tx(full0 + 8 * slot, I8_STAGE_BYTES);
+                    i8_bulk_g2s(dst, abase + (long long)kb * I8_A_BYTES, I8_A_BYTES, full0 + 8 * slot);
+                    i8_bulk_g2s(dst + I8_A_BYTES, gb + ((long long)kb * T + s) * (I8_DIG * (long long)I8_B_BYTES),
+                                I8_DIG * I8_B_BYTES, full0 + 8 * slot);
+                }
             }
         }
     } else if (warp == I8_EPI_WARPS + 1) {
@@ -273,32 +280,30 @@ __global__ void __launch_bounds__(I8_THREADS, 1) i8_contract_kernel(const I8Para
             const unsigned idescA = idesc0 | ((unsigned)((4 * I8_N) >> 3) << 17);      // N = 256: digits 0-3
             const unsigned idescB = idesc0 | ((unsigned)((3 * I8_N) >> 3) << 17);      // N = 192: digits 4-6
             constexpr unsigned B_LBO = I8_DIG * 8 * 128;                              // chunk stride of the 448-row operand
-            unsigned it = 0, acc_it = 0;
-            for (int jt = jt_begin; jt < jt_end; ++jt) {
-                const RowTile tile = p.jtiles[jt];
+            unsigned it = 0;
+            for (int u = 0; u < nunits; ++u) {
+                const RowTile tile = p.jtiles[unit_jt(u)];
                 const ChromDesc cd = p.chrom[tile.c];
                 const int nkb = min(tile.I + 1, (cd.m + I8_KB - 1) / I8_KB);
-                for (int s = 0; s < T; ++s, ++acc_it) {
-                    i8_mbar_wait(accempty, (acc_it & 1u) ^ 1u);           // epilogue has drained the accumulators
+                i8_mbar_wait(accempty, ((unsigned)u & 1u) ^ 1u);           // epilogue has drained the accumulators
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                for (int kb = 0; kb < nkb; ++kb, ++it) {
+                    const unsigned slot = it % I8_STAGES, ph = (it / I8_STAGES) & 1u;
+                    i8_mbar_wait(full0 + 8 * slot, ph);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    for (int kb = 0; kb < nkb; ++kb, ++it) {
-                        const unsigned slot = it % I8_STAGES, ph = (it / I8_STAGES) & 1u;
-                        i8_mbar_wait(full0 + 8 * slot, ph);
-                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                        const unsigned a0 = i8_smem_u32(stage0 + slot * I8_STAGE_BYTES);
-                        const unsigned b0 = a0 + I8_A_BYTES;
+                    const unsigned a0 = i8_smem_u32(stage0 + slot * I8_STAGE_BYTES);
+                    const unsigned b0 = a0 + I8_A_BYTES;
 #pragma unroll
-                        for (int kk = 0; kk < I8_KB / 32; ++kk) {
-                            const unsigned long long da = i8_desc(a0 + kk * 2 * (I8_M * 16), I8_M * 16, 128);
-                            const unsigned long long db0 = i8_desc(b0 + kk * 2 * B_LBO, B_LBO, 128);
-                            const unsigned long long db1 = i8_desc(b0 + 32 * 128 + kk * 2 * B_LBO, B_LBO, 128);
-                            i8_mma(tmem_base, da, db0, idescA, (kb | kk) != 0);
-                            i8_mma(tmem_base + 4 * I8_N, da, db1, idescB, (kb | kk) != 0);
-                        }
-                        i8_commit(empty0 + 8 * slot);                     // frees the smem slot when these MMAs retire
+                    for (int kk = 0; kk < I8_KB / 32; ++kk) {
+                        const unsigned long long da = i8_desc(a0 + kk * 2 * (I8_M * 16), I8_M * 16, 128);
+                        const unsigned long long db0 = i8_desc(b0 + kk * 2 * B_LBO, B_LBO, 128);
+                        const unsigned long long db1 = i8_desc(b0 + 32 * 128 + kk * 2 * B_LBO, B_LBO, 128);
+                        i8_mma(tmem_base, da, db0, idescA, (kb | kk) != 0);
+                        i8_mma(tmem_base + 4 * I8_N, da, db1, idescB, (kb | kk) != 0);
                     }
-                    i8_commit(accfull);                                    // accumulators of trait s are complete
+                    i8_commit(empty0 + 8 * slot);                         // frees the smem slot when these MMAs retire
                 }
+                i8_commit(accfull);                                        // accumulators of this (tile, trait) are complete
             }
         }
     } else {
@@ -309,82 +314,157 @@ __global__ void __launch_bounds__(I8_THREADS, 1) i8_contract_kernel(const I8Para
         const bool live = unit < p.n_units;
         int pa = 0, pb = 0;
         if (live) { pa = p.unit_a[unit]; pb = (p.mode == MASK_XI) ? p.unit_b[unit] : 0; }
-        double Z[T][T];
-#pragma unroll
-        for (int t = 0; t < T; ++t)
-#pragma unroll
-            for (int s = 0; s < T; ++s) Z[t][s] = 0.0;
         const unsigned tlane = tmem_base + ((unsigned)(quarter * 32) << 16) + half * 32;
-        unsigned acc_it = 0;
-        for (int jt = jt_begin; jt < jt_end; ++jt) {
-            const RowTile tile = p.jtiles[jt];
-            const ChromDesc cd = p.chrom[tile.c];
-            const long long prow = (long long)cd.pad_off + 64 * tile.I;      // padded index of the tile's first row
-            // stage d_t[j] and scale_s[j] of the 64 rows in shared memory (double-buffered by tile parity)
-            double* rb = rowbuf + ((jt - jt_begin) & 1) * (2 * T * 64);
-            for (int i = etid; i < 2 * T * 64; i += 32 * I8_EPI_WARPS) {
-                const int which = i / (T * 64), rem = i - which * (T * 64), t = rem >> 6, j = rem & 63;
-                rb[i] = __ldg((which ? p.scale : p.emat) + (long long)t * p.mp_total + prow + j);
+        if constexpr (!SOUTER) {
+            double Z[TT][TT];
+    #pragma unroll
+            for (int t = 0; t < TT; ++t)
+    #pragma unroll
+                for (int s = 0; s < TT; ++s) Z[t][s] = 0.0;
+            unsigned acc_it = 0;
+            for (int jt = jt_begin; jt < jt_end; ++jt) {
+                const RowTile tile = p.jtiles[jt];
+                const ChromDesc cd = p.chrom[tile.c];
+                const long long prow = (long long)cd.pad_off + 64 * tile.I;      // padded index of the tile's first row
+                // stage d_t[j] and scale_s[j] of the 64 rows in shared memory (double-buffered by tile parity)
+                double* rb = rowbuf + ((jt - jt_begin) & 1) * (2 * T * 64);
+                for (int i = etid; i < 2 * T * 64; i += 32 * I8_EPI_WARPS) {
+                    const int which = i / (T * 64), rem = i - which * (T * 64), t = rem >> 6, j = rem & 63;
+                    rb[i] = __ldg((which ? p.scale : p.emat) + (long long)t * p.mp_total + prow + j);
+                }
+                unsigned nz = 0u, ng = 0u;                                       // this thread's 32 rows = one word
+                if (live) {
+                    const long long wi = (prow >> 5) + half;
+                    const unsigned A = __ldg(p.planeA + (long long)pa * p.wpp + wi), B = __ldg(p.planeB + (long long)pa * p.wpp + wi);
+                    if (p.mode == MASK_XI) {
+                        const unsigned A2 = __ldg(p.planeA + (long long)pb * p.wpp + wi), B2 = __ldg(p.planeB + (long long)pb * p.wpp + wi);
+                        nz = (A ^ B) & (A2 ^ B2);
+                        ng = ((~A & B) ^ (~A2 & B2)) & nz;
+                    } else {
+                        nz = A ^ B;
+                        ng = (p.mode == MASK_DELTA) ? (~A & B) : 0u;
+                    }
+                }
+                asm volatile("bar.sync 1, %0;" ::"n"(32 * I8_EPI_WARPS) : "memory");
+                const double* erow = rb + half * 32;                 // d_t[j]:     erow[t * 64 + c]
+                const double* srow = rb + T * 64 + half * 32;        // scale_s[j]: srow[s * 64 + c]
+    #pragma unroll
+                for (int s = 0; s < TT; ++s, ++acc_it) {               // unrolled: Z[t][s] must stay in registers
+                    i8_mbar_wait(accfull, acc_it & 1u);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    #pragma unroll 1
+                    for (int cb = 0; cb < 8; ++cb) {                                 // 4 SNP rows at a time
+                        int dig[I8_DIG][4];
+    #pragma unroll
+                        for (int i = 0; i < I8_DIG; ++i) i8_tmem_ld4(tlane + i * I8_N + cb * 4, dig[i]);
+                        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                        if (cb == 7) {                                               // TMEM fully read: next trait's MMAs may start
+                            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                            __syncwarp();
+                            if (lane == 0) i8_mbar_arrive(accempty);
+                        }
+                        const unsigned nzw = nz >> (4 * cb), ngw = ng >> (4 * cb);
+    #pragma unroll
+                        for (int c = 0; c < 4; ++c) {
+                            // sum_i S_i 128^-(i+1): pairs of digits combined exactly in int32, then 4 exact int->fp64 terms
+                            const int w0 = dig[0][c] * 128 + dig[1][c], w1 = dig[2][c] * 128 + dig[3][c];
+                            const int w2 = dig[4][c] * 128 + dig[5][c], w3 = dig[6][c];
+                            double v = (double)w3 * 0x1p-49;
+                            v = fma((double)w2, 0x1p-42, v);
+                            v = fma((double)w1, 0x1p-28, v);
+                            v = fma((double)w0, 0x1p-14, v);
+                            v *= srow[s * 64 + cb * 4 + c];                // exact power-of-two row scale
+                            long long bits = __double_as_longlong(v);
+                            if (!((nzw >> c) & 1u)) bits = 0ll;
+                            bits ^= (long long)((ngw >> c) & 1u) << 63;
+                            v = __longlong_as_double(bits);
+    #pragma unroll
+                            for (int t = 0; t < TT; ++t) Z[t][s] = fma(erow[t * 64 + cb * 4 + c], v, Z[t][s]);
+                        }
+                    }
+                }
             }
-            unsigned nz = 0u, ng = 0u;                                       // this thread's 32 rows = one word
             if (live) {
-                const long long wi = (prow >> 5) + half;
-                const unsigned A = __ldg(p.planeA + (long long)pa * p.wpp + wi), B = __ldg(p.planeB + (long long)pa * p.wpp + wi);
-                if (p.mode == MASK_XI) {
-                    const unsigned A2 = __ldg(p.planeA + (long long)pb * p.wpp + wi), B2 = __ldg(p.planeB + (long long)pb * p.wpp + wi);
-                    nz = (A ^ B) & (A2 ^ B2);
-                    ng = ((~A & B) ^ (~A2 & B2)) & nz;
-                } else {
-                    nz = A ^ B;
-                    ng = (p.mode == MASK_DELTA) ? (~A & B) : 0u;
-                }
+                // the two column halves of a cross go to two partial slabs (summed by finalize_sym)
+                double* out = p.Zpart + ((long long)(split * 2 + half) * p.n_units + unit) * (T * T);
+    #pragma unroll
+                for (int t = 0; t < TT; ++t)
+    #pragma unroll
+                    for (int s = 0; s < TT; ++s) out[t * T + s] = Z[t][s];
             }
-            asm volatile("bar.sync 1, %0;" ::"n"(32 * I8_EPI_WARPS) : "memory");
-            const double* erow = rb + half * 32;                 // d_t[j]:     erow[t * 64 + c]
-            const double* srow = rb + T * 64 + half * 32;        // scale_s[j]: srow[s * 64 + c]
+        } else {
+            // ---- trait s outer, tile inner: Z[:, s] in registers, any T <= TT
+            unsigned acc_it = 0;
+            for (int s = 0; s < T; ++s) {
+                double zs[TT];
 #pragma unroll
-            for (int s = 0; s < T; ++s, ++acc_it) {               // unrolled: Z[t][s] must stay in registers
-                i8_mbar_wait(accfull, acc_it & 1u);
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                for (int t = 0; t < TT; ++t) zs[t] = 0.0;
+                for (int jt = jt_begin; jt < jt_end; ++jt, ++acc_it) {
+                    const RowTile tile = p.jtiles[jt];
+                    const ChromDesc cd = p.chrom[tile.c];
+                    const long long prow = (long long)cd.pad_off + 64 * tile.I;
+                    double* rb = rowbuf + (acc_it & 1) * ((T + 1) * 64);           // [T][64] d_t[j], then [64] scale_s[j]
+                    for (int i = etid; i < (T + 1) * 64; i += 32 * I8_EPI_WARPS) {
+                        const int t = i >> 6, j = i & 63;
+                        rb[i] = (t < T) ? __ldg(p.emat + (long long)t * p.mp_total + prow + j)
+                                        : __ldg(p.scale + (long long)s * p.mp_total + prow + j);
+                    }
+                    unsigned nz = 0u, ng = 0u;
+                    if (live) {
+                        const long long wi = (prow >> 5) + half;
+                        const unsigned A = __ldg(p.planeA + (long long)pa * p.wpp + wi), B = __ldg(p.planeB + (long long)pa * p.wpp + wi);
+                        if (p.mode == MASK_XI) {
+                            const unsigned A2 = __ldg(p.planeA + (long long)pb * p.wpp + wi), B2 = __ldg(p.planeB + (long long)pb * p.wpp + wi);
+                            nz = (A ^ B) & (A2 ^ B2);
+                            ng = ((~A & B) ^ (~A2 & B2)) & nz;
+                        } else {
+                            nz = A ^ B;
+                            ng = (p.mode == MASK_DELTA) ? (~A & B) : 0u;
+                        }
+                    }
+                    asm volatile("bar.sync 1, %0;" ::"n"(32 * I8_EPI_WARPS) : "memory");
+                    const double* erow = rb + half * 32;
+                    const double* srow = rb + T * 64 + half * 32;
+                    i8_mbar_wait(accfull, acc_it & 1u);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll 1
-                for (int cb = 0; cb < 8; ++cb) {                                 // 4 SNP rows at a time
-                    int dig[I8_DIG][4];
+                    for (int cb = 0; cb < 8; ++cb) {
+                        int dig[I8_DIG][4];
 #pragma unroll
-                    for (int i = 0; i < I8_DIG; ++i) i8_tmem_ld4(tlane + i * I8_N + cb * 4, dig[i]);
-                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                    if (cb == 7) {                                               // TMEM fully read: next trait's MMAs may start
-                        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-                        __syncwarp();
-                        if (lane == 0) i8_mbar_arrive(accempty);
-                    }
-                    const unsigned nzw = nz >> (4 * cb), ngw = ng >> (4 * cb);
+                        for (int i = 0; i < I8_DIG; ++i) i8_tmem_ld4(tlane + i * I8_N + cb * 4, dig[i]);
+                        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                        if (cb == 7) {
+                            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                            __syncwarp();
+                            if (lane == 0) i8_mbar_arrive(accempty);
+                        }
+                        const unsigned nzw = nz >> (4 * cb), ngw = ng >> (4 * cb);
 #pragma unroll
-                    for (int c = 0; c < 4; ++c) {
-                        // sum_i S_i 128^-(i+1): pairs of digits combined exactly in int32, then 4 exact int->fp64 terms
-                        const int w0 = dig[0][c] * 128 + dig[1][c], w1 = dig[2][c] * 128 + dig[3][c];
-                        const int w2 = dig[4][c] * 128 + dig[5][c], w3 = dig[6][c];
-                        double v = (double)w3 * 0x1p-49;
-                        v = fma((double)w2, 0x1p-42, v);
-                        v = fma((double)w1, 0x1p-28, v);
-                        v = fma((double)w0, 0x1p-14, v);
-                        v *= srow[s * 64 + cb * 4 + c];                // exact power-of-two row scale
-                        long long bits = __double_as_longlong(v);
-                        if (!((nzw >> c) & 1u)) bits = 0ll;
-                        bits ^= (long long)((ngw >> c) & 1u) << 63;
-                        v = __longlong_as_double(bits);
+                        for (int c = 0; c < 4; ++c) {
+                            const int w0 = dig[0][c] * 128 + dig[1][c], w1 = dig[2][c] * 128 + dig[3][c];
+                            const int w2 = dig[4][c] * 128 + dig[5][c], w3 = dig[6][c];
+                            double v = (double)w3 * 0x1p-49;
+                            v = fma((double)w2, 0x1p-42, v);
+                            v = fma((double)w1, 0x1p-28, v);
+                            v = fma((double)w0, 0x1p-14, v);
+                            v *= srow[cb * 4 + c];
+                            long long bits = __double_as_longlong(v);
+                            if (!((nzw >> c) & 1u)) bits = 0ll;
+                            bits ^= (long long)((ngw >> c) & 1u) << 63;
+                            v = __longlong_as_double(bits);
 #pragma unroll
-                        for (int t = 0; t < T; ++t) Z[t][s] = fma(erow[t * 64 + cb * 4 + c], v, Z[t][s]);
+                            for (int t = 0; t < TT; ++t)
+                                if (t < T) zs[t] = fma(erow[t * 64 + cb * 4 + c], v, zs[t]);
+                        }
                     }
                 }
+                if (live) {
+                    double* out = p.Zpart + ((long long)(split * 2 + half) * p.n_units + unit) * (T * T);
+#pragma unroll
+                    for (int t = 0; t < TT; ++t)
+                        if (t < T) out[t * T + s] = zs[t];
+                }
             }
-        }
-        if (live) {
-            // the two column halves of a cross go to two partial slabs (summed by finalize_sym)
-            double* out = p.Zpart + ((long long)(split * 2 + half) * p.n_units + unit) * (T * T);
-#pragma unroll
-            for (int t = 0; t < T; ++t)
-#pragma unroll
-                for (int s = 0; s < T; ++s) out[t * T + s] = Z[t][s];
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -395,7 +475,10 @@ __global__ void __launch_bounds__(I8_THREADS, 1) i8_contract_kernel(const I8Para
     }
 }
 
-size_t i8_smem_bytes(int T) { return (size_t)I8_STAGES * I8_STAGE_BYTES + (2 * I8_STAGES + 4) * 8 + (size_t)2 * 2 * T * 64 * 8; }
+size_t i8_smem_bytes(int T) {
+    const int rows = T <= 6 ? 2 * T : T + 1;          // per buffer: d_t[j] rows + scale rows (see the two epilogues)
+    return (size_t)I8_STAGES * I8_STAGE_BYTES + (2 * I8_STAGES + 4) * 8 + (size_t)2 * rows * 64 * 8;
+}
 
 cudaError_t launch_i8_build_xi(const unsigned* planeA, const unsigned* planeB, long long wpp, const int* sire,
                                const int* dam, long long n_units, int mode, long long nkb_total, signed char* xi,
@@ -424,15 +507,26 @@ cudaError_t launch_i8_contract(const I8Params& p, int ntiles, int nsplit, cudaSt
     const size_t smem = i8_smem_bytes(p.T);
     dim3 grid(ntiles, nsplit);
     cudaError_t e = cudaSuccess;
-#define GMS_I8(TV)                                                                                                  \
-    case TV:                                                                                                        \
-        e = cudaFuncSetAttribute(i8_contract_kernel<TV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);   \
-        if (e != cudaSuccess) return e;                                                                             \
-        i8_contract_kernel<TV><<<grid, I8_THREADS, smem, st>>>(p);                                                  \
-        break;
+#define GMS_I8(TV, SO)                                                                                                  \
+    {                                                                                                                   \
+        e = cudaFuncSetAttribute(i8_contract_kernel<TV, SO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);   \
+        if (e != cudaSuccess) return e;                                                                                 \
+        i8_contract_kernel<TV, SO><<<grid, I8_THREADS, smem, st>>>(p);                                                  \
+    }
     switch (p.T) {
-        GMS_I8(1) GMS_I8(2) GMS_I8(3) GMS_I8(4) GMS_I8(5) GMS_I8(6)
-        default: return cudaErrorInvalidValue;
+        case 1: GMS_I8(1, false) break;
+        case 2: GMS_I8(2, false) break;
+        case 3: GMS_I8(3, false) break;
+        case 4: GMS_I8(4, false) break;
+        case 5: GMS_I8(5, false) break;
+        case 6: GMS_I8(6, false) break;
+        default:
+            if (p.T <= 8) GMS_I8(8, true)
+            else if (p.T <= 12) GMS_I8(12, true)
+            else if (p.T <= 16) GMS_I8(16, true)
+            else if (p.T <= 24) GMS_I8(24, true)
+            else if (p.T <= 32) GMS_I8(32, true)
+            else return cudaErrorInvalidValue;
     }
 #undef GMS_I8
     return cudaGetLastError();

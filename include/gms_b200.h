@@ -83,17 +83,17 @@ GMS_API int gms_set_recomb_blocks(gms_handle* h, int C, const int64_t* m_c, cons
 GMS_API int gms_set_haplotypes_i32cm(gms_handle* h, int64_t P, int64_t m, const int32_t* hap);
 GMS_API int gms_set_haplotypes_u8rm(gms_handle* h, int64_t P, int64_t m, const uint8_t* hap);
 
-/* Optional: evaluation mode. The default, GMS_MODE_AUTO, uses GMS_MODE_INT8_TENSOR when it applies (T <= 6)
- * and GMS_MODE_DENSE otherwise; both are valid for any symmetric recombFreqMat and agree to FP64 rounding.
+/* Optional: evaluation mode. The default, GMS_MODE_AUTO, uses GMS_MODE_INT8_TENSOR when its operand images fit
+ * in HBM (a few GB at cassava scale) and GMS_MODE_DENSE otherwise; both are valid for any symmetric recombFreqMat and agree to FP64 rounding.
  * GMS_MODE_DENSE is the dense FP64 tensor (DMMA) contraction against the stored R / RoR blocks. GMS_MODE_MAP_SCAN is the map-structured
  * fast path: when the blocks came from gms_set_genmap() with positions sorted within each
  * chromosome, R[j,k] = exp(-2|x_j-x_k|/100) factorises and every quadratic form becomes a prefix-sum
  * scan over the non-zero SNPs of a unit (O(m T^2) per cross instead of O(m^2 T)); same results to ~1e-13.
  * Returns GMS_ESTATE if the handle's blocks did not come from a sorted map.
- * GMS_MODE_INT8_TENSOR (any symmetric matrix, AD / DirDom, T <= 6): the per-cross dominance contraction runs
+ * GMS_MODE_INT8_TENSOR (any symmetric matrix, any model, T <= 32): the per-cross dominance contraction runs
  * on the int8 tcgen05 tensor cores - RoR.d is split into 7 exact radix-128 int8 digit planes, xi is ternary,
  * int32 accumulation in TMEM is exact, digits are recombined in FP64 (error <= 2^-49 of the row maximum).
- * The per-parent tables still use the FP64 contraction. Falls back to GMS_MODE_DENSE for T > 6. */
+ * All tables (per parent and per cross) use it. Falls back to GMS_MODE_DENSE if the images would not fit. */
 enum { GMS_MODE_DENSE = 0, GMS_MODE_MAP_SCAN = 1, GMS_MODE_INT8_TENSOR = 2, GMS_MODE_AUTO = 3 };
 GMS_API int gms_set_mode(gms_handle* h, int mode);
 

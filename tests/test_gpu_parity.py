@@ -355,7 +355,8 @@ def test_predict_sharded_one_process(gms):
 
 
 # ---------------------------------------------------------------- exact int8 tensor-core path (tcgen05)
-@pytest.mark.parametrize("model,T", [("AD", 1), ("AD", 2), ("AD", 5), ("DirDom", 3), ("AD", 6)])
+@pytest.mark.parametrize("model,T", [("AD", 1), ("AD", 2), ("AD", 5), ("DirDom", 3), ("AD", 6), ("A", 4),
+                                     ("AD", 7), ("AD", 10), ("DirDom", 13), ("AD", 24)])
 def test_int8_tensor_mode_matches_oracle_and_dense(gms, model, T):
     s = synth(500 + T, [200, 131, 77, 300], P=24, T=T)
     rng = np.random.default_rng(8)
@@ -363,14 +364,16 @@ def test_int8_tensor_mode_matches_oracle_and_dense(gms, model, T):
     dam = rng.integers(0, 24, 150).astype(np.int32)
     sire[:5] = dam[:5]
     asub = s["asub"] if model == "DirDom" else None
+    dom = s["dom"] if model != "A" else None
     eng = gms.CrossVarEngine(0)
     eng.set_genmap(s["cM"], s["m_c"])
     eng.set_haplotypes(s["H"])
     eng.set_mode("fp64")
-    dense, nseg_d = eng.predict(model, s["add"], s["dom"], asub, sire, dam)
+    dense, nseg_d = eng.predict(model, s["add"], dom, asub, sire, dam)
     eng.set_mode("int8_tensor")
-    out, nseg = eng.predict(model, s["add"], s["dom"], asub, sire, dam)
-    want, wseg = oracle_slab(model, s["H"], s["R"], s["add"], s["dom"], asub, sire, dam)
+    out, nseg = eng.predict(model, s["add"], dom, asub, sire, dam)
+    assert eng.stats()["last_mode"] == 2
+    want, wseg = oracle_slab(model, s["H"], s["R"], s["add"], dom, asub, sire, dam)
     assert np.array_equal(nseg, wseg)
     assert rel_err(dense, want) < TOL
     assert rel_err(out, want) < TOL
@@ -407,10 +410,10 @@ def test_trait_count_limits(gms):
     out, nseg = eng.predict("AD", s["add"], s["dom"], None, sire, dam)            # T = 32: 2 units per tile
     want, wseg = oracle_slab("AD", s["H"], s["R"], s["add"], s["dom"], None, sire, dam)
     assert out.shape == (3, 528, 2) and np.array_equal(nseg, wseg) and rel_err(out, want) < TOL
-    assert eng.stats()["last_mode"] == 0                                           # auto resolved to the FP64 path (T > 6)
-    eng.set_mode("int8_tensor")                                                   # T > 6: falls back to the FP64 path
+    assert eng.stats()["last_mode"] == 2                                           # auto -> exact int8 tensor path
+    eng.set_mode("fp64")
     again, _ = eng.predict("AD", s["add"], s["dom"], None, sire, dam)
-    assert np.array_equal(again, out)
+    assert eng.stats()["last_mode"] == 0 and rel_err(again, want) < TOL
     big = np.zeros((s["m"], 33))
     with pytest.raises(gms.GmsError, match="1..32"):
         eng.predict("A", big, None, None, sire, dam)
