@@ -69,7 +69,10 @@ class ClockSampler:
 
     def _read(self):
         for ln in self.proc.stdout:
-            self.lines.append(ln.strip())
+            self.lines.append((time.time(), ln.strip()))
+
+    def window(self, t0, t1):
+        self.t0, self.t1 = t0, t1
 
     def stop(self):
         if not self.proc:
@@ -80,7 +83,11 @@ class ClockSampler:
         except Exception:
             self.proc.kill()
         sm, mx, pw, reasons = [], [], [], set()
-        for ln in self.lines:
+        t0, t1 = getattr(self, "t0", None), getattr(self, "t1", None)
+        inside = [ln for (ts, ln) in self.lines if t0 is None or (t0 <= ts <= t1 + 0.06)]
+        if not inside:          # timed region shorter than one sampling period: the closest samples under load
+            inside = [ln for (ts, ln) in self.lines if t1 is None or ts <= t1 + 0.06][-3:]
+        for ln in inside:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 9:
                 continue
@@ -301,17 +308,25 @@ def main():
         for _ in range(args.warmup):
             eng.compute(sync=True)
         sampler = ClockSampler(local_rank) if with_clocks else None
-        barrier()
         if sampler:
-            sampler.start()
+            sampler.start()       # nvidia-smi needs ~0.3 s to start: run it through the warm-up, keep the timed window
+            tw = time.time()
+            while len(sampler.lines) < 2 and time.time() - tw < 3.0:
+                eng.compute(sync=True)
+        barrier()
+        w0 = time.time()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
         for _ in range(args.steps):
             eng.compute(sync=False)
         e1.record(stream)
         barrier()
+        w1 = time.time()
         ms = max_over_ranks(e0.elapsed_time(e1))
-        clocks = sampler.stop() if sampler else None
+        clocks = None
+        if sampler:
+            sampler.window(w0, w1)
+            clocks = sampler.stop()
         # dominant-kernel duration: CUDA events recorded around the launch on the same stream (inside the
         # library); averaged over separate, synchronised steps so that every launch is read back
         kernel_ms, stage_ms = [], []

@@ -86,7 +86,8 @@ struct gms_handle {
     DevBuf<long long> gbase_d;
     DevBuf<signed char> xi_d, xi_het_d, xi_delta_d, G_d, G_add_d, G_asub_d;
     DevBuf<double> scale_d, scale_add_d, scale_asub_d;
-    DevBuf<int> split_i8_d, split_i8_par_d;
+    DevBuf<int> split_i8_d, split_i8_par_d, i8_rowpref_d, i8_blkpref_d;
+    int i8_nrows = 0, i8_nblks = 0;
     Plan plan_i8, plan_i8_par;
     bool use_i8 = false;
 
@@ -363,7 +364,7 @@ void gms_destroy(gms_handle* h) {
     h->S_asub.release(); h->split_scan_par_d.release(); h->split_scan_x_d.release();
     h->jtiles_d.release(); h->gbase_d.release(); h->xi_d.release(); h->G_d.release(); h->scale_d.release(); h->split_i8_d.release();
     h->xi_het_d.release(); h->xi_delta_d.release(); h->G_add_d.release(); h->G_asub_d.release(); h->scale_add_d.release();
-    h->scale_asub_d.release(); h->split_i8_par_d.release();
+    h->scale_asub_d.release(); h->split_i8_par_d.release(); h->i8_rowpref_d.release(); h->i8_blkpref_d.release();
     for (auto& ev : h->ev) if (ev) cudaEventDestroy(ev);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     delete h;
@@ -636,6 +637,23 @@ int gms_stage_inputs(gms_handle* h, int model, int T, const double* add, const d
             for (int J = 0; J < nJ; ++J) h->jtiles.push_back(RowTile{c, J});
         }
         h->i8_gbytes = gb;
+        {   // block prefixes so that ONE launch covers every chromosome of the shard (indexed by chromosome id)
+            std::vector<int> rowpref(h->C + 1, 0), blkpref(h->C + 1, 0);
+            int rows = 0, blks = 0;
+            for (int c = 0; c < h->C; ++c) {
+                rowpref[c] = rows; blkpref[c] = blks;
+                if (c >= h->c_begin && c < h->c_end) {
+                    const int nJ = (h->chrom[c].m + 63) / 64;
+                    rows += nJ * 64; blks += nJ * (nJ + 1) / 2;
+                }
+            }
+            rowpref[h->C] = rows; blkpref[h->C] = blks;
+            h->i8_nrows = rows; h->i8_nblks = blks;
+            CU(h->i8_rowpref_d.ensure(h->C + 1)); CU(h->i8_blkpref_d.ensure(h->C + 1));
+            CU(cudaMemcpyAsync(h->i8_rowpref_d.p, rowpref.data(), sizeof(int) * (h->C + 1), cudaMemcpyHostToDevice, h->stream));
+            CU(cudaMemcpyAsync(h->i8_blkpref_d.p, blkpref.data(), sizeof(int) * (h->C + 1), cudaMemcpyHostToDevice, h->stream));
+            CU(cudaStreamSynchronize(h->stream));     // the vectors above are locals
+        }
         CU(h->jtiles_d.ensure(h->jtiles.size()));
         CU(h->gbase_d.ensure(h->C));
         CU(cudaMemcpyAsync(h->jtiles_d.p, h->jtiles.data(), sizeof(RowTile) * h->jtiles.size(), cudaMemcpyHostToDevice, h->stream));
@@ -730,9 +748,9 @@ int gms_compute(gms_handle* h, int sync) {
     } else if (h->use_i8) {
         auto digits = [&](const double* tiles, const double* emat, DevBuf<signed char>& G, DevBuf<double>& sc) -> int {
             CU(cudaMemsetAsync(sc.p, 0, sizeof(double) * h->mp_total * T, h->stream));
-            for (int c = h->c_begin; c < h->c_end; ++c)
-                CU(launch_i8_build_digits(tiles, h->chrom_d.p, h->chrom[c], c, emat, h->mp_total, T, sc.p, h->gbase[c], G.p, h->stream));
-            h->st.last_launches += 2 * (h->c_end - h->c_begin);
+            CU(launch_i8_build_digits(tiles, h->chrom_d.p, h->c_begin, h->c_end, h->i8_rowpref_d.p, h->i8_nrows, h->i8_blkpref_d.p,
+                                      h->i8_nblks, emat, h->mp_total, T, sc.p, h->gbase_d.p, G.p, h->stream));
+            h->st.last_launches += 2;
             return GMS_OK;
         };
         if (int rc = digits(h->R.p, h->emat_add.p, h->G_add_d, h->scale_add_d)) return rc;

@@ -96,70 +96,95 @@ __device__ __forceinline__ double lprime64(const double* __restrict__ tiles, con
     return v;
 }
 
-// scale[s][pj] = 2^E with |G_s[j,k]| < 2^E for every k of row j's lower-triangle range (1 if the row is zero)
-__global__ void i8_rowscale_kernel(const double* __restrict__ tiles, const ChromDesc* __restrict__ chrom, int c,
-                                   const double* __restrict__ emat, long long mp_total, int T,
-                                   double* __restrict__ scale) {
+// scale[s][pj] = 2^E with |G_s[j,k]| < 2^E for every k of row j's lower-triangle range (1 if the row is zero).
+// One block per row; every L' element is read ONCE and used for all T traits.
+__global__ void i8_rowscale_kernel(const double* __restrict__ tiles, const ChromDesc* __restrict__ chrom, int c_begin,
+                                   int c_end, const int* __restrict__ rowpref, const double* __restrict__ emat,
+                                   long long mp_total, int T, double* __restrict__ scale) {
+    int c = c_begin;
+    while (c + 1 < c_end && (int)blockIdx.x >= rowpref[c + 1]) ++c;     // rowpref[c] = first block of chromosome c
     const ChromDesc cd = chrom[c];
-    const int row = blockIdx.x;                        // local row (< roundup(m,64))
-    const int s = blockIdx.y;
+    const int row = blockIdx.x - rowpref[c];           // local row (< roundup(m,64))
     const int kend = min(cd.m, ((row >> 6) + 1) << 6);
-    double mx = 0.0;
-    if (row < cd.m)
-        for (int k = threadIdx.x; k < kend; k += blockDim.x)
-            mx = fmax(mx, fabs(lprime64(tiles, cd, row, k) * emat[(long long)s * mp_total + cd.pad_off + k]));
-    __shared__ double sh[32];
+    double mx[MAX_T];
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = mx;
+    for (int s = 0; s < MAX_T; ++s) mx[s] = 0.0;
+    if (row < cd.m)
+        for (int k = threadIdx.x; k < kend; k += blockDim.x) {
+            const double l = fabs(lprime64(tiles, cd, row, k));
+            const double* e = emat + cd.pad_off + k;
+#pragma unroll
+            for (int s = 0; s < MAX_T; ++s)
+                if (s < T) mx[s] = fmax(mx[s], l * fabs(e[(long long)s * mp_total]));
+        }
+    __shared__ double sh[4][MAX_T];
+#pragma unroll
+    for (int s = 0; s < MAX_T; ++s) {
+        if (s < T) {
+            double v = mx[s];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+            if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5][s] = v;
+        }
+    }
     __syncthreads();
-    if (threadIdx.x == 0) {
-        for (int i = 1; i < (int)(blockDim.x >> 5); ++i) mx = fmax(mx, sh[i]);
+    if (threadIdx.x < T) {
+        double v = 0.0;
+        for (int i = 0; i < (int)(blockDim.x >> 5); ++i) v = fmax(v, sh[i][threadIdx.x]);
         int e = 0;
-        if (mx > 0.0) { (void)frexp(mx, &e); }          // mx = f * 2^e, f in [0.5, 1)  =>  mx < 2^e
-        scale[(long long)s * mp_total + cd.pad_off + row] = ldexp(1.0, e);
+        if (v > 0.0) { (void)frexp(v, &e); }            // v = f * 2^e, f in [0.5, 1)  =>  v < 2^e
+        scale[(long long)threadIdx.x * mp_total + cd.pad_off + row] = ldexp(1.0, e);
     }
 }
 
-// digit images: (c, J, kb <= J, s, digit i): [cc (4)][r1 (8)][r0 (8)][16 bytes]; one thread = 16 consecutive k of a row
-__global__ void i8_build_digits_kernel(const double* __restrict__ tiles, const ChromDesc* __restrict__ chrom, int c,
-                                       const double* __restrict__ emat, long long mp_total, int T,
-                                       const double* __restrict__ scale, long long gbase, signed char* __restrict__ G) {
+// digit images: (c, J, kb <= J, s): one 448-row K-major operand per (block, trait); one thread = 16 consecutive k of a
+// row, L' read once and reused for all T traits
+__global__ void i8_build_digits_kernel(const double* __restrict__ tiles, const ChromDesc* __restrict__ chrom, int c_begin,
+                                       int c_end, const int* __restrict__ blkpref, const double* __restrict__ emat,
+                                       long long mp_total, int T, const double* __restrict__ scale,
+                                       const long long* __restrict__ gbase_c, signed char* __restrict__ G) {
+    int c = c_begin;
+    while (c + 1 < c_end && (int)blockIdx.x >= blkpref[c + 1]) ++c;     // blkpref[c] = first block of chromosome c
     const ChromDesc cd = chrom[c];
-    const int blk = blockIdx.x;                       // index of (J, kb) in the lower block triangle
+    const long long gbase = gbase_c[c];
+    const int blk = blockIdx.x - blkpref[c];          // index of (J, kb) in the lower block triangle
     int J = (int)((sqrt(8.0 * blk + 1.0) - 1.0) * 0.5);
     while ((J + 1) * (J + 2) / 2 <= blk) ++J;
     while (J * (J + 1) / 2 > blk) --J;
     const int kb = blk - J * (J + 1) / 2;
-    const int s = blockIdx.y;
     const int r = threadIdx.x & 63, cc = threadIdx.x >> 6;      // 256 threads: 64 rows x 4 chunks
     const int row = J * 64 + r;
-    signed char d[I8_DIG][16];
-    const double inv = 1.0 / scale[(long long)s * mp_total + cd.pad_off + row];     // exact: a power of two
+    double lp[16];
 #pragma unroll
     for (int b = 0; b < 16; ++b) {
         const int col = kb * 64 + cc * 16 + b;
-        double g = 0.0;
-        if (row < cd.m && col < cd.m)
-            g = lprime64(tiles, cd, row, col) * emat[(long long)s * mp_total + cd.pad_off + col];
-        double rr = g * inv;                           // |rr| < 1, exact
-#pragma unroll
-        for (int i = 0; i < I8_DIG; ++i) {
-            rr *= 128.0;                               // exact
-            const double t = trunc(rr);                // |t| <= 127
-            d[i][b] = (signed char)(int)t;
-            rr -= t;                                   // exact
-        }
+        lp[b] = (row < cd.m && col < cd.m) ? lprime64(tiles, cd, row, col) : 0.0;
     }
     // the 7 digit planes of one (block, trait) form ONE K-major operand of 7 x 64 = 448 rows:
     // [chunk cc (4)][row group R1 = 8 i + r1 (56)][r0 (8)][16 bytes]  ->  LBO = 56 * 128 B, SBO = 128 B,
     // so a k32-step needs two MMAs (N = 256: digits 0-3, N = 192: digits 4-6) instead of seven N = 64 ones
     const int r1 = r >> 3, r0 = r & 7;
+    const double* ecol = emat + cd.pad_off + kb * 64 + cc * 16;
+    for (int s = 0; s < T; ++s) {
+        const double inv = 1.0 / scale[(long long)s * mp_total + cd.pad_off + row];     // exact: a power of two
+        signed char d[I8_DIG][16];
 #pragma unroll
-    for (int i = 0; i < I8_DIG; ++i) {
-        signed char* dst = G + gbase + (((long long)blk * T + s) * (I8_DIG * (long long)I8_B_BYTES)) +
-                           ((cc * (I8_DIG * 8) + (i * 8 + r1)) * 8 + r0) * 16;
-        *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(d[i]);
+        for (int b = 0; b < 16; ++b) {
+            double rr = (lp[b] * ecol[(long long)s * mp_total + b]) * inv;             // |rr| < 1
+#pragma unroll
+            for (int i = 0; i < I8_DIG; ++i) {
+                rr *= 128.0;                               // exact
+                const double t = trunc(rr);                // |t| <= 127
+                d[i][b] = (signed char)(int)t;
+                rr -= t;                                   // exact
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < I8_DIG; ++i) {
+            signed char* dst = G + gbase + (((long long)blk * T + s) * (I8_DIG * (long long)I8_B_BYTES)) +
+                               ((cc * (I8_DIG * 8) + (i * 8 + r1)) * 8 + r0) * 16;
+            *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(d[i]);
+        }
     }
 }
 
@@ -491,14 +516,13 @@ cudaError_t launch_i8_build_xi(const unsigned* planeA, const unsigned* planeB, l
     return cudaGetLastError();
 }
 
-cudaError_t launch_i8_build_digits(const double* tiles, const ChromDesc* chrom_d, const ChromDesc& cd, int c,
-                                   const double* emat, long long mp_total, int T, double* scale, long long gbase,
-                                   signed char* G, cudaStream_t st) {
-    const int nJ = (cd.m + 63) / 64;
-    dim3 g1(nJ * 64, T);
-    i8_rowscale_kernel<<<g1, 128, 0, st>>>(tiles, chrom_d, c, emat, mp_total, T, scale);
-    dim3 g2(nJ * (nJ + 1) / 2, T);
-    i8_build_digits_kernel<<<g2, 256, 0, st>>>(tiles, chrom_d, c, emat, mp_total, T, scale, gbase, G);
+cudaError_t launch_i8_build_digits(const double* tiles, const ChromDesc* chrom_d, int c_begin, int c_end,
+                                   const int* rowpref_d, int nrows, const int* blkpref_d, int nblks, const double* emat,
+                                   long long mp_total, int T, double* scale, const long long* gbase_d, signed char* G,
+                                   cudaStream_t st) {
+    if (nrows == 0) return cudaSuccess;
+    i8_rowscale_kernel<<<nrows, 128, 0, st>>>(tiles, chrom_d, c_begin, c_end, rowpref_d, emat, mp_total, T, scale);
+    i8_build_digits_kernel<<<nblks, 256, 0, st>>>(tiles, chrom_d, c_begin, c_end, blkpref_d, emat, mp_total, T, scale, gbase_d, G);
     return cudaGetLastError();
 }
 
