@@ -59,3 +59,47 @@ def test_edge_shapes(case, mode):
     want, wseg = oracle_slab(model, H, R, add, d, a, sire, dam)
     assert np.array_equal(nseg, wseg)
     assert rel_err(out, want) < 1e-9
+
+
+def test_one_engine_many_calls():
+    """State handling of a long-lived handle (the CV driver's usage): changing model, trait count, cross
+    count, mode, chromosome shard and haplotypes between calls on ONE engine; every answer against the oracle."""
+    import genomicmateselectr_b200 as g
+    m_c, cM, chrom, H, add, dom, asub, R = make(5, [150, 90, 33], 12, 9)
+    rng = np.random.default_rng(0)
+    eng = g.CrossVarEngine(0)
+    eng.set_genmap(cM, m_c)
+    eng.set_haplotypes(H)
+    plan = [("AD", 5, 200, "auto"), ("A", 2, 7, "fp64"), ("DirDom", 9, 130, "auto"), ("AD", 1, 1, "map_scan"),
+            ("AD", 6, 300, "int8_tensor"), ("AD", 3, 0, "auto"), ("DirDom", 4, 50, "fp64"), ("A", 9, 64, "map_scan")]
+    for model, T, N, mode in plan:
+        sire = rng.integers(0, 12, N).astype(np.int32)
+        dam = rng.integers(0, 12, N).astype(np.int32)
+        d = dom[:, :T] if model != "A" else None
+        a = asub[:, :T] if model == "DirDom" else None
+        eng.set_mode(mode)
+        out, nseg = eng.predict(model, add[:, :T], d, a, sire, dam)
+        want, wseg = oracle_slab(model, H, R, add[:, :T], d, a, sire, dam)
+        assert np.array_equal(nseg, wseg), (model, T, N, mode)
+        if N:
+            assert rel_err(out, want) < 1e-9, (model, T, N, mode)
+        gebv, mbv, _ = eng.cross_means(add[:, :T], None, sire, dam)            # interleaved "next row" call
+        assert np.allclose(gebv, (H[0::2].astype(float) + H[1::2]) @ add[:, :T], rtol=1e-12)
+    # new haplotypes (fewer parents) on the same map, then a chromosome shard
+    H2 = H[:8]
+    eng.set_haplotypes(H2)
+    eng.set_mode("auto")
+    sire, dam = np.array([0, 1, 2, 3], np.int32), np.array([3, 3, 0, 2], np.int32)
+    out, nseg = eng.predict("AD", add[:, :4], dom[:, :4], None, sire, dam)
+    want, wseg = oracle_slab("AD", H2, R, add[:, :4], dom[:, :4], None, sire, dam)
+    assert np.array_equal(nseg, wseg) and rel_err(out, want) < 1e-9
+    acc, accn = np.zeros_like(out), np.zeros_like(nseg)
+    for c0, c1 in ((0, 2), (2, 3)):
+        eng.set_chromosome_shard(c0, c1)
+        o, n = eng.predict("AD", add[:, :4], dom[:, :4], None, sire, dam)
+        acc += o
+        accn += n
+    assert np.array_equal(accn, wseg) and rel_err(acc, want) < 1e-9
+    with pytest.raises(g.GmsError, match="out of range"):
+        eng.predict("A", add[:, :1], None, None, [9], [0])                      # parent 9 no longer exists
+    eng.close()
