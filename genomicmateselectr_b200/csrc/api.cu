@@ -3,6 +3,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <new>
@@ -90,6 +91,8 @@ struct gms_handle {
     int i8_nrows = 0, i8_nblks = 0;
     Plan plan_i8, plan_i8_par;
     bool use_i8 = false;
+    bool i8_pair = false;              // 2-CTA clusters with multicast digit tiles (GMS_I8_PAIR=1 enables; measured: no gain,
+                                       // the kernel is not L2-bound - see DESIGN.md)
 
     // map-structured fast path
     int mode = GMS_MODE_AUTO;          // requested
@@ -345,6 +348,7 @@ int gms_create(gms_handle** out, int device) {
         return fail(h, GMS_ECUDA, std::string("cudaStreamCreate: ") + cudaGetErrorString(e));
     }
     nh->stream = nh->own_stream;
+    if (const char* ev = getenv("GMS_I8_PAIR")) nh->i8_pair = atoi(ev) != 0;
     for (auto& ev : nh->ev) cudaEventCreate(&ev);
     *out = nh;
     return GMS_OK;
@@ -598,7 +602,7 @@ int gms_stage_inputs(gms_handle* h, int model, int T, const double* add, const d
 
     // resolve the evaluation mode
     const int NU = BN / T, TT = T * T;
-    const long long npad = (N + 127) / 128 * 128, ppad = (h->nP + 127) / 128 * 128;
+    const long long npad = (N + 255) / 256 * 256, ppad = (h->nP + 255) / 256 * 256;   // even numbers of 128-unit tiles (CTA pairs)
     // int8 path: mask images (npad + 2 ppad) x mp bytes and up to 3 digit-plane sets must fit comfortably
     double dig_bytes = 0;
     for (int c = h->c_begin; c < h->c_end; ++c) {
@@ -791,7 +795,7 @@ int gms_compute(gms_handle* h, int sync) {
             ip.unit_a = ua; ip.unit_b = ub; ip.n_units = n_units; ip.T = h->T; ip.mode = mode;
             ip.Zpart = h->Z.p;
             if (e0) CU(cudaEventRecord(e0, h->stream));
-            CU(launch_i8_contract(ip, pl.ntiles, pl.nsplit, h->stream));
+            CU(launch_i8_contract(ip, pl.ntiles, pl.nsplit, h->i8_pair, h->stream));
             if (e1) CU(cudaEventRecord(e1, h->stream));
             CU(launch_finalize_sym(h->Z.p, 2 * pl.nsplit, n_units, h->T, Xout, h->stream, true));
             h->st.last_launches += 2;

@@ -39,7 +39,7 @@ __global__ void i8_build_xi_kernel(const unsigned* __restrict__ planeA, const un
     // one thread = one (unit, 16-byte chunk): 16 consecutive k of one cross
     const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long chunks_per_unit = nkb_total * 4;
-    const long long npad = (n_units + I8_M - 1) / I8_M * I8_M;
+    const long long npad = (n_units + 2 * I8_M - 1) / (2 * I8_M) * (2 * I8_M);     // an even number of 128-cross tiles (CTA pairs)
     if (gid >= npad * chunks_per_unit) return;
     // consecutive threads -> consecutive rows (so that the 16-byte stores of a warp are contiguous)
     const long long tile_chunk = gid / I8_M;            // (X, kbglobal, cc)
@@ -230,17 +230,39 @@ __device__ __forceinline__ void i8_mma(unsigned tmem_d, unsigned long long da, u
         ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate), "r"(0u)
         : "memory");
 }
+// the same copy delivered to the same shared-memory offset (and mbarrier) of every CTA in `mask` of the cluster
+__device__ __forceinline__ void i8_bulk_g2s_mc(unsigned dst, const void* src, unsigned bytes, unsigned bar, unsigned short mask) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar), "h"(mask) : "memory");
+}
+__device__ __forceinline__ void i8_commit_mc(unsigned bar, unsigned short mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(bar), "h"(mask) : "memory");
+}
+__device__ __forceinline__ void i8_cluster_sync() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ unsigned i8_cta_rank() {
+    unsigned r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
 __device__ __forceinline__ void i8_commit(unsigned bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
-__device__ __forceinline__ void i8_tmem_ld4(unsigned taddr, int (&v)[4]) {
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];"
-                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]) : "r"(taddr) : "memory");
+constexpr int I8_EC = 8;             // accumulator columns per tcgen05.ld (x8) in the epilogue
+__device__ __forceinline__ void i8_tmem_ldc(unsigned taddr, int (&v)[I8_EC]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                 : "r"(taddr) : "memory");
 }
 
 // TT = T (SOUTER = false, T <= 6: loop "64-row tile outer, trait s inner", the cross's whole T x T table in registers)
 // or TT >= T (SOUTER = true, any T <= 32: loop "trait s outer, tile inner", one column Z[:, s] in registers).
-template <int TT, bool SOUTER>
+// PAIR = true: launched as clusters of 2 CTAs (two adjacent cross tiles, same tile range). Each CTA fetches its own xi tile
+// and HALF of every digit tile, multicast to both CTAs, so the dominant L2 -> SM operand stream is halved; a smem slot is
+// released only when the MMAs of BOTH CTAs have retired (multicast tcgen05.commit on both `empty` barriers).
+template <int TT, bool SOUTER, bool PAIR>
 __global__ void __launch_bounds__(I8_THREADS, 1) i8_contract_kernel(const I8Params p) {
     const int T = SOUTER ? p.T : TT;
     extern __shared__ __align__(1024) unsigned char smem[];
@@ -260,7 +282,7 @@ __global__ void __launch_bounds__(I8_THREADS, 1) i8_contract_kernel(const I8Para
     auto unit_s = [&](int u) { return SOUTER ? u / njt : u % T; };
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < I8_STAGES; ++s) { i8_mbar_init(full0 + 8 * s, 1); i8_mbar_init(empty0 + 8 * s, 1); }
+        for (int s = 0; s < I8_STAGES; ++s) { i8_mbar_init(full0 + 8 * s, 1); i8_mbar_init(empty0 + 8 * s, PAIR ? 2 : 1); }
         i8_mbar_init(accfull, 1);
         i8_mbar_init(accempty, I8_EPI_WARPS);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -271,8 +293,10 @@ __global__ void __launch_bounds__(I8_THREADS, 1) i8_contract_kernel(const I8Para
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
+    if (PAIR) i8_cluster_sync();          // the peer's barriers must exist before anything is multicast to them
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const unsigned tmem_base = *tmem_slot;
+    const unsigned crank = PAIR ? i8_cta_rank() : 0u;
 
     if (warp == I8_EPI_WARPS) {
         // ------------------------------------------------------------------ producer (one lane)
@@ -292,8 +316,13 @@ __global__ void __launch_bounds__(I8_THREADS, 1) i8_contract_kernel(const I8Para
                     const unsigned dst = i8_smem_u32(stage0 + slot * I8_STAGE_BYTES);
                     i8_mbar_expect_tx(full0 + 8 * slot, I8_STAGE_BYTES);
                     i8_bulk_g2s(dst, abase + (long long)kb * I8_A_BYTES, I8_A_BYTES, full0 + 8 * slot);
-                    i8_bulk_g2s(dst + I8_A_BYTES, gb + ((long long)kb * T + s) * (I8_DIG * (long long)I8_B_BYTES),
-                                I8_DIG * I8_B_BYTES, full0 + 8 * slot);
+                    const signed char* gsrc = gb + ((long long)kb * T + s) * (I8_DIG * (long long)I8_B_BYTES);
+                    if (PAIR) {
+                        constexpr unsigned HALF = I8_DIG * I8_B_BYTES / 2;
+                        i8_bulk_g2s_mc(dst + I8_A_BYTES + crank * HALF, gsrc + crank * HALF, HALF, full0 + 8 * slot, 3);
+                    } else {
+                        i8_bulk_g2s(dst + I8_A_BYTES, gsrc, I8_DIG * I8_B_BYTES, full0 + 8 * slot);
+                    }
                 }
             }
         }
@@ -326,7 +355,8 @@ __global__ void __launch_bounds__(I8_THREADS, 1) i8_contract_kernel(const I8Para
                         i8_mma(tmem_base, da, db0, idescA, (kb | kk) != 0);
                         i8_mma(tmem_base + 4 * I8_N, da, db1, idescB, (kb | kk) != 0);
                     }
-                    i8_commit(empty0 + 8 * slot);                         // frees the smem slot when these MMAs retire
+                    if (PAIR) i8_commit_mc(empty0 + 8 * slot, 3);         // frees the slot in BOTH CTAs when these MMAs retire
+                    else i8_commit(empty0 + 8 * slot);                    // frees the smem slot when these MMAs retire
                 }
                 i8_commit(accfull);                                        // accumulators of this (tile, trait) are complete
             }
@@ -378,19 +408,19 @@ __global__ void __launch_bounds__(I8_THREADS, 1) i8_contract_kernel(const I8Para
                     i8_mbar_wait(accfull, acc_it & 1u);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     #pragma unroll 1
-                    for (int cb = 0; cb < 8; ++cb) {                                 // 4 SNP rows at a time
-                        int dig[I8_DIG][4];
+                    for (int cb = 0; cb < 32 / I8_EC; ++cb) {                        // I8_EC SNP rows at a time
+                        int dig[I8_DIG][I8_EC];
     #pragma unroll
-                        for (int i = 0; i < I8_DIG; ++i) i8_tmem_ld4(tlane + i * I8_N + cb * 4, dig[i]);
+                        for (int i = 0; i < I8_DIG; ++i) i8_tmem_ldc(tlane + i * I8_N + cb * I8_EC, dig[i]);
                         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                        if (cb == 7) {                                               // TMEM fully read: next trait's MMAs may start
+                        if (cb == 32 / I8_EC - 1) {                                               // TMEM fully read: next trait's MMAs may start
                             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                             __syncwarp();
                             if (lane == 0) i8_mbar_arrive(accempty);
                         }
-                        const unsigned nzw = nz >> (4 * cb), ngw = ng >> (4 * cb);
+                        const unsigned nzw = nz >> (I8_EC * cb), ngw = ng >> (I8_EC * cb);
     #pragma unroll
-                        for (int c = 0; c < 4; ++c) {
+                        for (int c = 0; c < I8_EC; ++c) {
                             // sum_i S_i 128^-(i+1): pairs of digits combined exactly in int32, then 4 exact int->fp64 terms
                             const int w0 = dig[0][c] * 128 + dig[1][c], w1 = dig[2][c] * 128 + dig[3][c];
                             const int w2 = dig[4][c] * 128 + dig[5][c], w3 = dig[6][c];
@@ -398,13 +428,13 @@ __global__ void __launch_bounds__(I8_THREADS, 1) i8_contract_kernel(const I8Para
                             v = fma((double)w2, 0x1p-42, v);
                             v = fma((double)w1, 0x1p-28, v);
                             v = fma((double)w0, 0x1p-14, v);
-                            v *= srow[s * 64 + cb * 4 + c];                // exact power-of-two row scale
+                            v *= srow[s * 64 + cb * I8_EC + c];                // exact power-of-two row scale
                             long long bits = __double_as_longlong(v);
                             if (!((nzw >> c) & 1u)) bits = 0ll;
                             bits ^= (long long)((ngw >> c) & 1u) << 63;
                             v = __longlong_as_double(bits);
     #pragma unroll
-                            for (int t = 0; t < TT; ++t) Z[t][s] = fma(erow[t * 64 + cb * 4 + c], v, Z[t][s]);
+                            for (int t = 0; t < TT; ++t) Z[t][s] = fma(erow[t * 64 + cb * I8_EC + c], v, Z[t][s]);
                         }
                     }
                 }
@@ -453,33 +483,33 @@ __global__ void __launch_bounds__(I8_THREADS, 1) i8_contract_kernel(const I8Para
                     i8_mbar_wait(accfull, acc_it & 1u);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll 1
-                    for (int cb = 0; cb < 8; ++cb) {
-                        int dig[I8_DIG][4];
+                    for (int cb = 0; cb < 32 / I8_EC; ++cb) {
+                        int dig[I8_DIG][I8_EC];
 #pragma unroll
-                        for (int i = 0; i < I8_DIG; ++i) i8_tmem_ld4(tlane + i * I8_N + cb * 4, dig[i]);
+                        for (int i = 0; i < I8_DIG; ++i) i8_tmem_ldc(tlane + i * I8_N + cb * I8_EC, dig[i]);
                         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                        if (cb == 7) {
+                        if (cb == 32 / I8_EC - 1) {
                             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                             __syncwarp();
                             if (lane == 0) i8_mbar_arrive(accempty);
                         }
-                        const unsigned nzw = nz >> (4 * cb), ngw = ng >> (4 * cb);
+                        const unsigned nzw = nz >> (I8_EC * cb), ngw = ng >> (I8_EC * cb);
 #pragma unroll
-                        for (int c = 0; c < 4; ++c) {
+                        for (int c = 0; c < I8_EC; ++c) {
                             const int w0 = dig[0][c] * 128 + dig[1][c], w1 = dig[2][c] * 128 + dig[3][c];
                             const int w2 = dig[4][c] * 128 + dig[5][c], w3 = dig[6][c];
                             double v = (double)w3 * 0x1p-49;
                             v = fma((double)w2, 0x1p-42, v);
                             v = fma((double)w1, 0x1p-28, v);
                             v = fma((double)w0, 0x1p-14, v);
-                            v *= srow[cb * 4 + c];
+                            v *= srow[cb * I8_EC + c];
                             long long bits = __double_as_longlong(v);
                             if (!((nzw >> c) & 1u)) bits = 0ll;
                             bits ^= (long long)((ngw >> c) & 1u) << 63;
                             v = __longlong_as_double(bits);
 #pragma unroll
                             for (int t = 0; t < TT; ++t)
-                                if (t < T) zs[t] = fma(erow[t * 64 + cb * 4 + c], v, zs[t]);
+                                if (t < T) zs[t] = fma(erow[t * 64 + cb * I8_EC + c], v, zs[t]);
                         }
                     }
                 }
@@ -494,6 +524,7 @@ __global__ void __launch_bounds__(I8_THREADS, 1) i8_contract_kernel(const I8Para
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
+    if (PAIR) i8_cluster_sync();          // do not exit while the peer can still write into this CTA's shared memory
     if (warp == I8_EPI_WARPS) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
@@ -508,7 +539,7 @@ size_t i8_smem_bytes(int T) {
 cudaError_t launch_i8_build_xi(const unsigned* planeA, const unsigned* planeB, long long wpp, const int* sire,
                                const int* dam, long long n_units, int mode, long long nkb_total, signed char* xi,
                                cudaStream_t st) {
-    const long long npad = (n_units + I8_M - 1) / I8_M * I8_M;
+    const long long npad = (n_units + 2 * I8_M - 1) / (2 * I8_M) * (2 * I8_M);
     const long long total = npad * nkb_total * 4;
     if (total == 0) return cudaSuccess;
     i8_build_xi_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(planeA, planeB, wpp, sire, dam, n_units, mode,
@@ -526,17 +557,28 @@ cudaError_t launch_i8_build_digits(const double* tiles, const ChromDesc* chrom_d
     return cudaGetLastError();
 }
 
-cudaError_t launch_i8_contract(const I8Params& p, int ntiles, int nsplit, cudaStream_t st) {
+cudaError_t launch_i8_contract(const I8Params& p, int ntiles, int nsplit, bool pair, cudaStream_t st) {
     if (ntiles == 0) return cudaSuccess;
     const size_t smem = i8_smem_bytes(p.T);
-    dim3 grid(ntiles, nsplit);
     cudaError_t e = cudaSuccess;
-#define GMS_I8(TV, SO)                                                                                                  \
-    {                                                                                                                   \
-        e = cudaFuncSetAttribute(i8_contract_kernel<TV, SO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);   \
-        if (e != cudaSuccess) return e;                                                                                 \
-        i8_contract_kernel<TV, SO><<<grid, I8_THREADS, smem, st>>>(p);                                                  \
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(pair ? (ntiles + 1) / 2 * 2 : ntiles, nsplit, 1);
+    cfg.blockDim = dim3(I8_THREADS, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pair ? 1 : 0;
+#define GMS_I8_ONE(TV, SO, PR)                                                                                             \
+    {                                                                                                                      \
+        e = cudaFuncSetAttribute(i8_contract_kernel<TV, SO, PR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);  \
+        if (e != cudaSuccess) return e;                                                                                    \
+        e = cudaLaunchKernelEx(&cfg, i8_contract_kernel<TV, SO, PR>, p);                                                   \
+        if (e != cudaSuccess) return e;                                                                                    \
     }
+#define GMS_I8(TV, SO) { if (pair) GMS_I8_ONE(TV, SO, true) else GMS_I8_ONE(TV, SO, false) }
     switch (p.T) {
         case 1: GMS_I8(1, false) break;
         case 2: GMS_I8(2, false) break;
@@ -553,6 +595,7 @@ cudaError_t launch_i8_contract(const I8Params& p, int ntiles, int nsplit, cudaSt
             else return cudaErrorInvalidValue;
     }
 #undef GMS_I8
+#undef GMS_I8_ONE
     return cudaGetLastError();
 }
 

@@ -74,7 +74,7 @@ cudaError_t launch_i8_build_digits(const double* tiles, const ChromDesc* chrom_d
                                    const int* rowpref_d, int nrows, const int* blkpref_d, int nblks, const double* emat,
                                    long long mp_total, int T, double* scale, const long long* gbase_d, signed char* G,
                                    cudaStream_t st);
-cudaError_t launch_i8_contract(const I8Params& p, int ntiles, int nsplit, cudaStream_t st);
+cudaError_t launch_i8_contract(const I8Params& p, int ntiles, int nsplit, bool pair, cudaStream_t st);
 
 // Nsegsnps per cross over words [w_begin, w_end) of the padded axis.
 cudaError_t launch_nseg(const unsigned* planeA, const unsigned* planeB, long long wpp, long long w_begin,

@@ -103,3 +103,20 @@ def test_one_engine_many_calls():
     with pytest.raises(g.GmsError, match="out of range"):
         eng.predict("A", add[:, :1], None, None, [9], [0])                      # parent 9 no longer exists
     eng.close()
+
+
+def test_int8_cta_pair_multicast_variant(monkeypatch):
+    """GMS_I8_PAIR=1: 2-CTA clusters, digit tiles fetched half by each CTA and multicast (kept as an option)."""
+    import genomicmateselectr_b200 as g
+    monkeypatch.setenv("GMS_I8_PAIR", "1")
+    m_c, cM, chrom, H, add, dom, asub, R = make(9, [200, 131, 77], 10, 5)
+    rng = np.random.default_rng(2)
+    sire = rng.integers(0, 10, 300).astype(np.int32)
+    dam = rng.integers(0, 10, 300).astype(np.int32)
+    with g.CrossVarEngine(0) as eng:
+        eng.set_genmap(cM, m_c)
+        eng.set_haplotypes(H)
+        eng.set_mode("int8_tensor")
+        out, nseg = eng.predict("AD", add, dom, None, sire, dam)
+    want, wseg = oracle_slab("AD", H, R, add, dom, None, sire, dam)
+    assert np.array_equal(nseg, wseg) and rel_err(out, want) < 1e-9
