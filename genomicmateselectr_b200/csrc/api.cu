@@ -89,7 +89,9 @@ struct gms_handle {
     DevBuf<double> scale_d, scale_add_d, scale_asub_d;
     DevBuf<int> split_i8_d, split_i8_par_d, i8_rowpref_d, i8_blkpref_d;
     int i8_nrows = 0, i8_nblks = 0;
-    Plan plan_i8, plan_i8_par;
+    Plan plan_i8, plan_i8_par, plan_i8_tail;
+    DevBuf<int> split_i8_tail_d;
+    long long i8_chunk = 0;            // crosses per pass of the per-cross int8 kernel (bounds the xi image)
     bool use_i8 = false;
     bool i8_pair = false;              // 2-CTA clusters with multicast digit tiles (GMS_I8_PAIR=1 enables; measured: no gain,
                                        // the kernel is not L2-bound - see DESIGN.md)
@@ -368,7 +370,7 @@ void gms_destroy(gms_handle* h) {
     h->S_asub.release(); h->split_scan_par_d.release(); h->split_scan_x_d.release();
     h->jtiles_d.release(); h->gbase_d.release(); h->xi_d.release(); h->G_d.release(); h->scale_d.release(); h->split_i8_d.release();
     h->xi_het_d.release(); h->xi_delta_d.release(); h->G_add_d.release(); h->G_asub_d.release(); h->scale_add_d.release();
-    h->scale_asub_d.release(); h->split_i8_par_d.release(); h->i8_rowpref_d.release(); h->i8_blkpref_d.release();
+    h->scale_asub_d.release(); h->split_i8_par_d.release(); h->split_i8_tail_d.release(); h->i8_rowpref_d.release(); h->i8_blkpref_d.release();
     for (auto& ev : h->ev) if (ev) cudaEventDestroy(ev);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     delete h;
@@ -609,7 +611,12 @@ int gms_stage_inputs(gms_handle* h, int model, int T, const double* add, const d
         const double nJ = (h->chrom[c].m + 63) / 64;
         dig_bytes += nJ * (nJ + 1) / 2 * T * 7 * 4096.0;
     }
-    const bool i8_ok = N > 0 && (double)(npad + 2 * ppad) * (double)h->mp_total < 24e9 && dig_bytes * (model + 1) < 60e9;
+    const bool i8_ok = N > 0 && (double)(2 * ppad) * (double)h->mp_total < 16e9 && dig_bytes * (model + 1) < 60e9;
+    // the per-cross pass is chunked so that the xi image stays below ~12 GB
+    long long chunk = (long long)(12e9 / (double)h->mp_total) / 256 * 256;
+    if (const char* ev = getenv("GMS_I8_CHUNK")) chunk = (atoll(ev) + 255) / 256 * 256;      // test hook
+    chunk = std::max<long long>(256, std::min<long long>(chunk, npad));
+    h->i8_chunk = chunk;
     h->eff_mode = h->mode;
     if (h->mode == GMS_MODE_AUTO) h->eff_mode = i8_ok ? GMS_MODE_INT8_TENSOR : GMS_MODE_DENSE;
     if (h->eff_mode == GMS_MODE_INT8_TENSOR && !i8_ok) h->eff_mode = GMS_MODE_DENSE;
@@ -668,7 +675,7 @@ int gms_stage_inputs(gms_handle* h, int model, int T, const double* add, const d
         if (model == GMS_MODEL_DIRDOM) { CU(h->G_asub_d.ensure((size_t)gb)); CU(h->scale_asub_d.ensure((size_t)h->mp_total * T)); }
         // mask images: parents (delta, het), crosses (xi)
         CU(h->xi_delta_d.ensure((size_t)ppad * h->mp_total));
-        if (model >= GMS_MODEL_AD) { CU(h->xi_het_d.ensure((size_t)ppad * h->mp_total)); CU(h->xi_d.ensure((size_t)npad * h->mp_total)); }
+        if (model >= GMS_MODEL_AD) { CU(h->xi_het_d.ensure((size_t)ppad * h->mp_total)); CU(h->xi_d.ensure((size_t)chunk * h->mp_total)); }
         // plans: contiguous ranges of jtiles of equal work (weight J + 1)
         auto i8plan = [&](long long units, Plan& pl, DevBuf<int>& dev) -> int {
             pl.ntiles = (int)((units + 127) / 128);
@@ -700,9 +707,13 @@ int gms_stage_inputs(gms_handle* h, int model, int T, const double* add, const d
             CU(cudaMemcpyAsync(dev.p, pl.split_begin.data(), sizeof(int) * pl.split_begin.size(), cudaMemcpyHostToDevice, h->stream));
             return GMS_OK;
         };
-        if (int rc = i8plan(model >= GMS_MODEL_AD ? N : 0, h->plan_i8, h->split_i8_d)) return rc;
+        const long long n_full = model >= GMS_MODEL_AD ? std::min<long long>(N, chunk) : 0;
+        const long long n_tail = model >= GMS_MODEL_AD && N > chunk ? N % chunk : 0;
+        if (int rc = i8plan(n_full, h->plan_i8, h->split_i8_d)) return rc;
+        if (int rc = i8plan(n_tail, h->plan_i8_tail, h->split_i8_tail_d)) return rc;
         if (int rc = i8plan(h->nP, h->plan_i8_par, h->split_i8_par_d)) return rc;
-        zneed = std::max<size_t>((size_t)2 * h->plan_i8.nsplit * (size_t)N * TT, (size_t)2 * h->plan_i8_par.nsplit * (size_t)h->nP * TT);
+        zneed = std::max<size_t>(std::max<size_t>((size_t)2 * h->plan_i8.nsplit * (size_t)n_full * TT, (size_t)2 * h->plan_i8_tail.nsplit * (size_t)n_tail * TT),
+                                 (size_t)2 * h->plan_i8_par.nsplit * (size_t)h->nP * TT);
     } else {
         make_plan(h, h->nP, NU, h->plan_par);
         make_plan(h, model >= GMS_MODEL_AD ? N : 0, NU, h->plan_x);
@@ -763,9 +774,8 @@ int gms_compute(gms_handle* h, int sync) {
         CU(launch_i8_build_xi(h->planeA.p, h->planeB.p, h->wpp, h->plist_d.p, nullptr, h->nP, MASK_DELTA, h->mp_total / 64, h->xi_delta_d.p, h->stream));
         if (h->model >= GMS_MODEL_AD) {
             CU(launch_i8_build_xi(h->planeA.p, h->planeB.p, h->wpp, h->plist_d.p, nullptr, h->nP, MASK_HET, h->mp_total / 64, h->xi_het_d.p, h->stream));
-            CU(launch_i8_build_xi(h->planeA.p, h->planeB.p, h->wpp, h->sire_d.p, h->dam_d.p, h->N, MASK_XI, h->mp_total / 64, h->xi_d.p, h->stream));
         }
-        h->st.last_launches += 1 + 2 * (h->model >= GMS_MODEL_AD);
+        h->st.last_launches += 1 + (h->model >= GMS_MODEL_AD);
     }
     if (h->eff_mode == GMS_MODE_MAP_SCAN) {
         // same tables through the prefix-sum recurrence (scan.cu)
@@ -810,9 +820,23 @@ int gms_compute(gms_handle* h, int sync) {
             if (int rc = run_i8(h->G_asub_d.p, h->scale_asub_d.p, h->xi_delta_d.p, h->emat_asub.p, MASK_DELTA, h->plist_d.p, nullptr,
                                 h->nP, h->plan_i8_par, h->split_i8_par_d.p, h->QB.p, nullptr, nullptr)) return rc;
         CU(cudaEventRecord(h->ev[1], h->stream));
-        if (h->model >= GMS_MODEL_AD)
-            if (int rc = run_i8(h->G_d.p, h->scale_d.p, h->xi_d.p, h->emat_dom.p, MASK_XI, h->sire_d.p, h->dam_d.p,
-                                h->N, h->plan_i8, h->split_i8_d.p, h->X.p, h->ev[4], h->ev[5])) return rc;
+        if (h->model >= GMS_MODEL_AD) {
+            // per-cross term, in passes of at most i8_chunk crosses (the xi mask image of a pass is chunk x mp bytes)
+            const bool one_pass = h->N <= h->i8_chunk;          // then the events bracket the kernel alone
+            if (!one_pass) CU(cudaEventRecord(h->ev[4], h->stream));
+            for (long long off = 0; off < h->N; off += h->i8_chunk) {
+                const long long n = std::min<long long>(h->i8_chunk, h->N - off);
+                const bool tail = n < h->i8_chunk && h->N > h->i8_chunk;
+                CU(launch_i8_build_xi(h->planeA.p, h->planeB.p, h->wpp, h->sire_d.p + off, h->dam_d.p + off, n, MASK_XI,
+                                      h->mp_total / 64, h->xi_d.p, h->stream));
+                h->st.last_launches += 1;
+                if (int rc = run_i8(h->G_d.p, h->scale_d.p, h->xi_d.p, h->emat_dom.p, MASK_XI, h->sire_d.p + off, h->dam_d.p + off, n,
+                                    tail ? h->plan_i8_tail : h->plan_i8, tail ? h->split_i8_tail_d.p : h->split_i8_d.p,
+                                    h->X.p + off * (long long)(h->T * h->T), one_pass ? h->ev[4] : nullptr,
+                                    one_pass ? h->ev[5] : nullptr)) return rc;
+            }
+            if (!one_pass) CU(cudaEventRecord(h->ev[5], h->stream));
+        }
     } else {
         // per-parent tables: Q_P = (a o delta_P)' R (a o delta_P), P_P = (d o het_P)' RoR (d o het_P)
         if (int rc = run_contract(h, h->R.p, h->emat_add.p, MASK_DELTA, h->plist_d.p, nullptr, h->nP, h->plan_par,

@@ -120,3 +120,23 @@ def test_int8_cta_pair_multicast_variant(monkeypatch):
         out, nseg = eng.predict("AD", add, dom, None, sire, dam)
     want, wseg = oracle_slab("AD", H, R, add, dom, None, sire, dam)
     assert np.array_equal(nseg, wseg) and rel_err(out, want) < 1e-9
+
+
+def test_int8_cross_chunking(monkeypatch):
+    """The per-cross int8 pass runs in chunks of crosses when the xi mask image would be too large
+    (GMS_I8_CHUNK is a test hook that forces small chunks): full chunks + a ragged tail == one pass."""
+    import genomicmateselectr_b200 as g
+    m_c, cM, chrom, H, add, dom, asub, R = make(12, [150, 100], 9, 3)
+    rng = np.random.default_rng(3)
+    sire = rng.integers(0, 9, 700).astype(np.int32)
+    dam = rng.integers(0, 9, 700).astype(np.int32)
+    want, wseg = oracle_slab("AD", H, R, add, dom, None, sire, dam)
+    for chunk in ("256", "512", "100000"):
+        monkeypatch.setenv("GMS_I8_CHUNK", chunk)
+        with g.CrossVarEngine(0) as eng:
+            eng.set_genmap(cM, m_c)
+            eng.set_haplotypes(H)
+            eng.set_mode("int8_tensor")
+            out, nseg = eng.predict("AD", add, dom, None, sire, dam)
+            assert eng.stats()["last_mode"] == 2
+        assert np.array_equal(nseg, wseg) and rel_err(out, want) < 1e-9, chunk
