@@ -93,8 +93,7 @@ struct gms_handle {
     DevBuf<int> split_i8_tail_d;
     long long i8_chunk = 0;            // crosses per pass of the per-cross int8 kernel (bounds the xi image)
     bool use_i8 = false;
-    bool i8_pair = false;              // 2-CTA clusters with multicast digit tiles (GMS_I8_PAIR=1 enables; measured: no gain,
-                                       // the kernel is not L2-bound - see DESIGN.md)
+    bool i8_pair = false;              // tcgen05 cta_group::2: CTA pairs form one M = 256 tile (GMS_I8_CG2=1 enables)
 
     // map-structured fast path
     int mode = GMS_MODE_AUTO;          // requested
@@ -350,7 +349,7 @@ int gms_create(gms_handle** out, int device) {
         return fail(h, GMS_ECUDA, std::string("cudaStreamCreate: ") + cudaGetErrorString(e));
     }
     nh->stream = nh->own_stream;
-    if (const char* ev = getenv("GMS_I8_PAIR")) nh->i8_pair = atoi(ev) != 0;
+    if (const char* ev = getenv("GMS_I8_CG2")) nh->i8_pair = atoi(ev) != 0;
     for (auto& ev : nh->ev) cudaEventCreate(&ev);
     *out = nh;
     return GMS_OK;
@@ -764,7 +763,7 @@ int gms_compute(gms_handle* h, int sync) {
         auto digits = [&](const double* tiles, const double* emat, DevBuf<signed char>& G, DevBuf<double>& sc) -> int {
             CU(cudaMemsetAsync(sc.p, 0, sizeof(double) * h->mp_total * T, h->stream));
             CU(launch_i8_build_digits(tiles, h->chrom_d.p, h->c_begin, h->c_end, h->i8_rowpref_d.p, h->i8_nrows, h->i8_blkpref_d.p,
-                                      h->i8_nblks, emat, h->mp_total, T, sc.p, h->gbase_d.p, G.p, h->stream));
+                                      h->i8_nblks, emat, h->mp_total, T, sc.p, h->gbase_d.p, G.p, h->i8_pair, h->stream));
             h->st.last_launches += 2;
             return GMS_OK;
         };

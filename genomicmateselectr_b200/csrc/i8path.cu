@@ -26,8 +26,14 @@ constexpr int I8_KB = 64;        // k per pipeline stage (bytes of int8)
 constexpr int I8_DIG = 7;        // radix-128 digits
 constexpr int I8_A_BYTES = I8_M * I8_KB;            // 8 KiB
 constexpr int I8_B_BYTES = I8_N * I8_KB;            // 4 KiB per digit
-constexpr int I8_STAGE_BYTES = I8_A_BYTES + I8_DIG * I8_B_BYTES;   // 36 KiB
-constexpr int I8_STAGES = 5;
+constexpr int I8_B_ALL = I8_DIG * I8_B_BYTES;       // 28 KiB: the 448-row digit operand of one k-block
+// per-variant stage geometry: single-CTA UMMA keeps the whole digit operand, a cta_group::2 pair keeps half per CTA
+template <bool CG2> struct I8Geo {
+    static constexpr int B_STAGE = CG2 ? I8_B_ALL / 2 : I8_B_ALL;
+    static constexpr int STAGE_BYTES = I8_A_BYTES + B_STAGE;           // 36 KiB / 22 KiB
+    static constexpr int STAGES = CG2 ? 8 : 5;                         // 180 KiB / 176 KiB
+};
+constexpr int I8_MAX_STAGES = 8;
 constexpr int I8_EPI_WARPS = 8;     // two per TMEM lane quarter: each takes 32 of the 64 accumulator columns
 constexpr int I8_THREADS = 32 * (I8_EPI_WARPS + 2);
 
@@ -142,7 +148,7 @@ __global__ void i8_rowscale_kernel(const double* __restrict__ tiles, const Chrom
 __global__ void i8_build_digits_kernel(const double* __restrict__ tiles, const ChromDesc* __restrict__ chrom, int c_begin,
                                        int c_end, const int* __restrict__ blkpref, const double* __restrict__ emat,
                                        long long mp_total, int T, const double* __restrict__ scale,
-                                       const long long* __restrict__ gbase_c, signed char* __restrict__ G) {
+                                       const long long* __restrict__ gbase_c, signed char* __restrict__ G, int cg2) {
     int c = c_begin;
     while (c + 1 < c_end && (int)blockIdx.x >= blkpref[c + 1]) ++c;     // blkpref[c] = first block of chromosome c
     const ChromDesc cd = chrom[c];
@@ -181,9 +187,19 @@ __global__ void i8_build_digits_kernel(const double* __restrict__ tiles, const C
         }
 #pragma unroll
         for (int i = 0; i < I8_DIG; ++i) {
-            signed char* dst = G + gbase + (((long long)blk * T + s) * (I8_DIG * (long long)I8_B_BYTES)) +
-                               ((cc * (I8_DIG * 8) + (i * 8 + r1)) * 8 + r0) * 16;
-            *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(d[i]);
+            signed char* img = G + gbase + (((long long)blk * T + s) * (long long)I8_B_ALL);
+            int off;
+            if (!cg2) {
+                off = ((cc * (I8_DIG * 8) + (i * 8 + r1)) * 8 + r0) * 16;             // one 448-row operand
+            } else {
+                // cta_group::2: the N = 256 MMA takes rows 0-127 from the leader and 128-255 from the peer, the N = 192
+                // MMA rows 0-95 / 96-191; each CTA's half is a 224-row operand [128 rows | 96 rows], halves back to back
+                const int g = i * 64 + r;                                           // row of the 448-row operand
+                const int h = g < 256 ? g / 128 : (g - 256) / 96;
+                const int lr = g < 256 ? g % 128 : 128 + (g - 256) % 96;
+                off = h * (I8_B_ALL / 2) + ((cc * 28 + (lr >> 3)) * 8 + (lr & 7)) * 16;
+            }
+            *reinterpret_cast<uint4*>(img + off) = *reinterpret_cast<const uint4*>(d[i]);
         }
     }
 }
@@ -230,13 +246,26 @@ __device__ __forceinline__ void i8_mma(unsigned tmem_d, unsigned long long da, u
         ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate), "r"(0u)
         : "memory");
 }
-// the same copy delivered to the same shared-memory offset (and mbarrier) of every CTA in `mask` of the cluster
-__device__ __forceinline__ void i8_bulk_g2s_mc(unsigned dst, const void* src, unsigned bytes, unsigned bar, unsigned short mask) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;"
-                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar), "h"(mask) : "memory");
+// arrive on the mbarrier at the same shared-memory offset in CTA `rank` of the cluster
+__device__ __forceinline__ void i8_mbar_arrive_remote(unsigned bar, unsigned rank) {
+    asm volatile("{\n.reg .b32 ra;\nmapa.shared::cluster.u32 ra, %0, %1;\nmbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n}\n"
+                 ::"r"(bar), "r"(rank) : "memory");
 }
-__device__ __forceinline__ void i8_commit_mc(unsigned bar, unsigned short mask) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+// one M = 256 MMA over a CTA pair: each CTA supplies its 128 A rows and HALF of the B rows from its own shared memory (same
+// offsets in both CTAs); rows 0-127 of D land in the leader's TMEM, rows 128-255 in the peer's. Issued by the leader only.
+__device__ __forceinline__ void i8_mma_cg2(unsigned tmem_d, unsigned long long da, unsigned long long db, unsigned idesc,
+                                           unsigned accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::2.kind::i8 [%0], %1, %2, %3, {%5, %5, %5, %5, %5, %5, %5, %5}, p;\n"
+        "}\n"
+        ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate), "r"(0u)
+        : "memory");
+}
+__device__ __forceinline__ void i8_commit_cg2(unsigned bar, unsigned short mask) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
                  ::"r"(bar), "h"(mask) : "memory");
 }
 __device__ __forceinline__ void i8_cluster_sync() {
@@ -259,19 +288,22 @@ __device__ __forceinline__ void i8_tmem_ldc(unsigned taddr, int (&v)[I8_EC]) {
 
 // TT = T (SOUTER = false, T <= 6: loop "64-row tile outer, trait s inner", the cross's whole T x T table in registers)
 // or TT >= T (SOUTER = true, any T <= 32: loop "trait s outer, tile inner", one column Z[:, s] in registers).
-// PAIR = true: launched as clusters of 2 CTAs (two adjacent cross tiles, same tile range). Each CTA fetches its own xi tile
-// and HALF of every digit tile, multicast to both CTAs, so the dominant L2 -> SM operand stream is halved; a smem slot is
-// released only when the MMAs of BOTH CTAs have retired (multicast tcgen05.commit on both `empty` barriers).
-template <int TT, bool SOUTER, bool PAIR>
+// CG2 = true: launched as clusters of 2 CTAs = two adjacent cross tiles forming ONE M = 256 tile (tcgen05 cta_group::2).
+// Each CTA stages its own xi tile and only HALF of every digit tile; the leader CTA's MMA thread issues the pair's MMAs once
+// both halves have landed (the peer relays its `full` phases to the leader), and its commits release the slot / publish the
+// accumulators in BOTH CTAs. This halves the shared-memory traffic per MAC, which is what bounds the single-CTA kernel.
+template <int TT, bool SOUTER, bool CG2>
 __global__ void __launch_bounds__(I8_THREADS, 1) i8_contract_kernel(const I8Params p) {
     const int T = SOUTER ? p.T : TT;
     extern __shared__ __align__(1024) unsigned char smem[];
     unsigned char* stage0 = smem;
+    constexpr int I8_STAGES = I8Geo<CG2>::STAGES, I8_STAGE_BYTES = I8Geo<CG2>::STAGE_BYTES, B_STAGE = I8Geo<CG2>::B_STAGE;
     unsigned long long* bars = reinterpret_cast<unsigned long long*>(smem + I8_STAGES * I8_STAGE_BYTES);
-    unsigned* tmem_slot = reinterpret_cast<unsigned*>(bars + 2 * I8_STAGES + 2);
-    double* rowbuf = reinterpret_cast<double*>(bars + 2 * I8_STAGES + 4);   // [2 buffers][2 T (or T + 1)][64]: d_t[j], scale_s[j]
-    const unsigned full0 = i8_smem_u32(bars), empty0 = i8_smem_u32(bars + I8_STAGES);
-    const unsigned accfull = i8_smem_u32(bars + 2 * I8_STAGES), accempty = i8_smem_u32(bars + 2 * I8_STAGES + 1);
+    unsigned* tmem_slot = reinterpret_cast<unsigned*>(bars + 2 * I8_MAX_STAGES + 2);
+    double* rowbuf = reinterpret_cast<double*>(bars + 2 * I8_MAX_STAGES + 4);   // [2 buffers][2 T (or T + 1)][64]: d_t[j], scale_s[j]
+    const unsigned full0 = i8_smem_u32(bars), empty0 = i8_smem_u32(bars + I8_MAX_STAGES);
+    const unsigned accfull = i8_smem_u32(bars + 2 * I8_MAX_STAGES), accempty = i8_smem_u32(bars + 2 * I8_MAX_STAGES + 1);
+    const unsigned crank = CG2 ? i8_cta_rank() : 0u;       // 0 = leader of the pair
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const long long X = blockIdx.x;
     const int split = blockIdx.y;
@@ -282,21 +314,26 @@ __global__ void __launch_bounds__(I8_THREADS, 1) i8_contract_kernel(const I8Para
     auto unit_s = [&](int u) { return SOUTER ? u / njt : u % T; };
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < I8_STAGES; ++s) { i8_mbar_init(full0 + 8 * s, 1); i8_mbar_init(empty0 + 8 * s, PAIR ? 2 : 1); }
+        // CG2 leader: a `full` phase needs its own data AND the peer's relay; accumulators are drained by both CTAs' epilogues
+        for (int s = 0; s < I8_STAGES; ++s) { i8_mbar_init(full0 + 8 * s, (CG2 && crank == 0) ? 2 : 1); i8_mbar_init(empty0 + 8 * s, 1); }
         i8_mbar_init(accfull, 1);
-        i8_mbar_init(accempty, I8_EPI_WARPS);
+        i8_mbar_init(accempty, CG2 ? 2 * I8_EPI_WARPS : I8_EPI_WARPS);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == I8_EPI_WARPS) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(i8_smem_u32(tmem_slot)), "r"(512) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        if (CG2) {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(i8_smem_u32(tmem_slot)), "r"(512) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(i8_smem_u32(tmem_slot)), "r"(512) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    if (PAIR) i8_cluster_sync();          // the peer's barriers must exist before anything is multicast to them
+    if (CG2) i8_cluster_sync();           // the peer's barriers and TMEM must exist before anything touches them
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const unsigned tmem_base = *tmem_slot;
-    const unsigned crank = PAIR ? i8_cta_rank() : 0u;
 
     if (warp == I8_EPI_WARPS) {
         // ------------------------------------------------------------------ producer (one lane)
@@ -309,37 +346,48 @@ __global__ void __launch_bounds__(I8_THREADS, 1) i8_contract_kernel(const I8Para
                 const int J = tile.I;
                 const int nkb = min(J + 1, (cd.m + I8_KB - 1) / I8_KB);
                 const signed char* abase = p.xi + (X * p.nkb_total + (cd.pad_off >> 6)) * (long long)I8_A_BYTES;
-                const signed char* gb = p.G + p.gbase[tile.c] + ((long long)(J * (J + 1) / 2) * T) * (I8_DIG * (long long)I8_B_BYTES);
+                const signed char* gb = p.G + p.gbase[tile.c] + ((long long)(J * (J + 1) / 2) * T) * (long long)I8_B_ALL;
                 for (int kb = 0; kb < nkb; ++kb, ++it) {
                     const unsigned slot = it % I8_STAGES, ph = (it / I8_STAGES) & 1u;
                     i8_mbar_wait(empty0 + 8 * slot, ph ^ 1u);
                     const unsigned dst = i8_smem_u32(stage0 + slot * I8_STAGE_BYTES);
                     i8_mbar_expect_tx(full0 + 8 * slot, I8_STAGE_BYTES);
                     i8_bulk_g2s(dst, abase + (long long)kb * I8_A_BYTES, I8_A_BYTES, full0 + 8 * slot);
-                    const signed char* gsrc = gb + ((long long)kb * T + s) * (I8_DIG * (long long)I8_B_BYTES);
-                    if (PAIR) {
-                        constexpr unsigned HALF = I8_DIG * I8_B_BYTES / 2;
-                        i8_bulk_g2s_mc(dst + I8_A_BYTES + crank * HALF, gsrc + crank * HALF, HALF, full0 + 8 * slot, 3);
-                    } else {
-                        i8_bulk_g2s(dst + I8_A_BYTES, gsrc, I8_DIG * I8_B_BYTES, full0 + 8 * slot);
-                    }
+                    const signed char* gsrc = gb + ((long long)kb * T + s) * (long long)I8_B_ALL;
+                    i8_bulk_g2s(dst + I8_A_BYTES, gsrc + crank * B_STAGE, B_STAGE, full0 + 8 * slot);    // CG2: this CTA's half
                 }
             }
         }
     } else if (warp == I8_EPI_WARPS + 1) {
-        // ------------------------------------------------------------------ MMA issuer (one lane)
-        if (lane == 0) {
-            // instruction descriptor: D = S32, A = B = signed 8 bit, K-major both, N = 64, M = 128
-            const unsigned idesc0 = (2u << 4) | (1u << 7) | (1u << 10) | ((unsigned)(I8_M >> 4) << 24);
-            const unsigned idescA = idesc0 | ((unsigned)((4 * I8_N) >> 3) << 17);      // N = 256: digits 0-3
-            const unsigned idescB = idesc0 | ((unsigned)((3 * I8_N) >> 3) << 17);      // N = 192: digits 4-6
-            constexpr unsigned B_LBO = I8_DIG * 8 * 128;                              // chunk stride of the 448-row operand
+        // ------------------------------------------------------------------ MMA issuer (one lane; CG2: leader only)
+        if (lane == 0 && CG2 && crank != 0) {
+            // peer of a pair: relay every completed `full` phase (own xi tile + own half of the digits) to the leader
             unsigned it = 0;
             for (int u = 0; u < nunits; ++u) {
                 const RowTile tile = p.jtiles[unit_jt(u)];
                 const ChromDesc cd = p.chrom[tile.c];
                 const int nkb = min(tile.I + 1, (cd.m + I8_KB - 1) / I8_KB);
-                i8_mbar_wait(accempty, ((unsigned)u & 1u) ^ 1u);           // epilogue has drained the accumulators
+                for (int kb = 0; kb < nkb; ++kb, ++it) {
+                    const unsigned slot = it % I8_STAGES, ph = (it / I8_STAGES) & 1u;
+                    i8_mbar_wait(full0 + 8 * slot, ph);
+                    i8_mbar_arrive_remote(full0 + 8 * slot, 0);
+                }
+            }
+        } else if (lane == 0) {
+            // instruction descriptor: D = S32, A = B = signed 8 bit, K-major both; M = 128 (256 over a CTA pair)
+            const unsigned idesc0 = (2u << 4) | (1u << 7) | (1u << 10) | ((unsigned)((CG2 ? 2 * I8_M : I8_M) >> 4) << 24);
+            const unsigned idescA = idesc0 | ((unsigned)((4 * I8_N) >> 3) << 17);      // N = 256: digits 0-3
+            const unsigned idescB = idesc0 | ((unsigned)((3 * I8_N) >> 3) << 17);      // N = 192: digits 4-6
+            // rows of the digit operand held in THIS CTA's shared memory: all 448, or 128 + 96 (the pair's halves)
+            constexpr unsigned B_ROWS = CG2 ? (I8_DIG * I8_N) / 2 : I8_DIG * I8_N;
+            constexpr unsigned B_LBO = (B_ROWS / 8) * 128;                           // chunk stride
+            constexpr unsigned B_SECOND = (CG2 ? (4 * I8_N) / 2 : 4 * I8_N) / 8 * 128;   // byte offset of the N = 192 part
+            unsigned it = 0;
+            for (int u = 0; u < nunits; ++u) {
+                const RowTile tile = p.jtiles[unit_jt(u)];
+                const ChromDesc cd = p.chrom[tile.c];
+                const int nkb = min(tile.I + 1, (cd.m + I8_KB - 1) / I8_KB);
+                i8_mbar_wait(accempty, ((unsigned)u & 1u) ^ 1u);           // the epilogue(s) have drained the accumulators
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 for (int kb = 0; kb < nkb; ++kb, ++it) {
                     const unsigned slot = it % I8_STAGES, ph = (it / I8_STAGES) & 1u;
@@ -351,14 +399,20 @@ __global__ void __launch_bounds__(I8_THREADS, 1) i8_contract_kernel(const I8Para
                     for (int kk = 0; kk < I8_KB / 32; ++kk) {
                         const unsigned long long da = i8_desc(a0 + kk * 2 * (I8_M * 16), I8_M * 16, 128);
                         const unsigned long long db0 = i8_desc(b0 + kk * 2 * B_LBO, B_LBO, 128);
-                        const unsigned long long db1 = i8_desc(b0 + 32 * 128 + kk * 2 * B_LBO, B_LBO, 128);
-                        i8_mma(tmem_base, da, db0, idescA, (kb | kk) != 0);
-                        i8_mma(tmem_base + 4 * I8_N, da, db1, idescB, (kb | kk) != 0);
+                        const unsigned long long db1 = i8_desc(b0 + B_SECOND + kk * 2 * B_LBO, B_LBO, 128);
+                        if (CG2) {
+                            i8_mma_cg2(tmem_base, da, db0, idescA, (kb | kk) != 0);
+                            i8_mma_cg2(tmem_base + 4 * I8_N, da, db1, idescB, (kb | kk) != 0);
+                        } else {
+                            i8_mma(tmem_base, da, db0, idescA, (kb | kk) != 0);
+                            i8_mma(tmem_base + 4 * I8_N, da, db1, idescB, (kb | kk) != 0);
+                        }
                     }
-                    if (PAIR) i8_commit_mc(empty0 + 8 * slot, 3);         // frees the slot in BOTH CTAs when these MMAs retire
+                    if (CG2) i8_commit_cg2(empty0 + 8 * slot, 3);         // frees the slot in BOTH CTAs when these MMAs retire
                     else i8_commit(empty0 + 8 * slot);                    // frees the smem slot when these MMAs retire
                 }
-                i8_commit(accfull);                                        // accumulators of this (tile, trait) are complete
+                if (CG2) i8_commit_cg2(accfull, 3);                        // accumulators complete, in both CTAs' TMEM
+                else i8_commit(accfull);                                   // accumulators of this (tile, trait) are complete
             }
         }
     } else {
@@ -416,7 +470,7 @@ __global__ void __launch_bounds__(I8_THREADS, 1) i8_contract_kernel(const I8Para
                         if (cb == 32 / I8_EC - 1) {                                               // TMEM fully read: next trait's MMAs may start
                             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                             __syncwarp();
-                            if (lane == 0) i8_mbar_arrive(accempty);
+                            if (lane == 0) { if (CG2) i8_mbar_arrive_remote(accempty, 0); else i8_mbar_arrive(accempty); }
                         }
                         const unsigned nzw = nz >> (I8_EC * cb), ngw = ng >> (I8_EC * cb);
     #pragma unroll
@@ -491,7 +545,7 @@ __global__ void __launch_bounds__(I8_THREADS, 1) i8_contract_kernel(const I8Para
                         if (cb == 32 / I8_EC - 1) {
                             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                             __syncwarp();
-                            if (lane == 0) i8_mbar_arrive(accempty);
+                            if (lane == 0) { if (CG2) i8_mbar_arrive_remote(accempty, 0); else i8_mbar_arrive(accempty); }
                         }
                         const unsigned nzw = nz >> (I8_EC * cb), ngw = ng >> (I8_EC * cb);
 #pragma unroll
@@ -524,16 +578,18 @@ __global__ void __launch_bounds__(I8_THREADS, 1) i8_contract_kernel(const I8Para
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    if (PAIR) i8_cluster_sync();          // do not exit while the peer can still write into this CTA's shared memory
+    if (CG2) i8_cluster_sync();           // the pair's MMAs read both CTAs' shared memory and write both TMEMs
     if (warp == I8_EPI_WARPS) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+        if (CG2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+        else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
     }
 }
 
-size_t i8_smem_bytes(int T) {
+size_t i8_smem_bytes(int T, bool cg2) {
     const int rows = T <= 6 ? 2 * T : T + 1;          // per buffer: d_t[j] rows + scale rows (see the two epilogues)
-    return (size_t)I8_STAGES * I8_STAGE_BYTES + (2 * I8_STAGES + 4) * 8 + (size_t)2 * rows * 64 * 8;
+    const size_t stages = cg2 ? (size_t)I8Geo<true>::STAGES * I8Geo<true>::STAGE_BYTES : (size_t)I8Geo<false>::STAGES * I8Geo<false>::STAGE_BYTES;
+    return stages + (2 * I8_MAX_STAGES + 4) * 8 + (size_t)2 * rows * 64 * 8;
 }
 
 cudaError_t launch_i8_build_xi(const unsigned* planeA, const unsigned* planeB, long long wpp, const int* sire,
@@ -550,16 +606,16 @@ cudaError_t launch_i8_build_xi(const unsigned* planeA, const unsigned* planeB, l
 cudaError_t launch_i8_build_digits(const double* tiles, const ChromDesc* chrom_d, int c_begin, int c_end,
                                    const int* rowpref_d, int nrows, const int* blkpref_d, int nblks, const double* emat,
                                    long long mp_total, int T, double* scale, const long long* gbase_d, signed char* G,
-                                   cudaStream_t st) {
+                                   bool cg2, cudaStream_t st) {
     if (nrows == 0) return cudaSuccess;
     i8_rowscale_kernel<<<nrows, 128, 0, st>>>(tiles, chrom_d, c_begin, c_end, rowpref_d, emat, mp_total, T, scale);
-    i8_build_digits_kernel<<<nblks, 256, 0, st>>>(tiles, chrom_d, c_begin, c_end, blkpref_d, emat, mp_total, T, scale, gbase_d, G);
+    i8_build_digits_kernel<<<nblks, 256, 0, st>>>(tiles, chrom_d, c_begin, c_end, blkpref_d, emat, mp_total, T, scale, gbase_d, G, cg2 ? 1 : 0);
     return cudaGetLastError();
 }
 
 cudaError_t launch_i8_contract(const I8Params& p, int ntiles, int nsplit, bool pair, cudaStream_t st) {
     if (ntiles == 0) return cudaSuccess;
-    const size_t smem = i8_smem_bytes(p.T);
+    const size_t smem = i8_smem_bytes(p.T, pair);
     cudaError_t e = cudaSuccess;
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(pair ? (ntiles + 1) / 2 * 2 : ntiles, nsplit, 1);

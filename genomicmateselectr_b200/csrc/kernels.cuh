@@ -66,14 +66,14 @@ struct I8Params {
     int mode;
     double* Zpart;               // [nsplit][n_units][T*T]
 };
-size_t i8_smem_bytes(int T);
+size_t i8_smem_bytes(int T, bool cg2);
 cudaError_t launch_i8_build_xi(const unsigned* planeA, const unsigned* planeB, long long wpp, const int* sire,
                                const int* dam, long long n_units, int mode, long long nkb_total, signed char* xi,
                                cudaStream_t st);
 cudaError_t launch_i8_build_digits(const double* tiles, const ChromDesc* chrom_d, int c_begin, int c_end,
                                    const int* rowpref_d, int nrows, const int* blkpref_d, int nblks, const double* emat,
                                    long long mp_total, int T, double* scale, const long long* gbase_d, signed char* G,
-                                   cudaStream_t st);
+                                   bool cg2, cudaStream_t st);
 cudaError_t launch_i8_contract(const I8Params& p, int ntiles, int nsplit, bool pair, cudaStream_t st);
 
 // Nsegsnps per cross over words [w_begin, w_end) of the padded axis.

@@ -105,10 +105,10 @@ def test_one_engine_many_calls():
     eng.close()
 
 
-def test_int8_cta_pair_multicast_variant(monkeypatch):
-    """GMS_I8_PAIR=1: 2-CTA clusters, digit tiles fetched half by each CTA and multicast (kept as an option)."""
+def test_int8_cta_group2_variant(monkeypatch):
+    """GMS_I8_CG2=1: tcgen05 cta_group::2 - CTA pairs form one M = 256 tile, each CTA stages half of the digit operand."""
     import genomicmateselectr_b200 as g
-    monkeypatch.setenv("GMS_I8_PAIR", "1")
+    monkeypatch.setenv("GMS_I8_CG2", "1")
     m_c, cM, chrom, H, add, dom, asub, R = make(9, [200, 131, 77], 10, 5)
     rng = np.random.default_rng(2)
     sire = rng.integers(0, 10, 300).astype(np.int32)
