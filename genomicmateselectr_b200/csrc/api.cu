@@ -87,6 +87,9 @@ struct gms_handle {
     DevBuf<long long> gbase_d;
     DevBuf<signed char> xi_d, xi_het_d, xi_delta_d, G_d, G_add_d, G_asub_d;
     DevBuf<double> scale_d, scale_add_d, scale_asub_d;
+    DevBuf<int4> qtab_d, qtab_add_d, qtab_asub_d;      // fixed-point row weights of the integer-accumulating kernel
+    DevBuf<int> gexp_d, gexp_add_d, gexp_asub_d;
+    bool i8_ia = true;                 // i8v2.cu with exact integer accumulation when T <= 8 (GMS_I8_IA=0: FP64 epilogue)
     DevBuf<int> split_i8_d, split_i8_par_d, i8_rowpref_d, i8_blkpref_d;
     int i8_nrows = 0, i8_nblks = 0;
     Plan plan_i8, plan_i8_par, plan_i8_tail;
@@ -94,6 +97,9 @@ struct gms_handle {
     long long i8_chunk = 0;            // crosses per pass of the per-cross int8 kernel (bounds the xi image)
     bool use_i8 = false;
     bool i8_pair = false;              // tcgen05 cta_group::2: CTA pairs form one M = 256 tile (GMS_I8_CG2=1 enables)
+    bool i8_v2_ok = false;             // i8v2.cu kernel (GMS_I8_V2=1 enables; work in progress, not yet faster than i8path.cu); T <= 16
+    bool i8_v2 = false;                // the staged problem runs i8v2.cu
+    bool i8_mc = true;                 // i8v2.cu as row-half clusters with multicast xi tiles (GMS_I8_MC=0: one CTA per cross tile)
 
     // map-structured fast path
     int mode = GMS_MODE_AUTO;          // requested
@@ -350,6 +356,9 @@ int gms_create(gms_handle** out, int device) {
     }
     nh->stream = nh->own_stream;
     if (const char* ev = getenv("GMS_I8_CG2")) nh->i8_pair = atoi(ev) != 0;
+    if (const char* ev = getenv("GMS_I8_V2")) nh->i8_v2_ok = atoi(ev) != 0;
+    if (const char* ev = getenv("GMS_I8_MC")) nh->i8_mc = atoi(ev) != 0;
+    if (const char* ev = getenv("GMS_I8_IA")) nh->i8_ia = atoi(ev) != 0;
     for (auto& ev : nh->ev) cudaEventCreate(&ev);
     *out = nh;
     return GMS_OK;
@@ -369,6 +378,7 @@ void gms_destroy(gms_handle* h) {
     h->S_asub.release(); h->split_scan_par_d.release(); h->split_scan_x_d.release();
     h->jtiles_d.release(); h->gbase_d.release(); h->xi_d.release(); h->G_d.release(); h->scale_d.release(); h->split_i8_d.release();
     h->xi_het_d.release(); h->xi_delta_d.release(); h->G_add_d.release(); h->G_asub_d.release(); h->scale_add_d.release();
+    h->qtab_d.release(); h->qtab_add_d.release(); h->qtab_asub_d.release(); h->gexp_d.release(); h->gexp_add_d.release(); h->gexp_asub_d.release();
     h->scale_asub_d.release(); h->split_i8_par_d.release(); h->split_i8_tail_d.release(); h->i8_rowpref_d.release(); h->i8_blkpref_d.release();
     for (auto& ev : h->ev) if (ev) cudaEventDestroy(ev);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
@@ -620,6 +630,8 @@ int gms_stage_inputs(gms_handle* h, int model, int T, const double* add, const d
     if (h->mode == GMS_MODE_AUTO) h->eff_mode = i8_ok ? GMS_MODE_INT8_TENSOR : GMS_MODE_DENSE;
     if (h->eff_mode == GMS_MODE_INT8_TENSOR && !i8_ok) h->eff_mode = GMS_MODE_DENSE;
     h->use_i8 = h->eff_mode == GMS_MODE_INT8_TENSOR;
+    h->i8_v2 = h->use_i8 && h->i8_v2_ok && T <= 16;
+    const size_t npart = h->i8_v2 ? (size_t)i8v2_npart(h->i8_mc) : 2;     // partial slabs per split written by the int8 kernel
 
     size_t zneed = 0;
     if (h->eff_mode == GMS_MODE_MAP_SCAN) {
@@ -669,9 +681,17 @@ int gms_stage_inputs(gms_handle* h, int model, int T, const double* add, const d
         CU(cudaMemcpyAsync(h->jtiles_d.p, h->jtiles.data(), sizeof(RowTile) * h->jtiles.size(), cudaMemcpyHostToDevice, h->stream));
         CU(cudaMemcpyAsync(h->gbase_d.p, h->gbase.data(), sizeof(long long) * h->C, cudaMemcpyHostToDevice, h->stream));
         // digit planes: (R, add) [and (R, asub)] for the additive tables, (RoR, dom) for the dominance terms
+        const size_t qn = (h->i8_v2 && h->i8_ia && T <= 8) ? (size_t)h->mp_total * T * T : 1;
         CU(h->G_add_d.ensure((size_t)gb)); CU(h->scale_add_d.ensure((size_t)h->mp_total * T));
-        if (model >= GMS_MODEL_AD) { CU(h->G_d.ensure((size_t)gb)); CU(h->scale_d.ensure((size_t)h->mp_total * T)); }
-        if (model == GMS_MODEL_DIRDOM) { CU(h->G_asub_d.ensure((size_t)gb)); CU(h->scale_asub_d.ensure((size_t)h->mp_total * T)); }
+        CU(h->qtab_add_d.ensure(qn)); CU(h->gexp_add_d.ensure((size_t)T * T));
+        if (model >= GMS_MODEL_AD) {
+            CU(h->G_d.ensure((size_t)gb)); CU(h->scale_d.ensure((size_t)h->mp_total * T));
+            CU(h->qtab_d.ensure(qn)); CU(h->gexp_d.ensure((size_t)T * T));
+        }
+        if (model == GMS_MODEL_DIRDOM) {
+            CU(h->G_asub_d.ensure((size_t)gb)); CU(h->scale_asub_d.ensure((size_t)h->mp_total * T));
+            CU(h->qtab_asub_d.ensure(qn)); CU(h->gexp_asub_d.ensure((size_t)T * T));
+        }
         // mask images: parents (delta, het), crosses (xi)
         CU(h->xi_delta_d.ensure((size_t)ppad * h->mp_total));
         if (model >= GMS_MODEL_AD) { CU(h->xi_het_d.ensure((size_t)ppad * h->mp_total)); CU(h->xi_d.ensure((size_t)chunk * h->mp_total)); }
@@ -679,12 +699,13 @@ int gms_stage_inputs(gms_handle* h, int model, int T, const double* add, const d
         auto i8plan = [&](long long units, Plan& pl, DevBuf<int>& dev) -> int {
             pl.ntiles = (int)((units + 127) / 128);
             const int njt = (int)h->jtiles.size();
+            const int cpt = (h->i8_v2 && h->i8_mc) ? 2 : 1;        // CTAs per cross tile
             int ns = 1;
-            if (pl.ntiles < 2 * h->num_sms) ns = (2 * h->num_sms + pl.ntiles - 1) / std::max(1, pl.ntiles);
+            if (pl.ntiles * cpt < 2 * h->num_sms) ns = (2 * h->num_sms + pl.ntiles * cpt - 1) / std::max(1, pl.ntiles * cpt);
             else {
                 double best = 1e30;
                 for (int cand = 1; cand <= 8; ++cand) {
-                    const double ctas = (double)pl.ntiles * cand, waves = std::ceil(ctas / h->num_sms);
+                    const double ctas = (double)pl.ntiles * cpt * cand, waves = std::ceil(ctas / h->num_sms);
                     const double cost = waves * h->num_sms / ctas * (1.0 + 0.01 * (cand - 1));
                     if (cost < best - 1e-12) { best = cost; ns = cand; }
                 }
@@ -711,8 +732,8 @@ int gms_stage_inputs(gms_handle* h, int model, int T, const double* add, const d
         if (int rc = i8plan(n_full, h->plan_i8, h->split_i8_d)) return rc;
         if (int rc = i8plan(n_tail, h->plan_i8_tail, h->split_i8_tail_d)) return rc;
         if (int rc = i8plan(h->nP, h->plan_i8_par, h->split_i8_par_d)) return rc;
-        zneed = std::max<size_t>(std::max<size_t>((size_t)2 * h->plan_i8.nsplit * (size_t)n_full * TT, (size_t)2 * h->plan_i8_tail.nsplit * (size_t)n_tail * TT),
-                                 (size_t)2 * h->plan_i8_par.nsplit * (size_t)h->nP * TT);
+        zneed = std::max<size_t>(std::max<size_t>(npart * h->plan_i8.nsplit * (size_t)n_full * TT, npart * h->plan_i8_tail.nsplit * (size_t)n_tail * TT),
+                                 npart * h->plan_i8_par.nsplit * (size_t)h->nP * TT);
     } else {
         make_plan(h, h->nP, NU, h->plan_par);
         make_plan(h, model >= GMS_MODEL_AD ? N : 0, NU, h->plan_x);
@@ -760,16 +781,23 @@ int gms_compute(gms_handle* h, int sync) {
             CU(launch_scan_prepare(h->emat_asub.p, ab, ab + h->mp_total, h->mp_total, T, h->S_asub.p, h->stream));
         h->st.last_launches += h->model + 1;
     } else if (h->use_i8) {
-        auto digits = [&](const double* tiles, const double* emat, DevBuf<signed char>& G, DevBuf<double>& sc) -> int {
+        const bool ia = h->i8_v2 && h->i8_ia && T <= 8;
+        auto digits = [&](const double* tiles, const double* emat, DevBuf<signed char>& G, DevBuf<double>& sc, DevBuf<int4>& qt,
+                          DevBuf<int>& ge) -> int {
             CU(cudaMemsetAsync(sc.p, 0, sizeof(double) * h->mp_total * T, h->stream));
             CU(launch_i8_build_digits(tiles, h->chrom_d.p, h->c_begin, h->c_end, h->i8_rowpref_d.p, h->i8_nrows, h->i8_blkpref_d.p,
-                                      h->i8_nblks, emat, h->mp_total, T, sc.p, h->gbase_d.p, G.p, h->i8_pair, h->stream));
+                                      h->i8_nblks, emat, h->mp_total, T, sc.p, h->gbase_d.p, G.p, h->i8_v2 ? 2 : (h->i8_pair ? 1 : 0), h->stream));
             h->st.last_launches += 2;
+            if (ia) {
+                CU(launch_i8_build_qtab(emat, sc.p, h->mp_total, T, ge.p, qt.p, h->stream));
+                h->st.last_launches += 2;
+            }
             return GMS_OK;
         };
-        if (int rc = digits(h->R.p, h->emat_add.p, h->G_add_d, h->scale_add_d)) return rc;
-        if (h->model >= GMS_MODEL_AD) if (int rc = digits(h->R2.p, h->emat_dom.p, h->G_d, h->scale_d)) return rc;
-        if (h->model == GMS_MODEL_DIRDOM) if (int rc = digits(h->R.p, h->emat_asub.p, h->G_asub_d, h->scale_asub_d)) return rc;
+        if (int rc = digits(h->R.p, h->emat_add.p, h->G_add_d, h->scale_add_d, h->qtab_add_d, h->gexp_add_d)) return rc;
+        if (h->model >= GMS_MODEL_AD) if (int rc = digits(h->R2.p, h->emat_dom.p, h->G_d, h->scale_d, h->qtab_d, h->gexp_d)) return rc;
+        if (h->model == GMS_MODEL_DIRDOM)
+            if (int rc = digits(h->R.p, h->emat_asub.p, h->G_asub_d, h->scale_asub_d, h->qtab_asub_d, h->gexp_asub_d)) return rc;
         CU(launch_i8_build_xi(h->planeA.p, h->planeB.p, h->wpp, h->plist_d.p, nullptr, h->nP, MASK_DELTA, h->mp_total / 64, h->xi_delta_d.p, h->stream));
         if (h->model >= GMS_MODEL_AD) {
             CU(launch_i8_build_xi(h->planeA.p, h->planeB.p, h->wpp, h->plist_d.p, nullptr, h->nP, MASK_HET, h->mp_total / 64, h->xi_het_d.p, h->stream));
@@ -792,7 +820,8 @@ int gms_compute(gms_handle* h, int sync) {
                                   h->split_scan_x_d.p, h->X.p, h->ev[4], h->ev[5])) return rc;
     } else if (h->use_i8) {
         // exact int8 tcgen05 evaluation of all four tables (i8path.cu)
-        auto run_i8 = [&](const signed char* G, const double* scale, const signed char* xi, const double* emat, int mode,
+        const bool ia = h->i8_v2 && h->i8_ia && h->T <= 8;
+        auto run_i8 = [&](const signed char* G, const double* scale, const int4* qtab, const int* gexp, const signed char* xi, const double* emat, int mode,
                           const int* ua, const int* ub, long long n_units, const Plan& pl, const int* split_d, double* Xout,
                           cudaEvent_t e0, cudaEvent_t e1) -> int {
             if (n_units == 0) return GMS_OK;
@@ -802,21 +831,23 @@ int gms_compute(gms_handle* h, int sync) {
             ip.scale = scale; ip.emat = emat; ip.mp_total = h->mp_total;
             ip.planeA = h->planeA.p; ip.planeB = h->planeB.p; ip.wpp = h->wpp;
             ip.unit_a = ua; ip.unit_b = ub; ip.n_units = n_units; ip.T = h->T; ip.mode = mode;
-            ip.Zpart = h->Z.p;
+            ip.Zpart = h->Z.p; ip.qtab = qtab; ip.gexp = gexp;
+            if (const char* ev = getenv("GMS_I8_DEBUG")) ip.debug = atoi(ev);
             if (e0) CU(cudaEventRecord(e0, h->stream));
-            CU(launch_i8_contract(ip, pl.ntiles, pl.nsplit, h->i8_pair, h->stream));
+            if (h->i8_v2) CU(launch_i8v2_contract(ip, pl.ntiles, pl.nsplit, h->i8_mc, ia, h->stream));
+            else CU(launch_i8_contract(ip, pl.ntiles, pl.nsplit, h->i8_pair, h->stream));
             if (e1) CU(cudaEventRecord(e1, h->stream));
-            CU(launch_finalize_sym(h->Z.p, 2 * pl.nsplit, n_units, h->T, Xout, h->stream, true));
+            CU(launch_finalize_sym(h->Z.p, (h->i8_v2 ? i8v2_npart(h->i8_mc) : 2) * pl.nsplit, n_units, h->T, Xout, h->stream, true));
             h->st.last_launches += 2;
             return GMS_OK;
         };
-        if (int rc = run_i8(h->G_add_d.p, h->scale_add_d.p, h->xi_delta_d.p, h->emat_add.p, MASK_DELTA, h->plist_d.p, nullptr,
+        if (int rc = run_i8(h->G_add_d.p, h->scale_add_d.p, h->qtab_add_d.p, h->gexp_add_d.p, h->xi_delta_d.p, h->emat_add.p, MASK_DELTA, h->plist_d.p, nullptr,
                             h->nP, h->plan_i8_par, h->split_i8_par_d.p, h->QA.p, nullptr, nullptr)) return rc;
         if (h->model >= GMS_MODEL_AD)
-            if (int rc = run_i8(h->G_d.p, h->scale_d.p, h->xi_het_d.p, h->emat_dom.p, MASK_HET, h->plist_d.p, nullptr,
+            if (int rc = run_i8(h->G_d.p, h->scale_d.p, h->qtab_d.p, h->gexp_d.p, h->xi_het_d.p, h->emat_dom.p, MASK_HET, h->plist_d.p, nullptr,
                                 h->nP, h->plan_i8_par, h->split_i8_par_d.p, h->PD.p, nullptr, nullptr)) return rc;
         if (h->model == GMS_MODEL_DIRDOM)
-            if (int rc = run_i8(h->G_asub_d.p, h->scale_asub_d.p, h->xi_delta_d.p, h->emat_asub.p, MASK_DELTA, h->plist_d.p, nullptr,
+            if (int rc = run_i8(h->G_asub_d.p, h->scale_asub_d.p, h->qtab_asub_d.p, h->gexp_asub_d.p, h->xi_delta_d.p, h->emat_asub.p, MASK_DELTA, h->plist_d.p, nullptr,
                                 h->nP, h->plan_i8_par, h->split_i8_par_d.p, h->QB.p, nullptr, nullptr)) return rc;
         CU(cudaEventRecord(h->ev[1], h->stream));
         if (h->model >= GMS_MODEL_AD) {
@@ -829,7 +860,7 @@ int gms_compute(gms_handle* h, int sync) {
                 CU(launch_i8_build_xi(h->planeA.p, h->planeB.p, h->wpp, h->sire_d.p + off, h->dam_d.p + off, n, MASK_XI,
                                       h->mp_total / 64, h->xi_d.p, h->stream));
                 h->st.last_launches += 1;
-                if (int rc = run_i8(h->G_d.p, h->scale_d.p, h->xi_d.p, h->emat_dom.p, MASK_XI, h->sire_d.p + off, h->dam_d.p + off, n,
+                if (int rc = run_i8(h->G_d.p, h->scale_d.p, h->qtab_d.p, h->gexp_d.p, h->xi_d.p, h->emat_dom.p, MASK_XI, h->sire_d.p + off, h->dam_d.p + off, n,
                                     tail ? h->plan_i8_tail : h->plan_i8, tail ? h->split_i8_tail_d.p : h->split_i8_d.p,
                                     h->X.p + off * (long long)(h->T * h->T), one_pass ? h->ev[4] : nullptr,
                                     one_pass ? h->ev[5] : nullptr)) return rc;

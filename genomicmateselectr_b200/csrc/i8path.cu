@@ -17,6 +17,7 @@
 // Warp roles: 0-7 epilogue (tcgen05.ld; two warps per TMEM lane quarter, 32 accumulator columns each),
 // 8 bulk-copy producer, 9 MMA issuer.
 #include "kernels.cuh"
+#include "i8ptx.cuh"
 
 namespace gms {
 
@@ -148,7 +149,7 @@ __global__ void i8_rowscale_kernel(const double* __restrict__ tiles, const Chrom
 __global__ void i8_build_digits_kernel(const double* __restrict__ tiles, const ChromDesc* __restrict__ chrom, int c_begin,
                                        int c_end, const int* __restrict__ blkpref, const double* __restrict__ emat,
                                        long long mp_total, int T, const double* __restrict__ scale,
-                                       const long long* __restrict__ gbase_c, signed char* __restrict__ G, int cg2) {
+                                       const long long* __restrict__ gbase_c, signed char* __restrict__ G, int layout) {
     int c = c_begin;
     while (c + 1 < c_end && (int)blockIdx.x >= blkpref[c + 1]) ++c;     // blkpref[c] = first block of chromosome c
     const ChromDesc cd = chrom[c];
@@ -189,15 +190,21 @@ __global__ void i8_build_digits_kernel(const double* __restrict__ tiles, const C
         for (int i = 0; i < I8_DIG; ++i) {
             signed char* img = G + gbase + (((long long)blk * T + s) * (long long)I8_B_ALL);
             int off;
-            if (!cg2) {
+            if (layout == 0) {
                 off = ((cc * (I8_DIG * 8) + (i * 8 + r1)) * 8 + r0) * 16;             // one 448-row operand
-            } else {
+            } else if (layout == 1) {
                 // cta_group::2: the N = 256 MMA takes rows 0-127 from the leader and 128-255 from the peer, the N = 192
                 // MMA rows 0-95 / 96-191; each CTA's half is a 224-row operand [128 rows | 96 rows], halves back to back
                 const int g = i * 64 + r;                                           // row of the 448-row operand
                 const int h = g < 256 ? g / 128 : (g - 256) / 96;
                 const int lr = g < 256 ? g % 128 : 128 + (g - 256) % 96;
                 off = h * (I8_B_ALL / 2) + ((cc * 28 + (lr >> 3)) * 8 + (lr & 7)) * 16;
+            } else {
+                // i8v2.cu: the images of block row J are ordered [trait s][row half h][kb <= J], so that the k-blocks of one
+                // (32-row tile, trait) are contiguous; operand = 224 rows (digit i x 32 rows)
+                const int h = r >> 5, g = i * 32 + (r & 31);
+                img = G + gbase + (long long)(J * (J + 1) / 2) * T * I8_B_ALL + ((long long)(s * 2 + h) * (J + 1) + kb) * (I8_B_ALL / 2);
+                off = ((cc * 28 + (g >> 3)) * 8 + (g & 7)) * 16;
             }
             *reinterpret_cast<uint4*>(img + off) = *reinterpret_cast<const uint4*>(d[i]);
         }
@@ -205,80 +212,6 @@ __global__ void i8_build_digits_kernel(const double* __restrict__ tiles, const C
 }
 
 // ------------------------------------------------------------------------------------------ main kernel
-__device__ __forceinline__ unsigned i8_smem_u32(const void* p) { return static_cast<unsigned>(__cvta_generic_to_shared(p)); }
-__device__ __forceinline__ void i8_mbar_init(unsigned bar, unsigned count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void i8_mbar_arrive(unsigned bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void i8_mbar_expect_tx(unsigned bar, unsigned bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void i8_mbar_wait(unsigned bar, unsigned parity) {
-    unsigned ok;
-    do {
-        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
-                     : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
-    } while (!ok);
-}
-__device__ __forceinline__ void i8_bulk_g2s(unsigned dst, const void* src, unsigned bytes, unsigned bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
-}
-// K-major, no swizzle: uint128 offset of (row r0 + 8 r1, chunk c) = r0 + r1*SBO + c*LBO   (cute mma_traits_sm100.hpp)
-__device__ __forceinline__ unsigned long long i8_desc(unsigned smem_addr, unsigned lbo_bytes, unsigned sbo_bytes) {
-    unsigned long long d = 0;
-    d |= (unsigned long long)((smem_addr >> 4) & 0x3FFFu);
-    d |= (unsigned long long)((lbo_bytes >> 4) & 0x3FFFu) << 16;
-    d |= (unsigned long long)((sbo_bytes >> 4) & 0x3FFFu) << 32;
-    d |= 1ull << 46;                                  // descriptor version (Blackwell)
-    return d;                                         // base_offset 0, lbo_mode 0, layout_type 0 = SWIZZLE_NONE
-}
-__device__ __forceinline__ void i8_mma(unsigned tmem_d, unsigned long long da, unsigned long long db, unsigned idesc,
-                                       unsigned accumulate) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "setp.ne.b32 p, %4, 0;\n"
-        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n"
-        "}\n"
-        ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate), "r"(0u)
-        : "memory");
-}
-// arrive on the mbarrier at the same shared-memory offset in CTA `rank` of the cluster
-__device__ __forceinline__ void i8_mbar_arrive_remote(unsigned bar, unsigned rank) {
-    asm volatile("{\n.reg .b32 ra;\nmapa.shared::cluster.u32 ra, %0, %1;\nmbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n}\n"
-                 ::"r"(bar), "r"(rank) : "memory");
-}
-// one M = 256 MMA over a CTA pair: each CTA supplies its 128 A rows and HALF of the B rows from its own shared memory (same
-// offsets in both CTAs); rows 0-127 of D land in the leader's TMEM, rows 128-255 in the peer's. Issued by the leader only.
-__device__ __forceinline__ void i8_mma_cg2(unsigned tmem_d, unsigned long long da, unsigned long long db, unsigned idesc,
-                                           unsigned accumulate) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "setp.ne.b32 p, %4, 0;\n"
-        "tcgen05.mma.cta_group::2.kind::i8 [%0], %1, %2, %3, {%5, %5, %5, %5, %5, %5, %5, %5}, p;\n"
-        "}\n"
-        ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate), "r"(0u)
-        : "memory");
-}
-__device__ __forceinline__ void i8_commit_cg2(unsigned bar, unsigned short mask) {
-    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-                 ::"r"(bar), "h"(mask) : "memory");
-}
-__device__ __forceinline__ void i8_cluster_sync() {
-    asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-__device__ __forceinline__ unsigned i8_cta_rank() {
-    unsigned r;
-    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-    return r;
-}
-__device__ __forceinline__ void i8_commit(unsigned bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
 constexpr int I8_EC = 8;             // accumulator columns per tcgen05.ld (x8) in the epilogue
 __device__ __forceinline__ void i8_tmem_ldc(unsigned taddr, int (&v)[I8_EC]) {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
@@ -400,6 +333,7 @@ __global__ void __launch_bounds__(I8_THREADS, 1) i8_contract_kernel(const I8Para
                         const unsigned long long da = i8_desc(a0 + kk * 2 * (I8_M * 16), I8_M * 16, 128);
                         const unsigned long long db0 = i8_desc(b0 + kk * 2 * B_LBO, B_LBO, 128);
                         const unsigned long long db1 = i8_desc(b0 + B_SECOND + kk * 2 * B_LBO, B_LBO, 128);
+                        if (p.debug & 2) continue;
                         if (CG2) {
                             i8_mma_cg2(tmem_base, da, db0, idescA, (kb | kk) != 0);
                             i8_mma_cg2(tmem_base + 4 * I8_N, da, db1, idescB, (kb | kk) != 0);
@@ -461,6 +395,12 @@ __global__ void __launch_bounds__(I8_THREADS, 1) i8_contract_kernel(const I8Para
                 for (int s = 0; s < TT; ++s, ++acc_it) {               // unrolled: Z[t][s] must stay in registers
                     i8_mbar_wait(accfull, acc_it & 1u);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    if (p.debug & 1) {
+                        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                        __syncwarp();
+                        if (lane == 0) { if (CG2) i8_mbar_arrive_remote(accempty, 0); else i8_mbar_arrive(accempty); }
+                        continue;
+                    }
     #pragma unroll 1
                     for (int cb = 0; cb < 32 / I8_EC; ++cb) {                        // I8_EC SNP rows at a time
                         int dig[I8_DIG][I8_EC];
@@ -606,10 +546,10 @@ cudaError_t launch_i8_build_xi(const unsigned* planeA, const unsigned* planeB, l
 cudaError_t launch_i8_build_digits(const double* tiles, const ChromDesc* chrom_d, int c_begin, int c_end,
                                    const int* rowpref_d, int nrows, const int* blkpref_d, int nblks, const double* emat,
                                    long long mp_total, int T, double* scale, const long long* gbase_d, signed char* G,
-                                   bool cg2, cudaStream_t st) {
+                                   int layout, cudaStream_t st) {
     if (nrows == 0) return cudaSuccess;
     i8_rowscale_kernel<<<nrows, 128, 0, st>>>(tiles, chrom_d, c_begin, c_end, rowpref_d, emat, mp_total, T, scale);
-    i8_build_digits_kernel<<<nblks, 256, 0, st>>>(tiles, chrom_d, c_begin, c_end, blkpref_d, emat, mp_total, T, scale, gbase_d, G, cg2 ? 1 : 0);
+    i8_build_digits_kernel<<<nblks, 256, 0, st>>>(tiles, chrom_d, c_begin, c_end, blkpref_d, emat, mp_total, T, scale, gbase_d, G, layout);
     return cudaGetLastError();
 }
 

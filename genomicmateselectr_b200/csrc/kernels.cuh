@@ -65,6 +65,9 @@ struct I8Params {
     int T;
     int mode;
     double* Zpart;               // [nsplit][n_units][T*T]
+    const int4* qtab;            // i8v2 integer accumulation: [trait s][mp_total][trait t] fixed-point weights (q0, q1, q2, -)
+    const int* gexp;             // [T x T] their exponents
+    int debug;                   // profiling only (GMS_I8_DEBUG): 1 = no epilogue arithmetic, 2 = no MMAs, 4 = no loads (i8v2); results are garbage
 };
 size_t i8_smem_bytes(int T, bool cg2);
 cudaError_t launch_i8_build_xi(const unsigned* planeA, const unsigned* planeB, long long wpp, const int* sire,
@@ -73,8 +76,18 @@ cudaError_t launch_i8_build_xi(const unsigned* planeA, const unsigned* planeB, l
 cudaError_t launch_i8_build_digits(const double* tiles, const ChromDesc* chrom_d, int c_begin, int c_end,
                                    const int* rowpref_d, int nrows, const int* blkpref_d, int nblks, const double* emat,
                                    long long mp_total, int T, double* scale, const long long* gbase_d, signed char* G,
-                                   bool cg2, cudaStream_t st);
+                                   int layout, cudaStream_t st);     // layout: 0 / 1 = i8path.cu (plain / cta_group::2), 2 = i8v2.cu
 cudaError_t launch_i8_contract(const I8Params& p, int ntiles, int nsplit, bool pair, cudaStream_t st);
+// i8v2.cu: 32-row tiles, two TMEM accumulators (epilogue overlapped with the next unit's MMAs), T <= 16; writes
+// i8v2_npart() partial slabs per split. mc: clusters of two CTAs share a cross tile and take one row half each (the grid
+// is then 2 x ntiles wide); mc = false runs both halves in one CTA
+int i8v2_npart(bool mc);
+size_t i8v2_smem_bytes(int T, bool ia);
+// ia: exact integer accumulation of the quadratic forms (T <= 8; needs p.qtab / p.gexp from launch_i8_build_qtab), so that
+// no floating-point instruction runs next to the MMAs
+cudaError_t launch_i8v2_contract(const I8Params& p, int ntiles, int nsplit, bool mc, bool ia, cudaStream_t st);
+cudaError_t launch_i8_build_qtab(const double* emat, const double* scale, long long mp_total, int T, int* gexp, int4* qtab,
+                                 cudaStream_t st);
 
 // Nsegsnps per cross over words [w_begin, w_end) of the padded axis.
 cudaError_t launch_nseg(const unsigned* planeA, const unsigned* planeB, long long wpp, long long w_begin,

@@ -16,6 +16,24 @@ for mode in (["fp64"] + modes if "fp64" not in modes else modes):
     eng.stage("AD", d["add"], d["dom"], None, d["sire"], d["dam"])
     eng.compute(sync=True)
     eng.compute(sync=True)
+    if os.environ.get("PM_LOOP"):
+        # sustained loop with SM clock / power sampling (nvidia-smi), to see throttling under this mode
+        import subprocess, threading, time
+        samples, stop = [], threading.Event()
+        def sampler():
+            while not stop.is_set():
+                r = subprocess.run(["nvidia-smi", "--query-gpu=clocks.sm,power.draw", "--format=csv,noheader,nounits", "-i", "0"],
+                                   capture_output=True, text=True).stdout.strip().split(",")
+                try: samples.append((float(r[0]), float(r[1])))
+                except Exception: pass
+                time.sleep(0.05)
+        th = threading.Thread(target=sampler); th.start()
+        t0 = time.time(); ks = []
+        while time.time() - t0 < float(os.environ["PM_LOOP"]):
+            eng.compute(sync=True); ks.append(eng.stats()["last_ms_cross_kernel"])
+        stop.set(); th.join()
+        sm = sorted(x[0] for x in samples[2:]); pw = sorted(x[1] for x in samples[2:])
+        if sm: print(f"  loop: kernel median {sorted(ks)[len(ks)//2]:.3f} ms over {len(ks)} runs; SM MHz median {sm[len(sm)//2]:.0f} min {sm[0]:.0f}; power W median {pw[len(pw)//2]:.0f} max {pw[-1]:.0f}")
     out, nseg = eng.fetch()
     st = eng.stats()
     if ref is None:
