@@ -710,6 +710,7 @@ int gms_stage_inputs(gms_handle* h, int model, int T, const double* add, const d
                     if (cost < best - 1e-12) { best = cost; ns = cand; }
                 }
             }
+            if (h->i8_v2) ns = std::max(ns, (njt + i8v2_max_tiles_per_split() - 1) / i8v2_max_tiles_per_split() + 1);
             ns = std::max(1, std::min(ns, njt));
             pl.nsplit = ns;
             pl.split_begin.assign(ns + 1, 0);

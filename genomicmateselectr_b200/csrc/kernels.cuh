@@ -82,6 +82,7 @@ cudaError_t launch_i8_contract(const I8Params& p, int ntiles, int nsplit, bool p
 // i8v2_npart() partial slabs per split. mc: clusters of two CTAs share a cross tile and take one row half each (the grid
 // is then 2 x ntiles wide); mc = false runs both halves in one CTA
 int i8v2_npart(bool mc);
+int i8v2_max_tiles_per_split();       // the plan must cut the 64-row tile list into splits no longer than this
 size_t i8v2_smem_bytes(int T, bool ia);
 // ia: exact integer accumulation of the quadratic forms (T <= 8; needs p.qtab / p.gexp from launch_i8_build_qtab), so that
 // no floating-point instruction runs next to the MMAs
