@@ -96,7 +96,7 @@ struct gms_handle {
     DevBuf<int> split_i8_tail_d;
     long long i8_chunk = 0;            // crosses per pass of the per-cross int8 kernel (bounds the xi image)
     bool use_i8 = false;
-    bool i8_pair = false;              // tcgen05 cta_group::2: CTA pairs form one M = 256 tile (GMS_I8_CG2=1 enables)
+    bool i8_pair = true;               // tcgen05 cta_group::2: CTA pairs form one M = 256 tile (GMS_I8_CG2=0: one CTA per 128 crosses)
     bool i8_v2_ok = false;             // i8v2.cu kernel (GMS_I8_V2=1 enables; work in progress, not yet faster than i8path.cu); T <= 16
     bool i8_v2 = false;                // the staged problem runs i8v2.cu
     bool i8_mc = true;                 // i8v2.cu as row-half clusters with multicast xi tiles (GMS_I8_MC=0: one CTA per cross tile)
@@ -710,7 +710,7 @@ int gms_stage_inputs(gms_handle* h, int model, int T, const double* add, const d
                     if (cost < best - 1e-12) { best = cost; ns = cand; }
                 }
             }
-            if (h->i8_v2) ns = std::max(ns, (njt + i8v2_max_tiles_per_split() - 1) / i8v2_max_tiles_per_split() + 1);
+            ns = std::max(ns, (njt + i8v2_max_tiles_per_split() - 1) / i8v2_max_tiles_per_split());     // the kernels' shared-memory work list
             ns = std::max(1, std::min(ns, njt));
             pl.nsplit = ns;
             pl.split_begin.assign(ns + 1, 0);

@@ -35,6 +35,7 @@ template <bool CG2> struct I8Geo {
     static constexpr int STAGES = CG2 ? 8 : 5;                         // 180 KiB / 176 KiB
 };
 constexpr int I8_MAX_STAGES = 8;
+constexpr int I8_TTAB = 512;        // 64-row tiles per split that fit the shared-memory copy of the work list (the host plan keeps splits below it)
 constexpr int I8_EPI_WARPS = 8;     // two per TMEM lane quarter: each takes 32 of the 64 accumulator columns
 constexpr int I8_THREADS = 32 * (I8_EPI_WARPS + 2);
 
@@ -139,7 +140,7 @@ __global__ void i8_rowscale_kernel(const double* __restrict__ tiles, const Chrom
         double v = 0.0;
         for (int i = 0; i < (int)(blockDim.x >> 5); ++i) v = fmax(v, sh[i][threadIdx.x]);
         int e = 0;
-        if (v > 0.0) { (void)frexp(v, &e); }            // v = f * 2^e, f in [0.5, 1)  =>  v < 2^e
+        if (v > 0x1p-900) { (void)frexp(v, &e); }       // v = f * 2^e, f in [0.5, 1)  =>  v < 2^e; a row below 2^-900 counts as zero
         scale[(long long)threadIdx.x * mp_total + cd.pad_off + row] = ldexp(1.0, e);
     }
 }
@@ -233,7 +234,8 @@ __global__ void __launch_bounds__(I8_THREADS, 1) i8_contract_kernel(const I8Para
     constexpr int I8_STAGES = I8Geo<CG2>::STAGES, I8_STAGE_BYTES = I8Geo<CG2>::STAGE_BYTES, B_STAGE = I8Geo<CG2>::B_STAGE;
     unsigned long long* bars = reinterpret_cast<unsigned long long*>(smem + I8_STAGES * I8_STAGE_BYTES);
     unsigned* tmem_slot = reinterpret_cast<unsigned*>(bars + 2 * I8_MAX_STAGES + 2);
-    double* rowbuf = reinterpret_cast<double*>(bars + 2 * I8_MAX_STAGES + 4);   // [2 buffers][2 T (or T + 1)][64]: d_t[j], scale_s[j]
+    int4* ttab = reinterpret_cast<int4*>(bars + 2 * I8_MAX_STAGES + 4);        // this CTA's range of the 64-row tile list (I8_TTAB entries)
+    double* rowbuf = reinterpret_cast<double*>(ttab + I8_TTAB);                // [2 buffers][3 T (or T + 2)][64]: d_t[j], then m_s[j] = 2^-49 scale_s[j], -2^52 m_s[j]
     const unsigned full0 = i8_smem_u32(bars), empty0 = i8_smem_u32(bars + I8_MAX_STAGES);
     const unsigned accfull = i8_smem_u32(bars + 2 * I8_MAX_STAGES), accempty = i8_smem_u32(bars + 2 * I8_MAX_STAGES + 1);
     const unsigned crank = CG2 ? i8_cta_rank() : 0u;       // 0 = leader of the pair
@@ -241,10 +243,26 @@ __global__ void __launch_bounds__(I8_THREADS, 1) i8_contract_kernel(const I8Para
     const long long X = blockIdx.x;
     const int split = blockIdx.y;
     const int jt_begin = p.split_begin[split], jt_end = p.split_begin[split + 1];
-    const int njt = jt_end - jt_begin, nunits = njt * T;       // a unit = one (tile, trait) accumulator pass
-    // unit u -> (tile, trait) in this kernel's loop order
-    auto unit_jt = [&](int u) { return jt_begin + (SOUTER ? u % njt : u / T); };
-    auto unit_s = [&](int u) { return SOUTER ? u / njt : u % T; };
+    // the CTA's range of the work list, once, in shared memory: (J | nkb << 16, padded index of the tile's first row, index of
+    // its first (block, trait) digit image) - no role chases jtiles -> chrom -> gbase through global memory per unit
+    for (int i = threadIdx.x; i < jt_end - jt_begin; i += I8_THREADS) {
+        const RowTile t = p.jtiles[jt_begin + i];
+        const ChromDesc cd = p.chrom[t.c];
+        const long long gblk = p.gbase[t.c] / I8_B_ALL + (long long)(t.I * (t.I + 1) / 2) * p.T;
+        ttab[i] = make_int4(t.I | (min(t.I + 1, (cd.m + I8_KB - 1) / I8_KB) << 16), cd.pad_off + 64 * t.I, (int)(gblk & 0xFFFFFFFFll), (int)(gblk >> 32));
+    }
+    // every role walks the units (64-row tile, trait) in the same order: f(tile entry, s)
+    auto for_units = [&](auto f) {
+        if (!SOUTER) {
+            for (int jt = jt_begin; jt < jt_end; ++jt) {
+                const int4 e = ttab[jt - jt_begin];
+                for (int s = 0; s < T; ++s) f(e, s);
+            }
+        } else {
+            for (int s = 0; s < T; ++s)
+                for (int jt = jt_begin; jt < jt_end; ++jt) f(ttab[jt - jt_begin], s);
+        }
+    };
 
     if (threadIdx.x == 0) {
         // CG2 leader: a `full` phase needs its own data AND the peer's relay; accumulators are drained by both CTAs' epilogues
@@ -269,44 +287,41 @@ __global__ void __launch_bounds__(I8_THREADS, 1) i8_contract_kernel(const I8Para
     const unsigned tmem_base = *tmem_slot;
 
     if (warp == I8_EPI_WARPS) {
-        // ------------------------------------------------------------------ producer (one lane)
-        if (lane == 0) {
-            unsigned it = 0;
-            for (int u = 0; u < nunits; ++u) {
-                const RowTile tile = p.jtiles[unit_jt(u)];
-                const int s = unit_s(u);
-                const ChromDesc cd = p.chrom[tile.c];
-                const int J = tile.I;
-                const int nkb = min(J + 1, (cd.m + I8_KB - 1) / I8_KB);
-                const signed char* abase = p.xi + (X * p.nkb_total + (cd.pad_off >> 6)) * (long long)I8_A_BYTES;
-                const signed char* gb = p.G + p.gbase[tile.c] + ((long long)(J * (J + 1) / 2) * T) * (long long)I8_B_ALL;
-                for (int kb = 0; kb < nkb; ++kb, ++it) {
-                    const unsigned slot = it % I8_STAGES, ph = (it / I8_STAGES) & 1u;
-                    i8_mbar_wait(empty0 + 8 * slot, ph ^ 1u);
-                    const unsigned dst = i8_smem_u32(stage0 + slot * I8_STAGE_BYTES);
-                    i8_mbar_expect_tx(full0 + 8 * slot, I8_STAGE_BYTES);
-                    i8_bulk_g2s(dst, abase + (long long)kb * I8_A_BYTES, I8_A_BYTES, full0 + 8 * slot);
-                    const signed char* gsrc = gb + ((long long)kb * T + s) * (long long)I8_B_ALL;
-                    i8_bulk_g2s(dst + I8_A_BYTES, gsrc + crank * B_STAGE, B_STAGE, full0 + 8 * slot);    // CG2: this CTA's half
+        // ------------------------------------------------------------------ producer: the whole warp walks the loop (addresses and
+        // counters stay in uniform registers), one elected lane issues the copies
+        unsigned slot = 0, ph = 0;
+        for_units([&](const int4 e, int s) {
+            const int J = e.x & 0xFFFF, nkb = e.x >> 16;
+            const long long gblk = ((long long)e.w << 32) | (unsigned)e.z;
+            const signed char* abase = p.xi + (X * p.nkb_total + ((e.y - 64 * J) >> 6)) * (long long)I8_A_BYTES;
+            const signed char* gb = p.G + (gblk + s) * (long long)I8_B_ALL + crank * B_STAGE;       // CG2: this CTA's half
+            for (int kb = 0; kb < nkb; ++kb) {
+                i8_mbar_wait(empty0 + 8 * slot, ph ^ 1u);
+                if (v2_elect()) {
+                    const unsigned dst = i8_smem_u32(stage0) + slot * I8_STAGE_BYTES, bar = full0 + 8 * slot;
+                    i8_mbar_expect_tx(bar, I8_STAGE_BYTES);
+                    i8_bulk_g2s(dst, abase + (long long)kb * I8_A_BYTES, I8_A_BYTES, bar);
+                    i8_bulk_g2s(dst + I8_A_BYTES, gb + (long long)kb * T * I8_B_ALL, B_STAGE, bar);
                 }
+                __syncwarp();
+                if (++slot == I8_STAGES) { slot = 0; ph ^= 1u; }
             }
-        }
+        });
     } else if (warp == I8_EPI_WARPS + 1) {
-        // ------------------------------------------------------------------ MMA issuer (one lane; CG2: leader only)
-        if (lane == 0 && CG2 && crank != 0) {
+        // ------------------------------------------------------------------ MMA issuer (CG2: the leader; the peer relays)
+        if (CG2 && crank != 0) {
             // peer of a pair: relay every completed `full` phase (own xi tile + own half of the digits) to the leader
-            unsigned it = 0;
-            for (int u = 0; u < nunits; ++u) {
-                const RowTile tile = p.jtiles[unit_jt(u)];
-                const ChromDesc cd = p.chrom[tile.c];
-                const int nkb = min(tile.I + 1, (cd.m + I8_KB - 1) / I8_KB);
-                for (int kb = 0; kb < nkb; ++kb, ++it) {
-                    const unsigned slot = it % I8_STAGES, ph = (it / I8_STAGES) & 1u;
+            unsigned slot = 0, ph = 0;
+            for_units([&](const int4 e, int) {
+                const int nkb = e.x >> 16;
+                for (int kb = 0; kb < nkb; ++kb) {
                     i8_mbar_wait(full0 + 8 * slot, ph);
-                    i8_mbar_arrive_remote(full0 + 8 * slot, 0);
+                    if (v2_elect()) i8_mbar_arrive_remote(full0 + 8 * slot, 0);
+                    __syncwarp();
+                    if (++slot == I8_STAGES) { slot = 0; ph ^= 1u; }
                 }
-            }
-        } else if (lane == 0) {
+            });
+        } else {
             // instruction descriptor: D = S32, A = B = signed 8 bit, K-major both; M = 128 (256 over a CTA pair)
             const unsigned idesc0 = (2u << 4) | (1u << 7) | (1u << 10) | ((unsigned)((CG2 ? 2 * I8_M : I8_M) >> 4) << 24);
             const unsigned idescA = idesc0 | ((unsigned)((4 * I8_N) >> 3) << 17);      // N = 256: digits 0-3
@@ -315,39 +330,44 @@ __global__ void __launch_bounds__(I8_THREADS, 1) i8_contract_kernel(const I8Para
             constexpr unsigned B_ROWS = CG2 ? (I8_DIG * I8_N) / 2 : I8_DIG * I8_N;
             constexpr unsigned B_LBO = (B_ROWS / 8) * 128;                           // chunk stride
             constexpr unsigned B_SECOND = (CG2 ? (4 * I8_N) / 2 : 4 * I8_N) / 8 * 128;   // byte offset of the N = 192 part
-            unsigned it = 0;
-            for (int u = 0; u < nunits; ++u) {
-                const RowTile tile = p.jtiles[unit_jt(u)];
-                const ChromDesc cd = p.chrom[tile.c];
-                const int nkb = min(tile.I + 1, (cd.m + I8_KB - 1) / I8_KB);
-                i8_mbar_wait(accempty, ((unsigned)u & 1u) ^ 1u);           // the epilogue(s) have drained the accumulators
+            // descriptors of slot 0, k32-step 0; everything else is an add on the 14-bit address field
+            const unsigned long long da0 = i8_desc(i8_smem_u32(stage0), I8_M * 16, 128);
+            const unsigned long long db0 = i8_desc(i8_smem_u32(stage0) + I8_A_BYTES, B_LBO, 128);
+            unsigned slot = 0, ph = 0, u = 0;
+            for_units([&](const int4 e, int) {
+                const int nkb = e.x >> 16;
+                i8_mbar_wait(accempty, (u & 1u) ^ 1u);                     // the epilogue(s) have drained the accumulators
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                for (int kb = 0; kb < nkb; ++kb, ++it) {
-                    const unsigned slot = it % I8_STAGES, ph = (it / I8_STAGES) & 1u;
+                for (int kb = 0; kb < nkb; ++kb) {
                     i8_mbar_wait(full0 + 8 * slot, ph);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    const unsigned a0 = i8_smem_u32(stage0 + slot * I8_STAGE_BYTES);
-                    const unsigned b0 = a0 + I8_A_BYTES;
+                    if (v2_elect()) {
+                        const unsigned long long das = da0 + ((slot * I8_STAGE_BYTES) >> 4), dbs = db0 + ((slot * I8_STAGE_BYTES) >> 4);
 #pragma unroll
-                    for (int kk = 0; kk < I8_KB / 32; ++kk) {
-                        const unsigned long long da = i8_desc(a0 + kk * 2 * (I8_M * 16), I8_M * 16, 128);
-                        const unsigned long long db0 = i8_desc(b0 + kk * 2 * B_LBO, B_LBO, 128);
-                        const unsigned long long db1 = i8_desc(b0 + B_SECOND + kk * 2 * B_LBO, B_LBO, 128);
-                        if (p.debug & 2) continue;
-                        if (CG2) {
-                            i8_mma_cg2(tmem_base, da, db0, idescA, (kb | kk) != 0);
-                            i8_mma_cg2(tmem_base + 4 * I8_N, da, db1, idescB, (kb | kk) != 0);
-                        } else {
-                            i8_mma(tmem_base, da, db0, idescA, (kb | kk) != 0);
-                            i8_mma(tmem_base + 4 * I8_N, da, db1, idescB, (kb | kk) != 0);
+                        for (int kk = 0; kk < I8_KB / 32; ++kk) {
+                            if (p.debug & 2) continue;
+                            const unsigned long long da = das + ((kk * 2 * (I8_M * 16)) >> 4);
+                            const unsigned long long dbA = dbs + ((kk * 2 * B_LBO) >> 4), dbB = dbs + ((B_SECOND + kk * 2 * B_LBO) >> 4);
+                            if (CG2) {
+                                i8_mma_cg2(tmem_base, da, dbA, idescA, (kb | kk) != 0);
+                                i8_mma_cg2(tmem_base + 4 * I8_N, da, dbB, idescB, (kb | kk) != 0);
+                            } else {
+                                i8_mma(tmem_base, da, dbA, idescA, (kb | kk) != 0);
+                                i8_mma(tmem_base + 4 * I8_N, da, dbB, idescB, (kb | kk) != 0);
+                            }
+                        }
+                        if (CG2) i8_commit_cg2(empty0 + 8 * slot, 3);     // frees the slot in BOTH CTAs when these MMAs retire
+                        else i8_commit(empty0 + 8 * slot);
+                        if (kb + 1 == nkb) {                               // accumulators of this (tile, trait) are complete
+                            if (CG2) i8_commit_cg2(accfull, 3);
+                            else i8_commit(accfull);
                         }
                     }
-                    if (CG2) i8_commit_cg2(empty0 + 8 * slot, 3);         // frees the slot in BOTH CTAs when these MMAs retire
-                    else i8_commit(empty0 + 8 * slot);                    // frees the smem slot when these MMAs retire
+                    __syncwarp();
+                    if (++slot == I8_STAGES) { slot = 0; ph ^= 1u; }
                 }
-                if (CG2) i8_commit_cg2(accfull, 3);                        // accumulators complete, in both CTAs' TMEM
-                else i8_commit(accfull);                                   // accumulators of this (tile, trait) are complete
-            }
+                ++u;
+            });
         }
     } else {
         // ------------------------------------------------------------------ epilogue: thread = one cross x one half of the columns
@@ -366,14 +386,19 @@ __global__ void __launch_bounds__(I8_THREADS, 1) i8_contract_kernel(const I8Para
                 for (int s = 0; s < TT; ++s) Z[t][s] = 0.0;
             unsigned acc_it = 0;
             for (int jt = jt_begin; jt < jt_end; ++jt) {
-                const RowTile tile = p.jtiles[jt];
-                const ChromDesc cd = p.chrom[tile.c];
-                const long long prow = (long long)cd.pad_off + 64 * tile.I;      // padded index of the tile's first row
-                // stage d_t[j] and scale_s[j] of the 64 rows in shared memory (double-buffered by tile parity)
-                double* rb = rowbuf + ((jt - jt_begin) & 1) * (2 * T * 64);
+                const long long prow = ttab[jt - jt_begin].y;                    // padded index of the tile's first row
+                // stage d_t[j] and, per (s, j), the pair (m, cm) = (2^-49 scale_s[j], -2^52 m) of the 64 rows in shared memory
+                // (double-buffered by tile parity); scale is a power of two >= 2^-900, so the pair is made with integer adds
+                double* rb = rowbuf + ((jt - jt_begin) & 1) * (3 * T * 64);
                 for (int i = etid; i < 2 * T * 64; i += 32 * I8_EPI_WARPS) {
                     const int which = i / (T * 64), rem = i - which * (T * 64), t = rem >> 6, j = rem & 63;
-                    rb[i] = __ldg((which ? p.scale : p.emat) + (long long)t * p.mp_total + prow + j);
+                    const double v = __ldg((which ? p.scale : p.emat) + (long long)t * p.mp_total + prow + j);
+                    if (!which) rb[i] = v;
+                    else {
+                        const int hi = __double2hiint(v);
+                        reinterpret_cast<double2*>(rb + T * 64)[rem] =
+                            make_double2(__hiloint2double(hi - (49 << 20), 0), __hiloint2double((hi + (3 << 20)) | (int)0x80000000, 0));
+                    }
                 }
                 unsigned nz = 0u, ng = 0u;                                       // this thread's 32 rows = one word
                 if (live) {
@@ -390,7 +415,7 @@ __global__ void __launch_bounds__(I8_THREADS, 1) i8_contract_kernel(const I8Para
                 }
                 asm volatile("bar.sync 1, %0;" ::"n"(32 * I8_EPI_WARPS) : "memory");
                 const double* erow = rb + half * 32;                 // d_t[j]:     erow[t * 64 + c]
-                const double* srow = rb + T * 64 + half * 32;        // scale_s[j]: srow[s * 64 + c]
+                const double2* mrow = reinterpret_cast<const double2*>(rb + T * 64) + half * 32;      // (m, cm): mrow[s * 64 + c]
     #pragma unroll
                 for (int s = 0; s < TT; ++s, ++acc_it) {               // unrolled: Z[t][s] must stay in registers
                     i8_mbar_wait(accfull, acc_it & 1u);
@@ -415,14 +440,9 @@ __global__ void __launch_bounds__(I8_THREADS, 1) i8_contract_kernel(const I8Para
                         const unsigned nzw = nz >> (I8_EC * cb), ngw = ng >> (I8_EC * cb);
     #pragma unroll
                         for (int c = 0; c < I8_EC; ++c) {
-                            // sum_i S_i 128^-(i+1): pairs of digits combined exactly in int32, then 4 exact int->fp64 terms
-                            const int w0 = dig[0][c] * 128 + dig[1][c], w1 = dig[2][c] * 128 + dig[3][c];
-                            const int w2 = dig[4][c] * 128 + dig[5][c], w3 = dig[6][c];
-                            double v = (double)w3 * 0x1p-49;
-                            v = fma((double)w2, 0x1p-42, v);
-                            v = fma((double)w1, 0x1p-28, v);
-                            v = fma((double)w0, 0x1p-14, v);
-                            v *= srow[s * 64 + cb * I8_EC + c];                // exact power-of-two row scale
+                            // sum_i S_i 128^(6-i) exactly as a 64-bit integer, then times 2^-49 scale: three FP64 instructions
+                            const double2 mc = mrow[s * 64 + cb * I8_EC + c];
+                            double v = v2_scaled(v2_combine(dig[0][c], dig[1][c], dig[2][c], dig[3][c], dig[4][c], dig[5][c], dig[6][c]), mc.x, mc.y);
                             long long bits = __double_as_longlong(v);
                             if (!((nzw >> c) & 1u)) bits = 0ll;
                             bits ^= (long long)((ngw >> c) & 1u) << 63;
@@ -449,14 +469,16 @@ __global__ void __launch_bounds__(I8_THREADS, 1) i8_contract_kernel(const I8Para
 #pragma unroll
                 for (int t = 0; t < TT; ++t) zs[t] = 0.0;
                 for (int jt = jt_begin; jt < jt_end; ++jt, ++acc_it) {
-                    const RowTile tile = p.jtiles[jt];
-                    const ChromDesc cd = p.chrom[tile.c];
-                    const long long prow = (long long)cd.pad_off + 64 * tile.I;
-                    double* rb = rowbuf + (acc_it & 1) * ((T + 1) * 64);           // [T][64] d_t[j], then [64] scale_s[j]
+                    const long long prow = ttab[jt - jt_begin].y;
+                    double* rb = rowbuf + (acc_it & 1) * ((T + 2) * 64);           // [T][64] d_t[j], then [64] pairs (m, cm) of trait s
                     for (int i = etid; i < (T + 1) * 64; i += 32 * I8_EPI_WARPS) {
                         const int t = i >> 6, j = i & 63;
-                        rb[i] = (t < T) ? __ldg(p.emat + (long long)t * p.mp_total + prow + j)
-                                        : __ldg(p.scale + (long long)s * p.mp_total + prow + j);
+                        if (t < T) rb[i] = __ldg(p.emat + (long long)t * p.mp_total + prow + j);
+                        else {
+                            const int hi = __double2hiint(__ldg(p.scale + (long long)s * p.mp_total + prow + j));
+                            reinterpret_cast<double2*>(rb + T * 64)[j] =
+                                make_double2(__hiloint2double(hi - (49 << 20), 0), __hiloint2double((hi + (3 << 20)) | (int)0x80000000, 0));
+                        }
                     }
                     unsigned nz = 0u, ng = 0u;
                     if (live) {
@@ -473,7 +495,7 @@ __global__ void __launch_bounds__(I8_THREADS, 1) i8_contract_kernel(const I8Para
                     }
                     asm volatile("bar.sync 1, %0;" ::"n"(32 * I8_EPI_WARPS) : "memory");
                     const double* erow = rb + half * 32;
-                    const double* srow = rb + T * 64 + half * 32;
+                    const double2* mrow = reinterpret_cast<const double2*>(rb + T * 64) + half * 32;
                     i8_mbar_wait(accfull, acc_it & 1u);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll 1
@@ -490,13 +512,8 @@ __global__ void __launch_bounds__(I8_THREADS, 1) i8_contract_kernel(const I8Para
                         const unsigned nzw = nz >> (I8_EC * cb), ngw = ng >> (I8_EC * cb);
 #pragma unroll
                         for (int c = 0; c < I8_EC; ++c) {
-                            const int w0 = dig[0][c] * 128 + dig[1][c], w1 = dig[2][c] * 128 + dig[3][c];
-                            const int w2 = dig[4][c] * 128 + dig[5][c], w3 = dig[6][c];
-                            double v = (double)w3 * 0x1p-49;
-                            v = fma((double)w2, 0x1p-42, v);
-                            v = fma((double)w1, 0x1p-28, v);
-                            v = fma((double)w0, 0x1p-14, v);
-                            v *= srow[cb * I8_EC + c];
+                            const double2 mc = mrow[cb * I8_EC + c];
+                            double v = v2_scaled(v2_combine(dig[0][c], dig[1][c], dig[2][c], dig[3][c], dig[4][c], dig[5][c], dig[6][c]), mc.x, mc.y);
                             long long bits = __double_as_longlong(v);
                             if (!((nzw >> c) & 1u)) bits = 0ll;
                             bits ^= (long long)((ngw >> c) & 1u) << 63;
@@ -527,9 +544,9 @@ __global__ void __launch_bounds__(I8_THREADS, 1) i8_contract_kernel(const I8Para
 }
 
 size_t i8_smem_bytes(int T, bool cg2) {
-    const int rows = T <= 6 ? 2 * T : T + 1;          // per buffer: d_t[j] rows + scale rows (see the two epilogues)
+    const int rows = T <= 6 ? 3 * T : T + 2;          // per buffer: d_t[j] rows + (m, cm) pair rows (see the two epilogues)
     const size_t stages = cg2 ? (size_t)I8Geo<true>::STAGES * I8Geo<true>::STAGE_BYTES : (size_t)I8Geo<false>::STAGES * I8Geo<false>::STAGE_BYTES;
-    return stages + (2 * I8_MAX_STAGES + 4) * 8 + (size_t)2 * rows * 64 * 8;
+    return stages + (2 * I8_MAX_STAGES + 4) * 8 + (size_t)I8_TTAB * 16 + (size_t)2 * rows * 64 * 8;
 }
 
 cudaError_t launch_i8_build_xi(const unsigned* planeA, const unsigned* planeB, long long wpp, const int* sire,

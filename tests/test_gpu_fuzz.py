@@ -105,11 +105,22 @@ def test_one_engine_many_calls():
     eng.close()
 
 
-def test_int8_cta_group2_variant(monkeypatch):
-    """GMS_I8_CG2=1: tcgen05 cta_group::2 - CTA pairs form one M = 256 tile, each CTA stages half of the digit operand."""
+@pytest.mark.parametrize("env", [
+    {"GMS_I8_CG2": "0"},                                            # one CTA per 128 crosses
+    {"GMS_I8_CG2": "1"},                                            # the default: tcgen05 cta_group::2 pairs (M = 256)
+    {"GMS_I8_V2": "1", "GMS_I8_IA": "0"},                           # i8v2.cu, FP64 burst in an MMA gap, xi multicast
+    {"GMS_I8_V2": "1", "GMS_I8_IA": "0", "GMS_I8_MC": "0"},         # the same without clusters
+    {"GMS_I8_V2": "1", "GMS_I8_IA": "1"},                           # i8v2.cu, exact integer accumulation
+], ids=["plain", "cta_group2", "v2_fp64", "v2_fp64_nomc", "v2_int"])
+@pytest.mark.parametrize("T", [1, 3, 5, 7])
+def test_int8_kernel_variants(monkeypatch, env, T):
+    """Every variant of the int8 tcgen05 kernel (environment switches read at gms_create) against the oracle: the default
+    (cta_group::2 pairs, each CTA staging half of the digit operand), the single-CTA kernel, and the opt-in second-generation
+    kernel (32-row tiles, two TMEM accumulators) in its FP64 and integer-accumulating forms."""
     import genomicmateselectr_b200 as g
-    monkeypatch.setenv("GMS_I8_CG2", "1")
-    m_c, cM, chrom, H, add, dom, asub, R = make(9, [200, 131, 77], 10, 5)
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    m_c, cM, chrom, H, add, dom, asub, R = make(9 + T, [200, 131, 77], 10, T)
     rng = np.random.default_rng(2)
     sire = rng.integers(0, 10, 300).astype(np.int32)
     dam = rng.integers(0, 10, 300).astype(np.int32)
@@ -117,8 +128,8 @@ def test_int8_cta_group2_variant(monkeypatch):
         eng.set_genmap(cM, m_c)
         eng.set_haplotypes(H)
         eng.set_mode("int8_tensor")
-        out, nseg = eng.predict("AD", add, dom, None, sire, dam)
-    want, wseg = oracle_slab("AD", H, R, add, dom, None, sire, dam)
+        out, nseg = eng.predict("DirDom", add, dom, asub, sire, dam)
+    want, wseg = oracle_slab("DirDom", H, R, add, dom, asub, sire, dam)
     assert np.array_equal(nseg, wseg) and rel_err(out, want) < 1e-9
 
 
