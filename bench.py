@@ -41,7 +41,7 @@ def parse():
     ap.add_argument("--workload", default="cassava", choices=["cassava", "large", "mini"])
     ap.add_argument("--crosses-per-gpu", type=int, default=None, help="default: the workload's N on every GPU")
     ap.add_argument("--model", default="AD", choices=["A", "AD", "DirDom"])
-    ap.add_argument("--cpu-sample", type=int, default=2, help="crosses per CPU-baseline step")
+    ap.add_argument("--cpu-sample", type=int, default=8, help="crosses per CPU-baseline step (3 steps, ~20 s on 16 cores)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
 
@@ -382,7 +382,7 @@ def main():
         ach = alg / (r["kernel_ms"] * 1e-3) / 1e12
         return {"bound": "tensor", "kernel": "i8_contract_kernel (tcgen05.mma kind::i8, int32 accumulators in TMEM, cp.async.bulk staged)",
                 "achieved": ach, "peak": int8_peak, "unit": "TFLOP/s", "op_type": "int8 multiply-add = 2 ops",
-                "frac": ach / int8_peak, "traffic": None,
+                "frac": ach / int8_peak, "traffic": traffic_i8,
                 "peak_source": "cuBLASLt int8 GEMM 8192^3 (torch._int_mm) measured in this run; nominal dense int8 4500",
                 "algorithmic_flops_per_launch": alg, "executed_flops_per_launch": exe,
                 "executed_tflops": exe / (r["kernel_ms"] * 1e-3) / 1e12,
@@ -392,11 +392,14 @@ def main():
                         "block x T traits x crosses; executed adds 64-granular block and 128-cross tile padding",
                 "kernel_ms": r["kernel_ms"], "kernel_share_of_step": r["kernel_ms"] / r["step_ms_sync"]}
 
-    traffic = None          # DRAM bytes per launch of the FP64 kernel, from the committed ncu capture of this config
+    # DRAM bytes per launch of the two contraction kernels, from the committed `ncu --set full` captures of this config
+    traffic = traffic_i8 = None
     try:
         tr = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
         if (tr["workload"], tr["crosses_per_gpu"], tr["model"]) == (args.workload, n_per, args.model):
             traffic = tr["dram_bytes_read"] + tr["dram_bytes_write"]
+            if "int8" in tr:
+                traffic_i8 = tr["int8"]["dram_bytes_read"] + tr["int8"]["dram_bytes_write"]
     except Exception:
         pass
 

@@ -788,7 +788,7 @@ int gms_compute(gms_handle* h, int sync) {
             CU(cudaMemsetAsync(sc.p, 0, sizeof(double) * h->mp_total * T, h->stream));
             CU(launch_i8_build_digits(tiles, h->chrom_d.p, h->c_begin, h->c_end, h->i8_rowpref_d.p, h->i8_nrows, h->i8_blkpref_d.p,
                                       h->i8_nblks, emat, h->mp_total, T, sc.p, h->gbase_d.p, G.p, h->i8_v2 ? 2 : (h->i8_pair ? 1 : 0), h->stream));
-            h->st.last_launches += 2;
+            h->st.last_launches += 3;
             if (ia) {
                 CU(launch_i8_build_qtab(emat, sc.p, h->mp_total, T, ge.p, qt.p, h->stream));
                 h->st.last_launches += 2;

@@ -34,7 +34,7 @@ template <bool CG2> struct I8Geo {
     static constexpr int STAGE_BYTES = I8_A_BYTES + B_STAGE;           // 36 KiB / 22 KiB
     static constexpr int STAGES = CG2 ? 8 : 5;                         // 180 KiB / 176 KiB
 };
-constexpr int I8_MAX_STAGES = 8;
+constexpr int I8_MAX_STAGES = 10;
 constexpr int I8_TTAB = 512;        // 64-row tiles per split that fit the shared-memory copy of the work list (the host plan keeps splits below it)
 constexpr int I8_EPI_WARPS = 8;     // two per TMEM lane quarter: each takes 32 of the 64 accumulator columns
 constexpr int I8_THREADS = 32 * (I8_EPI_WARPS + 2);
@@ -104,45 +104,54 @@ __device__ __forceinline__ double lprime64(const double* __restrict__ tiles, con
     return v;
 }
 
-// scale[s][pj] = 2^E with |G_s[j,k]| < 2^E for every k of row j's lower-triangle range (1 if the row is zero).
-// One block per row; every L' element is read ONCE and used for all T traits.
-__global__ void i8_rowscale_kernel(const double* __restrict__ tiles, const ChromDesc* __restrict__ chrom, int c_begin,
-                                   int c_end, const int* __restrict__ rowpref, const double* __restrict__ emat,
-                                   long long mp_total, int T, double* __restrict__ scale) {
+// Row scales, two steps. (1) rowmax[s][pj] = max_k |G_s[j,k]| over row j's lower-triangle range: one CTA per 64 x 64 block
+// with the digit builder's access pattern (every L' element read once, coalesced, used for all T traits), reduced in shared
+// memory and merged with an atomic max on the bit pattern (non-negative doubles order like unsigned integers; the buffer
+// starts at zero). (2) scale = 2^E with rowmax < 2^E (1 for a zero row; a row below 2^-900 counts as zero), in place.
+__global__ void i8_rowmax_kernel(const double* __restrict__ tiles, const ChromDesc* __restrict__ chrom, int c_begin, int c_end,
+                                 const int* __restrict__ blkpref, const double* __restrict__ emat, long long mp_total, int T,
+                                 unsigned long long* __restrict__ rowmax) {
     int c = c_begin;
-    while (c + 1 < c_end && (int)blockIdx.x >= rowpref[c + 1]) ++c;     // rowpref[c] = first block of chromosome c
+    while (c + 1 < c_end && (int)blockIdx.x >= blkpref[c + 1]) ++c;
     const ChromDesc cd = chrom[c];
-    const int row = blockIdx.x - rowpref[c];           // local row (< roundup(m,64))
-    const int kend = min(cd.m, ((row >> 6) + 1) << 6);
-    double mx[MAX_T];
+    const int blk = blockIdx.x - blkpref[c];
+    int J = (int)((sqrt(8.0 * blk + 1.0) - 1.0) * 0.5);
+    while ((J + 1) * (J + 2) / 2 <= blk) ++J;
+    while (J * (J + 1) / 2 > blk) --J;
+    const int kb = blk - J * (J + 1) / 2;
+    const int r = threadIdx.x & 63, cc = threadIdx.x >> 6;      // 256 threads: 64 rows x 4 chunks of 16 columns
+    const int row = J * 64 + r;
+    __shared__ unsigned long long sh[64][MAX_T];
+    for (int i = threadIdx.x; i < 64 * MAX_T; i += blockDim.x) (&sh[0][0])[i] = 0ull;
+    __syncthreads();
+    if (row < cd.m) {
+        double lp[16];
 #pragma unroll
-    for (int s = 0; s < MAX_T; ++s) mx[s] = 0.0;
-    if (row < cd.m)
-        for (int k = threadIdx.x; k < kend; k += blockDim.x) {
-            const double l = fabs(lprime64(tiles, cd, row, k));
-            const double* e = emat + cd.pad_off + k;
-#pragma unroll
-            for (int s = 0; s < MAX_T; ++s)
-                if (s < T) mx[s] = fmax(mx[s], l * fabs(e[(long long)s * mp_total]));
+        for (int b = 0; b < 16; ++b) {
+            const int col = kb * 64 + cc * 16 + b;
+            lp[b] = col < cd.m ? fabs(lprime64(tiles, cd, row, col)) : 0.0;
         }
-    __shared__ double sh[4][MAX_T];
+        const double* ecol = emat + cd.pad_off + kb * 64 + cc * 16;
+        for (int s = 0; s < T; ++s) {
+            double mx = 0.0;
 #pragma unroll
-    for (int s = 0; s < MAX_T; ++s) {
-        if (s < T) {
-            double v = mx[s];
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
-            if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5][s] = v;
+            for (int b = 0; b < 16; ++b) mx = fmax(mx, lp[b] * fabs(ecol[(long long)s * mp_total + b]));
+            atomicMax(&sh[r][s], (unsigned long long)__double_as_longlong(mx));
         }
     }
     __syncthreads();
-    if (threadIdx.x < T) {
-        double v = 0.0;
-        for (int i = 0; i < (int)(blockDim.x >> 5); ++i) v = fmax(v, sh[i][threadIdx.x]);
-        int e = 0;
-        if (v > 0x1p-900) { (void)frexp(v, &e); }       // v = f * 2^e, f in [0.5, 1)  =>  v < 2^e; a row below 2^-900 counts as zero
-        scale[(long long)threadIdx.x * mp_total + cd.pad_off + row] = ldexp(1.0, e);
+    for (int i = threadIdx.x; i < 64 * T; i += blockDim.x) {
+        const int rr = i % 64, s = i / 64;
+        if (J * 64 + rr < cd.m && sh[rr][s]) atomicMax(rowmax + (long long)s * mp_total + cd.pad_off + J * 64 + rr, sh[rr][s]);
     }
+}
+__global__ void i8_scale_kernel(double* __restrict__ scale, long long n) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double v = scale[i];
+    int e = 0;
+    if (v > 0x1p-900) (void)frexp(v, &e);           // v = f * 2^e, f in [0.5, 1)  =>  v < 2^e
+    scale[i] = ldexp(1.0, e);
 }
 
 // digit images: (c, J, kb <= J, s): one 448-row K-major operand per (block, trait); one thread = 16 consecutive k of a
@@ -231,7 +240,8 @@ __global__ void __launch_bounds__(I8_THREADS, 1) i8_contract_kernel(const I8Para
     const int T = SOUTER ? p.T : TT;
     extern __shared__ __align__(1024) unsigned char smem[];
     unsigned char* stage0 = smem;
-    constexpr int I8_STAGES = I8Geo<CG2>::STAGES, I8_STAGE_BYTES = I8Geo<CG2>::STAGE_BYTES, B_STAGE = I8Geo<CG2>::B_STAGE;
+    constexpr int I8_STAGE_BYTES = I8Geo<CG2>::STAGE_BYTES, B_STAGE = I8Geo<CG2>::B_STAGE;
+    const int I8_STAGES = p.stages;          // as many as fit next to the work list and the row data (i8_stages)
     unsigned long long* bars = reinterpret_cast<unsigned long long*>(smem + I8_STAGES * I8_STAGE_BYTES);
     unsigned* tmem_slot = reinterpret_cast<unsigned*>(bars + 2 * I8_MAX_STAGES + 2);
     int4* ttab = reinterpret_cast<int4*>(bars + 2 * I8_MAX_STAGES + 4);        // this CTA's range of the 64-row tile list (I8_TTAB entries)
@@ -543,10 +553,18 @@ __global__ void __launch_bounds__(I8_THREADS, 1) i8_contract_kernel(const I8Para
     }
 }
 
-size_t i8_smem_bytes(int T, bool cg2) {
+static size_t i8_fixed_smem(int T) {
     const int rows = T <= 6 ? 3 * T : T + 2;          // per buffer: d_t[j] rows + (m, cm) pair rows (see the two epilogues)
-    const size_t stages = cg2 ? (size_t)I8Geo<true>::STAGES * I8Geo<true>::STAGE_BYTES : (size_t)I8Geo<false>::STAGES * I8Geo<false>::STAGE_BYTES;
-    return stages + (2 * I8_MAX_STAGES + 4) * 8 + (size_t)I8_TTAB * 16 + (size_t)2 * rows * 64 * 8;
+    return (2 * I8_MAX_STAGES + 4) * 8 + (size_t)I8_TTAB * 16 + (size_t)2 * rows * 64 * 8;
+}
+// pipeline stages: as many as fit in the 227 KiB a CTA may use (the kernel is bound by the latency of its operand stream)
+int i8_stages(int T, bool cg2) {
+    const size_t stage = cg2 ? I8Geo<true>::STAGE_BYTES : I8Geo<false>::STAGE_BYTES;
+    const int n = (int)((232448 - i8_fixed_smem(T)) / stage);
+    return n < 2 ? 2 : (n > I8_MAX_STAGES ? I8_MAX_STAGES : n);
+}
+size_t i8_smem_bytes(int T, bool cg2) {
+    return (size_t)i8_stages(T, cg2) * (cg2 ? I8Geo<true>::STAGE_BYTES : I8Geo<false>::STAGE_BYTES) + i8_fixed_smem(T);
 }
 
 cudaError_t launch_i8_build_xi(const unsigned* planeA, const unsigned* planeB, long long wpp, const int* sire,
@@ -565,7 +583,9 @@ cudaError_t launch_i8_build_digits(const double* tiles, const ChromDesc* chrom_d
                                    long long mp_total, int T, double* scale, const long long* gbase_d, signed char* G,
                                    int layout, cudaStream_t st) {
     if (nrows == 0) return cudaSuccess;
-    i8_rowscale_kernel<<<nrows, 128, 0, st>>>(tiles, chrom_d, c_begin, c_end, rowpref_d, emat, mp_total, T, scale);
+    // `scale` arrives zeroed (cudaMemsetAsync in gms_compute)
+    i8_rowmax_kernel<<<nblks, 256, 0, st>>>(tiles, chrom_d, c_begin, c_end, blkpref_d, emat, mp_total, T, reinterpret_cast<unsigned long long*>(scale));
+    i8_scale_kernel<<<(unsigned)(((long long)T * mp_total + 255) / 256), 256, 0, st>>>(scale, (long long)T * mp_total);
     i8_build_digits_kernel<<<nblks, 256, 0, st>>>(tiles, chrom_d, c_begin, c_end, blkpref_d, emat, mp_total, T, scale, gbase_d, G, layout);
     return cudaGetLastError();
 }
@@ -573,6 +593,8 @@ cudaError_t launch_i8_build_digits(const double* tiles, const ChromDesc* chrom_d
 cudaError_t launch_i8_contract(const I8Params& p, int ntiles, int nsplit, bool pair, cudaStream_t st) {
     if (ntiles == 0) return cudaSuccess;
     const size_t smem = i8_smem_bytes(p.T, pair);
+    I8Params pp = p;
+    pp.stages = i8_stages(p.T, pair);
     cudaError_t e = cudaSuccess;
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(pair ? (ntiles + 1) / 2 * 2 : ntiles, nsplit, 1);
@@ -588,7 +610,7 @@ cudaError_t launch_i8_contract(const I8Params& p, int ntiles, int nsplit, bool p
     {                                                                                                                      \
         e = cudaFuncSetAttribute(i8_contract_kernel<TV, SO, PR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);  \
         if (e != cudaSuccess) return e;                                                                                    \
-        e = cudaLaunchKernelEx(&cfg, i8_contract_kernel<TV, SO, PR>, p);                                                   \
+        e = cudaLaunchKernelEx(&cfg, i8_contract_kernel<TV, SO, PR>, pp);                                                  \
         if (e != cudaSuccess) return e;                                                                                    \
     }
 #define GMS_I8(TV, SO) { if (pair) GMS_I8_ONE(TV, SO, true) else GMS_I8_ONE(TV, SO, false) }

@@ -65,6 +65,7 @@ struct I8Params {
     int T;
     int mode;
     double* Zpart;               // [nsplit][n_units][T*T]
+    int stages;                  // i8path.cu: pipeline depth (set by launch_i8_contract)
     const int4* qtab;            // i8v2 integer accumulation: [trait s][mp_total][trait t] fixed-point weights (q0, q1, q2, -)
     const int* gexp;             // [T x T] their exponents
     int debug;                   // profiling only (GMS_I8_DEBUG): 1 = no epilogue arithmetic, 2 = no MMAs, 4 = no loads (i8v2); results are garbage
