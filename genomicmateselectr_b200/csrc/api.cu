@@ -631,7 +631,7 @@ int gms_stage_inputs(gms_handle* h, int model, int T, const double* add, const d
     if (h->eff_mode == GMS_MODE_INT8_TENSOR && !i8_ok) h->eff_mode = GMS_MODE_DENSE;
     h->use_i8 = h->eff_mode == GMS_MODE_INT8_TENSOR;
     h->i8_v2 = h->use_i8 && h->i8_v2_ok && T <= 16;
-    const size_t npart = h->i8_v2 ? (size_t)i8v2_npart(h->i8_mc) : 2;     // partial slabs per split written by the int8 kernel
+    const size_t npart = h->i8_v2 ? (size_t)i8v2_npart(h->i8_mc) : (size_t)i8_npart(T);     // partial slabs per split written by the int8 kernel
 
     size_t zneed = 0;
     if (h->eff_mode == GMS_MODE_MAP_SCAN) {
@@ -710,20 +710,29 @@ int gms_stage_inputs(gms_handle* h, int model, int T, const double* add, const d
                     if (cost < best - 1e-12) { best = cost; ns = cand; }
                 }
             }
-            ns = std::max(ns, (njt + i8v2_max_tiles_per_split() - 1) / i8v2_max_tiles_per_split());     // the kernels' shared-memory work list
+            const int cap = i8v2_max_tiles_per_split();       // the kernels keep their range of the work list in shared memory
+            ns = std::max(ns, (njt + cap - 1) / cap);
             ns = std::max(1, std::min(ns, njt));
-            pl.nsplit = ns;
-            pl.split_begin.assign(ns + 1, 0);
-            double total = 0, acc = 0;
+            double total = 0;
             for (const RowTile& r : h->jtiles) total += r.I + 1;
-            int sp = 1;
-            for (int i = 0; i < njt && sp < ns; ++i) {
-                acc += h->jtiles[i].I + 1;
-                while (sp < ns && acc >= total * sp / ns && (njt - (i + 1)) >= (ns - sp)) pl.split_begin[sp++] = i + 1;
+            for (;; ++ns) {                                    // equal-work ranges; more of them until every range fits `cap`
+                pl.nsplit = ns;
+                pl.split_begin.assign(ns + 1, 0);
+                double acc = 0;
+                int sp = 1;
+                for (int i = 0; i < njt && sp < ns; ++i) {
+                    acc += h->jtiles[i].I + 1;
+                    while (sp < ns && acc >= total * sp / ns && (njt - (i + 1)) >= (ns - sp)) pl.split_begin[sp++] = i + 1;
+                }
+                for (; sp < ns; ++sp) pl.split_begin[sp] = std::max(pl.split_begin[sp - 1], njt - (ns - sp));
+                pl.split_begin[ns] = njt;
+                int longest = 0;
+                for (int i = 1; i <= ns; ++i) {
+                    pl.split_begin[i] = std::max(pl.split_begin[i], pl.split_begin[i - 1]);
+                    longest = std::max(longest, pl.split_begin[i] - pl.split_begin[i - 1]);
+                }
+                if (longest <= cap || ns >= njt) break;
             }
-            for (; sp < ns; ++sp) pl.split_begin[sp] = std::max(pl.split_begin[sp - 1], njt - (ns - sp));
-            pl.split_begin[ns] = njt;
-            for (int i = 1; i <= ns; ++i) pl.split_begin[i] = std::max(pl.split_begin[i], pl.split_begin[i - 1]);
             CU(dev.ensure(pl.split_begin.size()));
             CU(cudaMemcpyAsync(dev.p, pl.split_begin.data(), sizeof(int) * pl.split_begin.size(), cudaMemcpyHostToDevice, h->stream));
             return GMS_OK;
@@ -838,7 +847,7 @@ int gms_compute(gms_handle* h, int sync) {
             if (h->i8_v2) CU(launch_i8v2_contract(ip, pl.ntiles, pl.nsplit, h->i8_mc, ia, h->stream));
             else CU(launch_i8_contract(ip, pl.ntiles, pl.nsplit, h->i8_pair, h->stream));
             if (e1) CU(cudaEventRecord(e1, h->stream));
-            CU(launch_finalize_sym(h->Z.p, (h->i8_v2 ? i8v2_npart(h->i8_mc) : 2) * pl.nsplit, n_units, h->T, Xout, h->stream, true));
+            CU(launch_finalize_sym(h->Z.p, (h->i8_v2 ? i8v2_npart(h->i8_mc) : i8_npart(h->T)) * pl.nsplit, n_units, h->T, Xout, h->stream, true));
             h->st.last_launches += 2;
             return GMS_OK;
         };

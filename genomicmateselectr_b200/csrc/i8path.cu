@@ -36,8 +36,8 @@ template <bool CG2> struct I8Geo {
 };
 constexpr int I8_MAX_STAGES = 10;
 constexpr int I8_TTAB = 512;        // 64-row tiles per split that fit the shared-memory copy of the work list (the host plan keeps splits below it)
-constexpr int I8_EPI_WARPS = 8;     // two per TMEM lane quarter: each takes 32 of the 64 accumulator columns
-constexpr int I8_THREADS = 32 * (I8_EPI_WARPS + 2);
+// epilogue warps EW (template parameter, 8 or 16): EW / 4 per TMEM lane quarter, each takes 256 / EW of the 64 SNP rows of a
+// tile. 8 everywhere: with 16 a 576-thread CTA gets 96 registers per thread and the kernel is 13 % slower (measured, T = 5)
 
 // ------------------------------------------------------------------------------------------ prep: xi images
 // image (X tile, global k-block) : [chunk cc (4)][r1 (16)][r0 (8)][16 bytes], row r = 8 r1 + r0, k = 16 cc + b
@@ -222,11 +222,15 @@ __global__ void i8_build_digits_kernel(const double* __restrict__ tiles, const C
 }
 
 // ------------------------------------------------------------------------------------------ main kernel
-constexpr int I8_EC = 8;             // accumulator columns per tcgen05.ld (x8) in the epilogue
-__device__ __forceinline__ void i8_tmem_ldc(unsigned taddr, int (&v)[I8_EC]) {
+// accumulator columns per tcgen05.ld in the epilogue: x8, or x4 with 16 epilogue warps (registers)
+__device__ __forceinline__ void i8_tmem_ldc(unsigned taddr, int (&v)[8]) {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                  : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
                  : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void i8_tmem_ldc(unsigned taddr, int (&v)[4]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]) : "r"(taddr) : "memory");
 }
 
 // TT = T (SOUTER = false, T <= 6: loop "64-row tile outer, trait s inner", the cross's whole T x T table in registers)
@@ -235,8 +239,11 @@ __device__ __forceinline__ void i8_tmem_ldc(unsigned taddr, int (&v)[I8_EC]) {
 // Each CTA stages its own xi tile and only HALF of every digit tile; the leader CTA's MMA thread issues the pair's MMAs once
 // both halves have landed (the peer relays its `full` phases to the leader), and its commits release the slot / publish the
 // accumulators in BOTH CTAs. This halves the shared-memory traffic per MAC, which is what bounds the single-CTA kernel.
-template <int TT, bool SOUTER, bool CG2>
-__global__ void __launch_bounds__(I8_THREADS, 1) i8_contract_kernel(const I8Params p) {
+template <int TT, bool SOUTER, bool CG2, int EW>
+__global__ void __launch_bounds__(32 * (EW + 2), 1) i8_contract_kernel(const I8Params p) {
+    constexpr int I8_EPI_WARPS = EW, I8_THREADS = 32 * (EW + 2);
+    constexpr int RPT = 256 / EW;                    // SNP rows per epilogue thread and tile
+    constexpr int I8_EC = EW == 8 ? 8 : 4;
     const int T = SOUTER ? p.T : TT;
     extern __shared__ __align__(1024) unsigned char smem[];
     unsigned char* stage0 = smem;
@@ -381,13 +388,13 @@ __global__ void __launch_bounds__(I8_THREADS, 1) i8_contract_kernel(const I8Para
         }
     } else {
         // ------------------------------------------------------------------ epilogue: thread = one cross x one half of the columns
-        const int quarter = warp & 3, half = warp >> 2;       // TMEM lane quarter is fixed by warp id % 4
+        const int quarter = warp & 3, half = warp >> 2;       // TMEM lane quarter is fixed by warp id % 4; `half`: column group
         const int etid = threadIdx.x;                          // 0 .. 255
         const long long unit = X * I8_M + quarter * 32 + lane;
         const bool live = unit < p.n_units;
         int pa = 0, pb = 0;
         if (live) { pa = p.unit_a[unit]; pb = (p.mode == MASK_XI) ? p.unit_b[unit] : 0; }
-        const unsigned tlane = tmem_base + ((unsigned)(quarter * 32) << 16) + half * 32;
+        const unsigned tlane = tmem_base + ((unsigned)(quarter * 32) << 16) + half * RPT;
         if constexpr (!SOUTER) {
             double Z[TT][TT];
     #pragma unroll
@@ -410,9 +417,9 @@ __global__ void __launch_bounds__(I8_THREADS, 1) i8_contract_kernel(const I8Para
                             make_double2(__hiloint2double(hi - (49 << 20), 0), __hiloint2double((hi + (3 << 20)) | (int)0x80000000, 0));
                     }
                 }
-                unsigned nz = 0u, ng = 0u;                                       // this thread's 32 rows = one word
+                unsigned nz = 0u, ng = 0u;                                       // this thread's RPT rows: (part of) one word
                 if (live) {
-                    const long long wi = (prow >> 5) + half;
+                    const long long wi = (prow >> 5) + (half * RPT) / 32;
                     const unsigned A = __ldg(p.planeA + (long long)pa * p.wpp + wi), B = __ldg(p.planeB + (long long)pa * p.wpp + wi);
                     if (p.mode == MASK_XI) {
                         const unsigned A2 = __ldg(p.planeA + (long long)pb * p.wpp + wi), B2 = __ldg(p.planeB + (long long)pb * p.wpp + wi);
@@ -423,9 +430,10 @@ __global__ void __launch_bounds__(I8_THREADS, 1) i8_contract_kernel(const I8Para
                         ng = (p.mode == MASK_DELTA) ? (~A & B) : 0u;
                     }
                 }
+                if (RPT < 32) { nz >>= (half * RPT) % 32; ng >>= (half * RPT) % 32; }
                 asm volatile("bar.sync 1, %0;" ::"n"(32 * I8_EPI_WARPS) : "memory");
-                const double* erow = rb + half * 32;                 // d_t[j]:     erow[t * 64 + c]
-                const double2* mrow = reinterpret_cast<const double2*>(rb + T * 64) + half * 32;      // (m, cm): mrow[s * 64 + c]
+                const double* erow = rb + half * RPT;                // d_t[j]:     erow[t * 64 + c]
+                const double2* mrow = reinterpret_cast<const double2*>(rb + T * 64) + half * RPT;     // (m, cm): mrow[s * 64 + c]
     #pragma unroll
                 for (int s = 0; s < TT; ++s, ++acc_it) {               // unrolled: Z[t][s] must stay in registers
                     i8_mbar_wait(accfull, acc_it & 1u);
@@ -437,12 +445,12 @@ __global__ void __launch_bounds__(I8_THREADS, 1) i8_contract_kernel(const I8Para
                         continue;
                     }
     #pragma unroll 1
-                    for (int cb = 0; cb < 32 / I8_EC; ++cb) {                        // I8_EC SNP rows at a time
+                    for (int cb = 0; cb < RPT / I8_EC; ++cb) {                       // I8_EC SNP rows at a time
                         int dig[I8_DIG][I8_EC];
     #pragma unroll
                         for (int i = 0; i < I8_DIG; ++i) i8_tmem_ldc(tlane + i * I8_N + cb * I8_EC, dig[i]);
                         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                        if (cb == 32 / I8_EC - 1) {                                               // TMEM fully read: next trait's MMAs may start
+                        if (cb == RPT / I8_EC - 1 && !(p.debug & 512)) {                          // TMEM fully read: next trait's MMAs may start
                             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                             __syncwarp();
                             if (lane == 0) { if (CG2) i8_mbar_arrive_remote(accempty, 0); else i8_mbar_arrive(accempty); }
@@ -461,11 +469,16 @@ __global__ void __launch_bounds__(I8_THREADS, 1) i8_contract_kernel(const I8Para
                             for (int t = 0; t < TT; ++t) Z[t][s] = fma(erow[t * 64 + cb * I8_EC + c], v, Z[t][s]);
                         }
                     }
+                    if (p.debug & 512) {       // profiling: release the accumulator only after ALL the FP64 work of the unit
+                        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                        __syncwarp();
+                        if (lane == 0) { if (CG2) i8_mbar_arrive_remote(accempty, 0); else i8_mbar_arrive(accempty); }
+                    }
                 }
             }
             if (live) {
                 // the two column halves of a cross go to two partial slabs (summed by finalize_sym)
-                double* out = p.Zpart + ((long long)(split * 2 + half) * p.n_units + unit) * (T * T);
+                double* out = p.Zpart + ((long long)(split * (EW / 4) + half) * p.n_units + unit) * (T * T);
     #pragma unroll
                 for (int t = 0; t < TT; ++t)
     #pragma unroll
@@ -492,7 +505,7 @@ __global__ void __launch_bounds__(I8_THREADS, 1) i8_contract_kernel(const I8Para
                     }
                     unsigned nz = 0u, ng = 0u;
                     if (live) {
-                        const long long wi = (prow >> 5) + half;
+                        const long long wi = (prow >> 5) + (half * RPT) / 32;
                         const unsigned A = __ldg(p.planeA + (long long)pa * p.wpp + wi), B = __ldg(p.planeB + (long long)pa * p.wpp + wi);
                         if (p.mode == MASK_XI) {
                             const unsigned A2 = __ldg(p.planeA + (long long)pb * p.wpp + wi), B2 = __ldg(p.planeB + (long long)pb * p.wpp + wi);
@@ -503,18 +516,19 @@ __global__ void __launch_bounds__(I8_THREADS, 1) i8_contract_kernel(const I8Para
                             ng = (p.mode == MASK_DELTA) ? (~A & B) : 0u;
                         }
                     }
+                    if (RPT < 32) { nz >>= (half * RPT) % 32; ng >>= (half * RPT) % 32; }
                     asm volatile("bar.sync 1, %0;" ::"n"(32 * I8_EPI_WARPS) : "memory");
-                    const double* erow = rb + half * 32;
-                    const double2* mrow = reinterpret_cast<const double2*>(rb + T * 64) + half * 32;
+                    const double* erow = rb + half * RPT;
+                    const double2* mrow = reinterpret_cast<const double2*>(rb + T * 64) + half * RPT;
                     i8_mbar_wait(accfull, acc_it & 1u);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll 1
-                    for (int cb = 0; cb < 32 / I8_EC; ++cb) {
+                    for (int cb = 0; cb < RPT / I8_EC; ++cb) {
                         int dig[I8_DIG][I8_EC];
 #pragma unroll
                         for (int i = 0; i < I8_DIG; ++i) i8_tmem_ldc(tlane + i * I8_N + cb * I8_EC, dig[i]);
                         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                        if (cb == 32 / I8_EC - 1) {
+                        if (cb == RPT / I8_EC - 1) {
                             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                             __syncwarp();
                             if (lane == 0) { if (CG2) i8_mbar_arrive_remote(accempty, 0); else i8_mbar_arrive(accempty); }
@@ -535,7 +549,7 @@ __global__ void __launch_bounds__(I8_THREADS, 1) i8_contract_kernel(const I8Para
                     }
                 }
                 if (live) {
-                    double* out = p.Zpart + ((long long)(split * 2 + half) * p.n_units + unit) * (T * T);
+                    double* out = p.Zpart + ((long long)(split * (EW / 4) + half) * p.n_units + unit) * (T * T);
 #pragma unroll
                     for (int t = 0; t < TT; ++t)
                         if (t < T) out[t * T + s] = zs[t];
@@ -553,6 +567,9 @@ __global__ void __launch_bounds__(I8_THREADS, 1) i8_contract_kernel(const I8Para
     }
 }
 
+// epilogue warps for T traits (see the kernel)
+int i8_epi_warps(int T) { (void)T; return 8; }    // 16 (96 registers per thread, x4 TMEM loads) measured 13 % slower at T = 5
+int i8_npart(int T) { return i8_epi_warps(T) / 4; }       // partial slabs per split: one per column group
 static size_t i8_fixed_smem(int T) {
     const int rows = T <= 6 ? 3 * T : T + 2;          // per buffer: d_t[j] rows + (m, cm) pair rows (see the two epilogues)
     return (2 * I8_MAX_STAGES + 4) * 8 + (size_t)I8_TTAB * 16 + (size_t)2 * rows * 64 * 8;
@@ -598,7 +615,7 @@ cudaError_t launch_i8_contract(const I8Params& p, int ntiles, int nsplit, bool p
     cudaError_t e = cudaSuccess;
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(pair ? (ntiles + 1) / 2 * 2 : ntiles, nsplit, 1);
-    cfg.blockDim = dim3(I8_THREADS, 1, 1);
+    cfg.blockDim = dim3(32 * (i8_epi_warps(p.T) + 2), 1, 1);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
@@ -606,27 +623,27 @@ cudaError_t launch_i8_contract(const I8Params& p, int ntiles, int nsplit, bool p
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = pair ? 1 : 0;
-#define GMS_I8_ONE(TV, SO, PR)                                                                                             \
-    {                                                                                                                      \
-        e = cudaFuncSetAttribute(i8_contract_kernel<TV, SO, PR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);  \
-        if (e != cudaSuccess) return e;                                                                                    \
-        e = cudaLaunchKernelEx(&cfg, i8_contract_kernel<TV, SO, PR>, pp);                                                  \
-        if (e != cudaSuccess) return e;                                                                                    \
+#define GMS_I8_ONE(TV, SO, PR, EWV)                                                                                             \
+    {                                                                                                                           \
+        e = cudaFuncSetAttribute(i8_contract_kernel<TV, SO, PR, EWV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);  \
+        if (e != cudaSuccess) return e;                                                                                         \
+        e = cudaLaunchKernelEx(&cfg, i8_contract_kernel<TV, SO, PR, EWV>, pp);                                                  \
+        if (e != cudaSuccess) return e;                                                                                         \
     }
-#define GMS_I8(TV, SO) { if (pair) GMS_I8_ONE(TV, SO, true) else GMS_I8_ONE(TV, SO, false) }
+#define GMS_I8(TV, SO, EWV) { if (pair) GMS_I8_ONE(TV, SO, true, EWV) else GMS_I8_ONE(TV, SO, false, EWV) }
     switch (p.T) {
-        case 1: GMS_I8(1, false) break;
-        case 2: GMS_I8(2, false) break;
-        case 3: GMS_I8(3, false) break;
-        case 4: GMS_I8(4, false) break;
-        case 5: GMS_I8(5, false) break;
-        case 6: GMS_I8(6, false) break;
+        case 1: GMS_I8(1, false, 8) break;
+        case 2: GMS_I8(2, false, 8) break;
+        case 3: GMS_I8(3, false, 8) break;
+        case 4: GMS_I8(4, false, 8) break;
+        case 5: GMS_I8(5, false, 8) break;
+        case 6: GMS_I8(6, false, 8) break;
         default:
-            if (p.T <= 8) GMS_I8(8, true)
-            else if (p.T <= 12) GMS_I8(12, true)
-            else if (p.T <= 16) GMS_I8(16, true)
-            else if (p.T <= 24) GMS_I8(24, true)
-            else if (p.T <= 32) GMS_I8(32, true)
+            if (p.T <= 8) GMS_I8(8, true, 8)
+            else if (p.T <= 12) GMS_I8(12, true, 8)
+            else if (p.T <= 16) GMS_I8(16, true, 8)
+            else if (p.T <= 24) GMS_I8(24, true, 8)
+            else if (p.T <= 32) GMS_I8(32, true, 8)
             else return cudaErrorInvalidValue;
     }
 #undef GMS_I8

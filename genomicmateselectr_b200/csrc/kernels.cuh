@@ -79,6 +79,7 @@ cudaError_t launch_i8_build_digits(const double* tiles, const ChromDesc* chrom_d
                                    long long mp_total, int T, double* scale, const long long* gbase_d, signed char* G,
                                    int layout, cudaStream_t st);     // layout: 0 / 1 = i8path.cu (plain / cta_group::2), 2 = i8v2.cu
 cudaError_t launch_i8_contract(const I8Params& p, int ntiles, int nsplit, bool pair, cudaStream_t st);
+int i8_npart(int T);        // partial slabs per split written by launch_i8_contract
 // i8v2.cu: 32-row tiles, two TMEM accumulators (epilogue overlapped with the next unit's MMAs), T <= 16; writes
 // i8v2_npart() partial slabs per split. mc: clusters of two CTAs share a cross tile and take one row half each (the grid
 // is then 2 x ntiles wide); mc = false runs both halves in one CTA
