@@ -383,7 +383,9 @@ def main():
         return {"bound": "tensor", "kernel": "i8_contract_kernel (tcgen05.mma kind::i8, int32 accumulators in TMEM, cp.async.bulk staged)",
                 "achieved": ach, "peak": int8_peak, "unit": "TFLOP/s", "op_type": "int8 multiply-add = 2 ops",
                 "frac": ach / int8_peak, "traffic": traffic_i8,
-                "peak_source": "cuBLASLt int8 GEMM 8192^3 (torch._int_mm) measured in this run; nominal dense int8 4500",
+                "peak_source": "cuBLASLt int8 GEMM 8192^3 (torch._int_mm) measured in this run (MEASURED_PEAKS.json has bf16 only); "
+                               "nominal dense int8 4500",
+                "frac_of_nominal_int8": ach / 4500.0,
                 "algorithmic_flops_per_launch": alg, "executed_flops_per_launch": exe,
                 "executed_tflops": exe / (r["kernel_ms"] * 1e-3) / 1e12,
                 "executed_frac_of_peak": exe / (r["kernel_ms"] * 1e-3) / 1e12 / int8_peak,
