@@ -444,30 +444,54 @@ __global__ void __launch_bounds__(32 * (EW + 2), 1) i8_contract_kernel(const I8P
                         if (lane == 0) { if (CG2) i8_mbar_arrive_remote(accempty, 0); else i8_mbar_arrive(accempty); }
                         continue;
                     }
-    #pragma unroll 1
-                    for (int cb = 0; cb < RPT / I8_EC; ++cb) {                       // I8_EC SNP rows at a time
-                        int dig[I8_DIG][I8_EC];
+                    // software-pipelined over chunks of 4 SNP rows: the TMEM loads of chunk c + 1 are in flight while chunk c is
+                    // combined and accumulated (two register sets, A / B); the accumulator is released when the last chunk's
+                    // digits are in registers
+                    auto load4 = [&](int ch, int (&d)[I8_DIG][4]) {
     #pragma unroll
-                        for (int i = 0; i < I8_DIG; ++i) i8_tmem_ldc(tlane + i * I8_N + cb * I8_EC, dig[i]);
-                        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                        if (cb == RPT / I8_EC - 1 && !(p.debug & 512)) {                          // TMEM fully read: next trait's MMAs may start
-                            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-                            __syncwarp();
-                            if (lane == 0) { if (CG2) i8_mbar_arrive_remote(accempty, 0); else i8_mbar_arrive(accempty); }
-                        }
-                        const unsigned nzw = nz >> (I8_EC * cb), ngw = ng >> (I8_EC * cb);
+                        for (int i = 0; i < I8_DIG; ++i) i8_tmem_ldc(tlane + i * I8_N + ch * 4, d[i]);
+                    };
+                    auto wait4 = [&](int (&d)[I8_DIG][4]) {      // the registers are operands: nothing that reads them moves above
+                        asm volatile("tcgen05.wait::ld.sync.aligned;"
+                                     : "+r"(d[0][0]), "+r"(d[0][1]), "+r"(d[0][2]), "+r"(d[0][3]), "+r"(d[1][0]), "+r"(d[1][1]), "+r"(d[1][2]),
+                                       "+r"(d[1][3]), "+r"(d[2][0]), "+r"(d[2][1]), "+r"(d[2][2]), "+r"(d[2][3]), "+r"(d[3][0]), "+r"(d[3][1]),
+                                       "+r"(d[3][2]), "+r"(d[3][3]), "+r"(d[4][0]), "+r"(d[4][1]), "+r"(d[4][2]), "+r"(d[4][3]), "+r"(d[5][0]),
+                                       "+r"(d[5][1]), "+r"(d[5][2]), "+r"(d[5][3]), "+r"(d[6][0]), "+r"(d[6][1]), "+r"(d[6][2]), "+r"(d[6][3])
+                                     :: "memory");
+                    };
+                    auto release = [&]() {                       // TMEM fully read: the next (tile, trait)'s MMAs may start
+                        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                        __syncwarp();
+                        if (lane == 0) { if (CG2) i8_mbar_arrive_remote(accempty, 0); else i8_mbar_arrive(accempty); }
+                    };
+                    auto math4 = [&](int ch, const int (&d)[I8_DIG][4]) {
+                        const unsigned nzw = nz >> (4 * ch), ngw = ng >> (4 * ch);
     #pragma unroll
-                        for (int c = 0; c < I8_EC; ++c) {
+                        for (int c = 0; c < 4; ++c) {
                             // sum_i S_i 128^(6-i) exactly as a 64-bit integer, then times 2^-49 scale: three FP64 instructions
-                            const double2 mc = mrow[s * 64 + cb * I8_EC + c];
-                            double v = v2_scaled(v2_combine(dig[0][c], dig[1][c], dig[2][c], dig[3][c], dig[4][c], dig[5][c], dig[6][c]), mc.x, mc.y);
+                            const double2 mc = mrow[s * 64 + ch * 4 + c];
+                            double v = v2_scaled(v2_combine(d[0][c], d[1][c], d[2][c], d[3][c], d[4][c], d[5][c], d[6][c]), mc.x, mc.y);
                             long long bits = __double_as_longlong(v);
                             if (!((nzw >> c) & 1u)) bits = 0ll;
                             bits ^= (long long)((ngw >> c) & 1u) << 63;
                             v = __longlong_as_double(bits);
     #pragma unroll
-                            for (int t = 0; t < TT; ++t) Z[t][s] = fma(erow[t * 64 + cb * I8_EC + c], v, Z[t][s]);
+                            for (int t = 0; t < TT; ++t) Z[t][s] = fma(erow[t * 64 + ch * 4 + c], v, Z[t][s]);
                         }
+                    };
+                    constexpr int NCH = RPT / 4;                 // 8 chunks of 4 rows (an even number)
+                    int dA[I8_DIG][4], dB[I8_DIG][4];
+                    load4(0, dA);
+                    wait4(dA);
+    #pragma unroll 1
+                    for (int cp = 0; cp < NCH / 2; ++cp) {
+                        load4(2 * cp + 1, dB);
+                        math4(2 * cp, dA);
+                        wait4(dB);
+                        if (2 * cp + 1 == NCH - 1 && !(p.debug & 512)) release();
+                        if (cp + 1 < NCH / 2) load4(2 * cp + 2, dA);
+                        math4(2 * cp + 1, dB);
+                        if (cp + 1 < NCH / 2) wait4(dA);
                     }
                     if (p.debug & 512) {       // profiling: release the accumulator only after ALL the FP64 work of the unit
                         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
