@@ -112,7 +112,7 @@ def test_one_engine_many_calls():
     {"GMS_I8_V2": "1", "GMS_I8_IA": "0", "GMS_I8_MC": "0"},         # the same without clusters
     {"GMS_I8_V2": "1", "GMS_I8_IA": "1"},                           # i8v2.cu, exact integer accumulation
 ], ids=["plain", "cta_group2", "v2_fp64", "v2_fp64_nomc", "v2_int"])
-@pytest.mark.parametrize("T", [1, 3, 5, 7])
+@pytest.mark.parametrize("T", [1, 3, 5, 6, 7])
 def test_int8_kernel_variants(monkeypatch, env, T):
     """Every variant of the int8 tcgen05 kernel (environment switches read at gms_create) against the oracle: the default
     (cta_group::2 pairs, each CTA staging half of the digit operand), the single-CTA kernel, and the opt-in second-generation
@@ -151,3 +151,31 @@ def test_int8_cross_chunking(monkeypatch):
             out, nseg = eng.predict("AD", add, dom, None, sire, dam)
             assert eng.stats()["last_mode"] == 2
         assert np.array_equal(nseg, wseg) and rel_err(out, want) < 1e-9, chunk
+
+
+def test_int8_long_work_list():
+    """One 40,000-SNP chromosome (625 64-row tiles) and enough crosses that the plan would use ONE range of tiles per CTA:
+    the kernels keep their range of the work list in shared memory (512 entries), so the plan must cut it. No CPU oracle at
+    this size (a 12.8 GB matrix): the int8 tensor path must agree with the map-structured scan, which shares none of its code,
+    and a sample of crosses must not depend on how many crosses are predicted with them (different plan)."""
+    import genomicmateselectr_b200 as g
+    rng = np.random.default_rng(11)
+    m, P, T, N = 40000, 24, 2, 38400
+    cM = np.sort(rng.uniform(0, 300, m))
+    H = (rng.random((2 * P, m)) < rng.uniform(0.1, 0.9, m)).astype(np.uint8)
+    add, dom = rng.standard_normal((m, T)), rng.standard_normal((m, T))
+    sire = rng.integers(0, P, N).astype(np.int32)
+    dam = rng.integers(0, P, N).astype(np.int32)
+    with g.CrossVarEngine(0) as eng:
+        eng.set_genmap(cM, np.array([m]))
+        eng.set_haplotypes(H)
+        eng.set_mode("int8_tensor")
+        out, nseg = eng.predict("AD", add, dom, None, sire, dam)
+        assert eng.stats()["last_mode"] == 2
+        few, nfew = eng.predict("AD", add, dom, None, sire[:300], dam[:300])
+        eng.set_mode("map_scan")
+        ref, nref = eng.predict("AD", add, dom, None, sire, dam)
+    assert np.array_equal(nseg, nref) and np.array_equal(nfew, nseg[:300])
+    assert rel_err(out, ref) < 1e-9
+    assert rel_err(few, out[:300]) < 1e-12
+
