@@ -68,7 +68,10 @@ struct I8Params {
     int stages;                  // i8path.cu: pipeline depth (set by launch_i8_contract)
     const int4* qtab;            // i8v2 integer accumulation: [trait s][mp_total][trait t] fixed-point weights (q0, q1, q2, -)
     const int* gexp;             // [T x T] their exponents
-    int debug;                   // profiling only (GMS_I8_DEBUG): 1 = no epilogue arithmetic, 2 = no MMAs, 4 = no loads (i8v2); results are garbage
+    int debug;                   // profiling only (GMS_I8_DEBUG, bit mask; results are garbage): 1 no epilogue arithmetic, 2 no MMAs,
+                                 // 512 release the accumulator after all arithmetic of a unit (i8path.cu); i8v2.cu only: 4 no loads,
+                                 // 8 zero operands, 16 MMA warp does not wait for the FP64 burst, 32 TMEM loads only, 64 no TMEM
+                                 // loads, 128 tile-outer FP64 variant
 };
 size_t i8_smem_bytes(int T, bool cg2);
 cudaError_t launch_i8_build_xi(const unsigned* planeA, const unsigned* planeB, long long wpp, const int* sire,
