@@ -556,6 +556,18 @@ int gms_stage_inputs(gms_handle* h, int model, int T, const double* add, const d
     if (model == GMS_MODEL_DIRDOM && !asub) return fail(h, GMS_EINVAL, "allele-substitution effects are required for DirDom");
     if (N < 0 || (N > 0 && (!sire || !dam))) return fail(h, GMS_EINVAL, "bad cross list");
     if (N > (1LL << 31) - 1) return fail(h, GMS_EINVAL, "too many crosses in one call");
+    // NA / NaN / Inf effects would propagate to every variance in the reference (R arithmetic); here they are an error,
+    // like haplotype values outside {0, 1} (the digit planes of the int8 path have no representation for them)
+    for (const double* e : {add, model >= GMS_MODEL_AD ? dom : nullptr, model == GMS_MODEL_DIRDOM ? asub : nullptr}) {
+        if (!e) continue;
+        for (long long i = 0; i < h->m * (long long)T; ++i)
+            if (!std::isfinite(e[i])) {
+                char buf[160];
+                snprintf(buf, sizeof buf, "non-finite marker effect (%s effects, SNP %lld, trait %lld)",
+                         e == add ? "additive" : (e == dom ? "dominance" : "allele-substitution"), i % h->m, i / h->m);
+                return fail(h, GMS_EINVAL, buf);
+            }
+    }
     if (int rc = bind(h)) return rc;
     h->staged = h->computed = false;
     h->model = model;

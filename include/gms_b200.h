@@ -115,6 +115,7 @@ GMS_API int gms_trait_pairs(int T, int32_t* pair_t1, int32_t* pair_t2);
  *   add   : m x T column-major (trait t at add + t*m): AddEffectList     (R/predCrossVar.R:32-43)
  *   dom   : m x T, DomEffectList, required for AD and DIRDOM, else NULL
  *   asub  : m x T, allele-substitution effects for DIRDOM's VarBV, else NULL
+ *           (all effects must be finite: NA / NaN / Inf -> GMS_EINVAL; the reference would propagate them)
  *   N, sire[N], dam[N] : 0-based parent indices of each cross (selfs and duplicates allowed)
  *   out   : N x npairs x ncomp doubles, cross-major then pair-major; component order
  *           VarA [, VarD [, VarBV]]; pair order of gms_trait_pairs

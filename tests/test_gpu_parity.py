@@ -201,6 +201,10 @@ def test_edge_cases(gms, mode):
         eng.predict("A", s["add"], None, None, [0], [9])
     with pytest.raises(gms.GmsError, match="required"):
         eng.predict("AD", s["add"], None, None, [0], [1])
+    nan_dom = s["dom"].copy()
+    nan_dom[7, 0] = np.nan
+    with pytest.raises(gms.GmsError, match="non-finite marker effect"):      # the reference would return NaN variances
+        eng.predict("AD", s["add"], nan_dom, None, [0], [1])
     bad = H.copy()
     bad[3, 5] = 2
     with pytest.raises(gms.GmsError, match="outside"):
