@@ -1,4 +1,5 @@
-// Exact int8 tensor-core evaluation of the per-cross dominance term (opt-in: GMS_MODE_INT8_TENSOR).
+// Exact int8 tensor-core evaluation of the quadratic-form tables (per parent and per cross): GMS_MODE_INT8_TENSOR, what
+// GMS_MODE_AUTO resolves to.
 //
 // FP64 has no tcgen05 kind, but this contraction has a special shape: one operand is TERNARY.
 //     C_s[j,x] = sum_k G_s[j,k] xi_x[k],   G_s[j,k] = L'[j,k] d_s[k]  (FP64),   xi in {-1,0,+1}
@@ -7,15 +8,17 @@
 // Each digit plane times xi is an int8 x int8 -> int32 product whose sum over k <= 1920 terms is EXACT in
 // int32 (|sum| < 2^18), so the 5th-generation tensor cores (tcgen05.mma kind::i8, accumulators in TMEM)
 // do the O(m^2) work at int8 rate and the result differs from exact arithmetic only by the 2^-49 digit
-// truncation - tighter than a rounded FP64 dot product. The epilogue recombines the digits in FP64,
-// applies xi_x[j] d_t[j] and accumulates the T x T quadratic forms per cross in registers
-// (TMEM lane = cross, so the reduction over SNPs j is thread-local: no shuffles, no atomics).
+// truncation - tighter than a rounded FP64 dot product. The epilogue recombines the seven digit sums exactly in 64-bit
+// integer arithmetic, converts once to FP64 (i8ptx.cuh: v2_combine / v2_scaled), applies xi_x[j] d_t[j] and accumulates
+// the T x T quadratic forms per cross in registers (TMEM lane = cross, so the reduction over SNPs j is thread-local:
+// no shuffles, no atomics).
 //
 // Orientation: D[M = 128 crosses (TMEM lanes)][N = 64 SNP rows j] += Xi[128 x K] * Gdigit_i[64 x K]^T,
 // both operands K-major, no swizzle, pre-tiled in HBM in the UMMA canonical "interleaved" layout
 // (8 rows x 16 bytes core matrices) so that one cp.async.bulk lands them ready for the descriptors.
-// Warp roles: 0-7 epilogue (tcgen05.ld; two warps per TMEM lane quarter, 32 accumulator columns each),
-// 8 bulk-copy producer, 9 MMA issuer.
+// Warp roles: 0-7 epilogue (tcgen05.ld; two warps per TMEM lane quarter, 32 SNP rows each), 8 bulk-copy producer,
+// 9 MMA issuer; by default two CTAs form one M = 256 tile (tcgen05 cta_group::2). DESIGN.md section 4 has the measurements
+// behind every choice.
 #include "kernels.cuh"
 #include "i8ptx.cuh"
 
@@ -32,7 +35,6 @@ constexpr int I8_B_ALL = I8_DIG * I8_B_BYTES;       // 28 KiB: the 448-row digit
 template <bool CG2> struct I8Geo {
     static constexpr int B_STAGE = CG2 ? I8_B_ALL / 2 : I8_B_ALL;
     static constexpr int STAGE_BYTES = I8_A_BYTES + B_STAGE;           // 36 KiB / 22 KiB
-    static constexpr int STAGES = CG2 ? 8 : 5;                         // 180 KiB / 176 KiB
 };
 constexpr int I8_MAX_STAGES = 10;
 constexpr int I8_TTAB = 512;        // 64-row tiles per split that fit the shared-memory copy of the work list (the host plan keeps splits below it)
