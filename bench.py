@@ -2,18 +2,22 @@
 """Benchmark of the cross-variance hot path (BASELINE.json metric):
 cross variance-covariance predictions/sec (A+AD, 5 traits) on synthetic cassava-scale data.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cassava]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cassava|large]
+                    [--crosses-per-gpu n | --total-crosses n] [--grid <cross shards>x<chromosome shards>]
 
-A step = one pass of the hot path (modelType AD: VarA + VarD for all 15 trait pairs + Nsegsnps) over
-the whole batch of crosses.  N > 1: launched by torchrun, one rank per GPU, crosses sharded by rank
-(weak scaling: --crosses-per-gpu fixed), LD-decay tiles and haplotypes replicated, no data-path
-collective; the per-rank slabs are gathered to rank 0 in the e2e leg only.
+A step = one pass of the hot path (modelType AD: VarA + VarD for all 15 trait pairs + Nsegsnps) over the whole batch of
+crosses, with the per-handle cache OFF: every step rebuilds the operand images and every per-parent table.
+N > 1: launched by torchrun, one rank per GPU on a cross x chromosome grid (default N x 1): LD-decay tiles + haplotypes
+replicated (per chromosome shard), crosses split by rank, the per-parent stage split over the ranks of a chromosome
+column and finished by ONE all-gather of the table slices; a chromosome axis adds one all-reduce(sum) of the partial
+slabs. Default: weak scaling (--crosses-per-gpu fixed); --total-crosses fixes the whole job (strong scaling).
 
-  value     crosses/s with inputs resident in HBM (gms_compute only), CUDA events, max over ranks
-  e2e       the same through gms_predict with pinned HOST buffers (H2D + kernels + D2H [+ gather])
-  roofline  FP64 tensor (DMMA) roofline of the dominant kernel (per-cross dominance contraction)
-  cpu_baseline  the oracle's C restatement of the reference algorithm on the host cores (rank 0)
---impl reference times that CPU restatement alone (the reference is R; R is not installed here).
+  value     crosses/s with inputs resident in HBM (device work + the collectives of the path), CUDA events, max over ranks
+  e2e       the same through the C ABI with pinned HOST buffers (H2D + kernels + D2H [+ gather to rank 0])
+  roofline  tensor roofline of the dominant kernel (per-cross dominance contraction) + HBM roofline of the epilogue
+  parity    max error of >= 32 sampled crosses of THIS run, per evaluation mode, against the oracle's C restatement
+  cpu_baseline  that C restatement of the reference algorithm timed on the host cores (rank 0, N = 1 only)
+--impl reference times the CPU restatement alone (the reference is R; R is not installed here).
 """
 import argparse
 import json
@@ -39,9 +43,13 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cassava", choices=["cassava", "large", "mini"])
-    ap.add_argument("--crosses-per-gpu", type=int, default=None, help="default: the workload's N on every GPU")
+    ap.add_argument("--crosses-per-gpu", type=int, default=None, help="weak scaling: crosses per cross shard (default: the workload's N, "
+                    "capped at 50,000)")
+    ap.add_argument("--total-crosses", type=int, default=None, help="strong scaling: crosses of the whole job")
+    ap.add_argument("--grid", default=None, help="<cross shards>x<chromosome shards>, product = number of GPUs (default Nx1)")
     ap.add_argument("--model", default="AD", choices=["A", "AD", "DirDom"])
-    ap.add_argument("--cpu-sample", type=int, default=8, help="crosses per CPU-baseline step (3 steps, ~20 s on 16 cores)")
+    ap.add_argument("--modes", default="auto,fp64,map_scan", help="evaluation modes to measure; the first is the headline")
+    ap.add_argument("--cpu-sample", type=int, default=8, help="crosses per CPU-baseline step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
 
@@ -109,53 +117,49 @@ def measured_peaks():
         return {}
 
 
+def _best_ms(torch, fn, reps=5):
+    for _ in range(2):
+        fn()
+    torch.cuda.synchronize()
+    best = 1e30
+    for _ in range(reps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        torch.cuda.synchronize()
+        best = min(best, e0.elapsed_time(e1))
+    return best
+
+
 def dgemm_peak_tflops(torch):
     """FP64 ceiling on this box: cuBLAS DGEMM 8192^3, best of 5 (MEASURED_PEAKS.json has no FP64 figure)."""
     a = torch.randn(8192, 8192, dtype=torch.float64, device="cuda")
     b = torch.randn(8192, 8192, dtype=torch.float64, device="cuda")
-    for _ in range(2):
-        a @ b
-    torch.cuda.synchronize()
-    best = 1e30
-    for _ in range(5):
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        a @ b
-        e1.record()
-        torch.cuda.synchronize()
-        best = min(best, e0.elapsed_time(e1))
+    ms = _best_ms(torch, lambda: a @ b)
     del a, b
     torch.cuda.empty_cache()
-    return 2.0 * 8192 ** 3 / best / 1e9
+    return 2.0 * 8192 ** 3 / ms / 1e9
 
 
 def int8_peak_tops(torch):
-    """int8 tensor ceiling on this box: cuBLASLt int8 GEMM 8192^3 through torch._int_mm, best of 5."""
+    """int8 tensor rate a library reaches on this box: cuBLASLt int8 GEMM 8192^3 through torch._int_mm, best of 5."""
     try:
         a = torch.randint(-100, 100, (8192, 8192), dtype=torch.int8, device="cuda")
         b = torch.randint(-100, 100, (8192, 8192), dtype=torch.int8, device="cuda").t().contiguous().t()
-        for _ in range(2):
-            torch._int_mm(a, b)
-        torch.cuda.synchronize()
-        best = 1e30
-        for _ in range(5):
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            torch._int_mm(a, b)
-            e1.record()
-            torch.cuda.synchronize()
-            best = min(best, e0.elapsed_time(e1))
+        ms = _best_ms(torch, lambda: torch._int_mm(a, b))
         del a, b
         torch.cuda.empty_cache()
-        return 2.0 * 8192 ** 3 / best / 1e9
+        return 2.0 * 8192 ** 3 / ms / 1e9
     except Exception:
-        return 4500.0      # nominal dense int8, if the library call is unavailable
+        return None
 
 
 # ----------------------------------------------------------------------------------------------
 def cpu_reference_run(d, model, sample, steps, warmup, nthreads=0):
     """Time the oracle's C restatement of the reference algorithm (dense D per cross, one quadratic
-    form per trait pair) on the host cores: `sample` crosses per step, all threads inside a cross."""
+    form per trait pair) on the host cores: `sample` crosses per step, all threads inside a cross.
+    Also returns the outputs of every cross it evaluated (the parity samples)."""
     from oracle import crossvar_ref as CR
     from oracle import predcrossvar_oracle as O
     offs = np.concatenate([[0], np.cumsum(d["m_c"])])
@@ -171,13 +175,14 @@ def cpu_reference_run(d, model, sample, steps, warmup, nthreads=0):
         avail = os.cpu_count() or 1
     cores = nthreads or max(avail, CR.max_threads())
     rng = np.random.default_rng(12345)
-    times, nsegs = [], []
+    times, nsegs, samples = [], [], []
     for it in range(warmup + steps):
         pick = rng.integers(0, d["N"], sample)
         t0 = time.perf_counter()
         for x in pick:
-            _, nseg = prob.one_cross(int(d["sire"][x]), int(d["dam"][x]), "AD" if model != "A" else "A", cores)
+            out, nseg = prob.one_cross(int(d["sire"][x]), int(d["dam"][x]), "AD" if model != "A" else "A", cores)
             nsegs.append(nseg)
+            samples.append((int(x), out, nseg))
         dt = time.perf_counter() - t0
         if it >= warmup:
             times.append(dt)
@@ -187,7 +192,20 @@ def cpu_reference_run(d, model, sample, steps, warmup, nthreads=0):
                       f"(mean Nsegsnps {int(np.mean(nsegs))}); oracle/crossvar_ref.c = the reference's algorithm "
                       f"(dense m_seg^2 cross LD matrix, one quadratic form per trait pair) restated in C+OpenMP; "
                       f"R itself is not installed",
-            "ms_per_step": 1e3 * total / steps}
+            "ms_per_step": 1e3 * total / steps, "samples": samples}
+
+
+def parity_of(slab, nseg, samples, T):
+    """max error of the sampled crosses against the oracle outputs: strict relative error on the variances, and the
+    relative error of every entry with covariances guarded at 1e-6 sqrt(var var) (tests/util.py:rel_err)."""
+    from tests.util import rel_err, strict_rel_err
+    idx = np.array([x for x, _, _ in samples])
+    want = np.stack([o for _, o, _ in samples])
+    got = slab[idx][:, :, : want.shape[2]]
+    return {"crosses": int(len(idx)), "max_rel_err_variances_strict": strict_rel_err(got, want),
+            "max_rel_err_all_guarded": rel_err(got, want),
+            "nsegsnps_exact": bool(np.array_equal(nseg[idx], np.array([n for _, _, n in samples]))),
+            "tolerance": 1e-9, "oracle": "oracle/crossvar_ref.c (C restatement of R/predCrossVar.R:96-282, pinned to the vignette outputs)"}
 
 
 _REAL_STDOUT = None
@@ -215,23 +233,37 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     from genomicmateselectr_b200 import synth
     cfg = synth.CONFIGS[args.workload]
-    n_per = args.crosses_per_gpu or cfg["N"]
     T = cfg["T"]
+    nshard = world if args.impl == "ours" else args.gpus
+    gx, gc = (int(v) for v in args.grid.lower().split("x")) if args.grid else (nshard, 1)
+    if gx * gc != nshard:
+        raise SystemExit(f"bench.py: --grid {gx}x{gc} needs {gx * gc} GPUs, got {nshard}")
+    strong = args.total_crosses is not None
+    n_per = args.crosses_per_gpu or min(cfg["N"], 50_000)
+    n_total = args.total_crosses if strong else n_per * gx
     config = {"workload": f"synthetic {args.workload}-scale: {cfg['P']} phased parents, {sum(cfg['m_c'])} SNPs / "
-                          f"{len(cfg['m_c'])} chromosomes, {T} traits, {n_per} crosses per GPU, modelType {args.model}",
-              "model_type": args.model, "crosses_per_gpu": n_per, "parents": cfg["P"], "snps": int(sum(cfg["m_c"])),
-              "chromosomes": len(cfg["m_c"]), "traits": T, "sharding": "by cross, tiles+haplotypes replicated",
-              "l2_policy": "inputs larger than L2 (RoR tile image 283 MB at cassava scale, re-streamed every step)"}
+                          f"{len(cfg['m_c'])} chromosomes, {T} traits, "
+                          + (f"{n_total} crosses in total" if strong else f"{n_per} crosses per GPU") + f", modelType {args.model}",
+              "model_type": args.model, "crosses_total": n_total, "parents": cfg["P"], "snps": int(sum(cfg["m_c"])),
+              "chromosomes": len(cfg["m_c"]), "traits": T,
+              "grid": f"{gx} cross shards x {gc} chromosome shards",
+              "sharding": "crosses by rank; tiles + haplotypes replicated per chromosome shard; per-parent stage split over the "
+                          "cross shards + one all-gather of the table slices"
+                          + ("; partial slabs all-reduced over the chromosome axis" if gc > 1 else ""),
+              "cache": "off (every step rebuilds operand images and per-parent tables)",
+              "l2_policy": "inputs larger than L2 (digit images > 1 GB, RoR tile image 283 MB at cassava scale, re-streamed every step)"}
+    if not strong:
+        config["crosses_per_gpu"] = n_per
 
     # ------------------------------------------------------------------ reference arm (CPU)
     if args.impl == "reference":
         if rank != 0:
             return 0
-        d = synth.make(args.workload, N=min(cfg["N"], 50_000))
+        d = synth.make(args.workload, N=min(n_total, 50_000))
         r = cpu_reference_run(d, args.model, args.cpu_sample, args.steps, args.warmup)
         line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
+                "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
                 "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
                 "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
@@ -241,12 +273,14 @@ def main():
     # ------------------------------------------------------------------ our arm (GPU)
     import torch
     import torch.distributed as dist
-    from genomicmateselectr_b200 import CrossVarEngine
+    from genomicmateselectr_b200 import CrossVarEngine, sharding as S
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the engine has no CPU fallback")
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    layout = S.GridLayout(world, gx, gc)
+    xi, ci = layout.coords(rank)
 
     def barrier():
         if world > 1:
@@ -260,14 +294,14 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    n_total = n_per * world
     d = synth.make(args.workload, N=n_total)
-    lo, hi = rank * n_per, (rank + 1) * n_per
-    sire, dam = d["sire"][lo:hi].copy(), d["dam"][lo:hi].copy()
+    lo, hi = S.shard_range(n_total, xi, gx)
+    n_loc = hi - lo
     dom = d["dom"] if args.model != "A" else None
     asub = (d["add"] + d["dom"] * 0.1) if args.model == "DirDom" else None
 
     eng = CrossVarEngine(local_rank)
+    eng.set_cache(False)                  # the headline recomputes everything every step
     stream = torch.cuda.Stream()          # a real (non-default) stream: handle 0 would mean "engine's own stream"
     torch.cuda.set_stream(stream)
     eng.set_stream(stream.cuda_stream)
@@ -276,49 +310,68 @@ def main():
     eng.set_haplotypes(d["H"])
     torch.cuda.synchronize()
     setup_s = time.perf_counter() - t0
+    if world > 1:
+        S.grid_groups(layout, dist)       # process groups are created once, outside every timed region
 
     fp64_peak = dgemm_peak_tflops(torch)
-    int8_peak = int8_peak_tops(torch)
+    int8_lib = int8_peak_tops(torch)
+    pk = measured_peaks()
+    bf16_burst = pk.get("bf16_tflops")
+    int8_peak = 2.0 * bf16_burst if bf16_burst else 4500.0           # dense int8 = 2 x dense bf16 on the tcgen05 pipe
 
-    # pinned host buffers for the e2e legs
+    # pinned host buffers for the e2e legs (the WHOLE cross list: every rank derives the same parent set from it)
     npairs, ncomp = T * (T + 1) // 2, {"A": 1, "AD": 2, "DirDom": 3}[args.model]
     pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
     add_p = pin(np.asfortranarray(d["add"]).T)           # m x T column-major == (T, m) C-order
     dom_p = pin(np.asfortranarray(dom).T) if dom is not None else None
     asub_p = pin(np.asfortranarray(asub).T) if asub is not None else None
-    sire_p, dam_p = pin(sire), pin(dam)
-    out_p = torch.empty((n_per, npairs, ncomp), dtype=torch.float64).pin_memory()
-    nseg_p = torch.empty(n_per, dtype=torch.int32).pin_memory()
-    gather = [torch.empty((n_per, npairs, ncomp), dtype=torch.float64, device="cuda") for _ in range(world)] \
-        if (world > 1 and rank == 0) else None
+    sire_p, dam_p = pin(d["sire"]), pin(d["dam"])
+    out_p = torch.empty((n_loc, npairs, ncomp), dtype=torch.float64).pin_memory()
+    nseg_p = torch.empty(n_loc, dtype=torch.int32).pin_memory()
+    n_max = max(b - a for a, b in (S.shard_range(n_total, x, gx) for x in range(gx)))
+    gather = [torch.empty((n_max, npairs, ncomp), dtype=torch.float64, device="cuda") for _ in range(gx)] \
+        if (gx > 1 and rank == 0) else None
+    send = torch.zeros((n_max, npairs, ncomp), dtype=torch.float64, device="cuda") if gx > 1 else None
     f = lambda t: None if t is None else t.numpy().T      # back to an F-ordered (m, T) view of the pinned memory
 
+    def stage():
+        S.stage_local(eng, args.model, f(add_p), f(dom_p), f(asub_p), sire_p.numpy(), dam_p.numpy(), layout, d["m_c"], dist)
+
+    def compute(sync):
+        S.compute_local(eng, layout, dist, sync=sync, reduce_chromosomes=True)
+
     def e2e_step():
-        o, n = eng.predict(args.model, f(add_p), f(dom_p), f(asub_p), sire_p.numpy(), dam_p.numpy(),
-                           out=out_p.numpy(), nseg=nseg_p.numpy())
-        if world > 1:        # the "final gather of results" of the north star
-            dist.gather(out_p.cuda(non_blocking=True), gather, dst=0)
-        return float(o[0, 0, 0])
+        stage()
+        compute(False)
+        o, n = eng.fetch(out=out_p.numpy(), nseg=nseg_p.numpy())
+        if gx > 1:        # the "final gather of results" of the north star: chromosome-index-0 ranks -> rank 0
+            _, gather_group, _ = S.grid_groups(layout, dist)
+            if ci == 0:
+                send[:n_loc].copy_(out_p, non_blocking=True)
+                dist.gather(send, gather, dst=0, group=gather_group)
+        return float(o[0, 0, 0]) if n_loc else 0.0
+
+    saved = {}
 
     def measure(mode, with_clocks=False):
-        """One evaluation mode on the same staged inputs: device-resident throughput (gms_compute only: every
-        kernel incl. the device-side operand preparation), per-kernel times, and end-to-end through gms_predict."""
+        """One evaluation mode on the same staged inputs: device-resident throughput (every kernel incl. the device-side
+        operand preparation, plus the collectives of the path), per-kernel times, and end-to-end from host buffers."""
         eng.set_mode(mode)
-        eng.stage(args.model, d["add"], dom, asub, sire, dam)
+        stage()
         for _ in range(args.warmup):
-            eng.compute(sync=True)
+            compute(True)
         sampler = ClockSampler(local_rank) if with_clocks else None
         if sampler:
             sampler.start()       # nvidia-smi needs ~0.3 s to start: run it through the warm-up, keep the timed window
             tw = time.time()
             while len(sampler.lines) < 2 and time.time() - tw < 3.0:
-                eng.compute(sync=True)
+                compute(True)
         barrier()
         w0 = time.time()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
         for _ in range(args.steps):
-            eng.compute(sync=False)
+            compute(False)
         e1.record(stream)
         barrier()
         w1 = time.time()
@@ -331,11 +384,13 @@ def main():
         # library); averaged over separate, synchronised steps so that every launch is read back
         kernel_ms, stage_ms = [], []
         for _ in range(args.steps):
-            eng.compute(sync=True)
+            compute(True)
             s_ = eng.stats()
             kernel_ms.append(s_["last_ms_cross_kernel"])
             stage_ms.append((s_["last_ms_parent_stage"], s_["last_ms_cross_stage"], s_["last_ms_assemble"], s_["last_ms_total"]))
         st_ = eng.stats()
+        if world == 1:
+            saved[mode] = eng.fetch()
         for _ in range(min(2, args.warmup)):
             e2e_step()
         barrier()
@@ -354,66 +409,87 @@ def main():
                 "e2e_ms_per_step": 1e3 * e2e_s / args.steps, "clocks": clocks, "stats": st_}
 
     def fp64_roofline(r):
-        """FP64 tensor (DMMA) roofline of contract_kernel<MASK_XI>."""
+        """FP64 tensor (DMMA) roofline of contract_kernel<MASK_XI>: EXECUTED flops (lower block triangle) against DGEMM."""
         if args.model == "A" or r["kernel_ms"] <= 0:
             return None
-        alg = 2.0 * T * r["stats"]["S2"] * n_per            # SURVEY 8d dense count for the cross term, per launch
+        dense = 2.0 * T * r["stats"]["S2"] * n_loc          # SURVEY 8d dense count for the cross term, per launch
         exe = r["stats"]["last_flops_cross"]
-        ach = alg / (r["kernel_ms"] * 1e-3) / 1e12
+        ach = exe / (r["kernel_ms"] * 1e-3) / 1e12
         return {"bound": "tensor", "kernel": "contract_kernel<MASK_XI> (FP64 mma.sync DMMA, cp.async.bulk staged)",
                 "achieved": ach, "peak": fp64_peak, "unit": "TFLOP/s", "frac": ach / fp64_peak, "traffic": traffic,
+                "achieved_is": "executed flops (the kernel evaluates only the lower block triangle of the symmetric RoR blocks)",
                 "peak_source": "cuBLAS DGEMM 8192^3 measured in this run (MEASURED_PEAKS.json has no FP64 figure); "
                                "DMMA pipe probe tools/dmma_probe: 37.2 TFLOP/s; nominal 37-40",
-                "algorithmic_flops_per_launch": alg, "executed_flops_per_launch": exe,
-                "executed_tflops": exe / (r["kernel_ms"] * 1e-3) / 1e12,
-                "executed_frac_of_peak": exe / (r["kernel_ms"] * 1e-3) / 1e12 / fp64_peak,
-                "note": "algorithmic = dense 2*T*S2 per cross (no symmetry credit); the kernel executes only the lower "
-                        "block triangle of the symmetric RoR blocks, so frac can exceed 1",
+                "executed_flops_per_launch": exe, "dense_equivalent_flops_per_launch": dense,
+                "dense_equivalent_tflops": dense / (r["kernel_ms"] * 1e-3) / 1e12,
                 "kernel_ms": r["kernel_ms"], "kernel_share_of_step": r["kernel_ms"] / r["step_ms_sync"]}
 
     def int8_roofline(r):
-        """int8 tensor (tcgen05) roofline of i8_contract_kernel: 7 exact digit planes x ternary xi."""
+        """int8 tensor (tcgen05) roofline of i8_contract_kernel: 7 digit planes x ternary xi."""
         if args.model == "A" or r["kernel_ms"] <= 0:
             return None
         mc = np.asarray(d["m_c"], dtype=np.float64)
         nJ = np.ceil(mc / 64.0)
-        alg = 2.0 * 7 * T * n_per * float(np.sum(mc * (mc + 1) / 2))                    # lower triangle incl. diagonal, 7 digits
-        exe = 2.0 * 7 * T * (np.ceil(n_per / 128.0) * 128) * float(np.sum(64 * 64 * nJ * (nJ + 1) / 2))
+        alg = 2.0 * 7 * T * n_loc * float(np.sum(mc * (mc + 1) / 2))                    # lower triangle incl. diagonal, 7 digits
+        exe = 2.0 * 7 * T * (np.ceil(n_loc / 128.0) * 128) * float(np.sum(64 * 64 * nJ * (nJ + 1) / 2))
         ach = alg / (r["kernel_ms"] * 1e-3) / 1e12
         return {"bound": "tensor", "kernel": "i8_contract_kernel (tcgen05.mma kind::i8, int32 accumulators in TMEM, cp.async.bulk staged)",
                 "achieved": ach, "peak": int8_peak, "unit": "TFLOP/s", "op_type": "int8 multiply-add = 2 ops",
                 "frac": ach / int8_peak, "traffic": traffic_i8,
-                "peak_source": "cuBLASLt int8 GEMM 8192^3 (torch._int_mm) measured in this run (MEASURED_PEAKS.json has bf16 only); "
-                               "nominal dense int8 4500",
+                "peak_source": "2 x MEASURED_PEAKS.json bf16_tflops (burst; dense int8 runs at twice the bf16 rate on the tcgen05 pipe)"
+                               if bf16_burst else "nominal dense int8 4500 (MEASURED_PEAKS.json absent)",
                 "frac_of_nominal_int8": ach / 4500.0,
-                "algorithmic_flops_per_launch": alg, "executed_flops_per_launch": exe,
-                "executed_tflops": exe / (r["kernel_ms"] * 1e-3) / 1e12,
-                "executed_frac_of_peak": exe / (r["kernel_ms"] * 1e-3) / 1e12 / int8_peak,
-                "fp64_dense_equivalent_tflops": 2.0 * T * r["stats"]["S2"] * n_per / (r["kernel_ms"] * 1e-3) / 1e12,
+                "library_int8_gemm_tops_in_run": int8_lib,
+                "frac_of_library_int8_gemm_in_run": (ach / int8_lib) if int8_lib else None,
+                "algorithmic_ops_per_launch": alg, "executed_ops_per_launch": exe,
+                "executed_tops": exe / (r["kernel_ms"] * 1e-3) / 1e12,
                 "note": "algorithmic = 7 radix-128 digit planes x the exact lower triangle (incl. diagonal) of every chromosome "
-                        "block x T traits x crosses; executed adds 64-granular block and 128-cross tile padding",
+                        "block x T traits x crosses; executed adds 64-granular block and 128-cross tile padding. In FP64-flop terms "
+                        "(SURVEY 8d: 2 T S2 per cross) the kernel runs at "
+                        f"{2.0 * T * r['stats']['S2'] * n_loc / (r['kernel_ms'] * 1e-3) / 1e12:.0f} TFLOP/s-equivalent, a speed-up over "
+                        "the FP64 roofline, not a fraction of it",
                 "kernel_ms": r["kernel_ms"], "kernel_share_of_step": r["kernel_ms"] / r["step_ms_sync"]}
 
-    # DRAM bytes per launch of the two contraction kernels, from the committed `ncu --set full` captures of this config
-    traffic = traffic_i8 = None
-    try:
-        tr = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
-        if (tr["workload"], tr["crosses_per_gpu"], tr["model"]) == (args.workload, n_per, args.model):
-            traffic = tr["dram_bytes_read"] + tr["dram_bytes_write"]
-            if "int8" in tr:
-                traffic_i8 = tr["int8"]["dram_bytes_read"] + tr["int8"]["dram_bytes_write"]
-    except Exception:
-        pass
+    def epilogue_roofline(r):
+        """HBM roofline of the per-cross epilogue (nseg_kernel + assemble_kernel), SURVEY 8d bytes per cross."""
+        ms = r["stages_ms"]["assemble_nseg"]
+        if ms <= 0 or n_loc == 0:
+            return None
+        mp = r["stats"]["m_padded"]
+        per_cross = 4 * (mp // 8) + 2 * ncomp * npairs * 8 + npairs * ncomp * 8 + 4
+        ach = per_cross * n_loc / (ms * 1e-3) / 1e9
+        peak = pk.get("hbm_gbs") or 6455.6
+        return {"bound": "hbm", "kernels": "nseg_kernel + assemble_kernel", "achieved": ach, "peak": peak, "unit": "GB/s",
+                "frac": ach / peak, "bytes_per_cross": per_cross, "ms": ms, "share_of_step": ms / r["step_ms_sync"],
+                "note": "algorithmic bytes; the haplotype bit-planes (8.6 MB at cassava scale) and the per-parent tables are "
+                        "L2-resident, so DRAM traffic is mostly the result slab"}
 
-    head = measure("auto", with_clocks=True)                 # the default path of the library = the headline
+    # DRAM bytes per launch of the contraction kernels, from the committed `ncu --set full` captures of this config
+    traffic = traffic_i8 = None
+    for name in ("r2_traffic.json", "r1_traffic.json"):
+        try:
+            tr = json.load(open(os.path.join(ROOT, "profiles", name)))
+            if (tr["workload"], tr["crosses_per_gpu"], tr["model"]) == (args.workload, n_loc, args.model):
+                traffic = tr["dram_bytes_read"] + tr["dram_bytes_write"]
+                if "int8" in tr:
+                    traffic_i8 = tr["int8"]["dram_bytes_read"] + tr["int8"]["dram_bytes_write"]
+                break
+        except Exception:
+            pass
+
+    modes = [m for m in args.modes.split(",") if m]
+    head = measure(modes[0], with_clocks=True)                 # the default path of the library = the headline
     ms, value, launches, clocks, st = head["ms_per_step"] * args.steps, head["value"], head["launches"], head["clocks"], head["stats"]
     roof = int8_roofline(head) if head["resolved_mode"] == "int8_tensor" else fp64_roofline(head)
-    h2d = sum(t.numel() * t.element_size() for t in (add_p, dom_p, asub_p, sire_p, dam_p) if t is not None) \
-        + 2 * n_per * 4 + 4 * int(st["last_parents_used"])      # + sire/dam table slots + parent list
+    if roof is not None:
+        roof["epilogue"] = epilogue_roofline(head)
+    h2d = sum(t.numel() * t.element_size() for t in (add_p, dom_p, asub_p) if t is not None) \
+        + 2 * n_loc * 4 + 4 * int(st["last_parents_used"])      # effects + this rank's sire/dam + the parent list
     d2h = out_p.numel() * 8 + nseg_p.numel() * 4
     e2e = {"value": head["e2e_value"], "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
            "ms_per_step": head["e2e_ms_per_step"],
-           "api": "gms_predict (C ABI) via CrossVarEngine.predict, pinned host buffers, default mode"}
+           "api": "gms_stage_inputs_range + gms_compute_parents / gms_compute_crosses + gms_fetch_outputs (C ABI) via "
+                  "CrossVarEngine, pinned host buffers, default mode, cache off"}
 
     def leg(mode, note, roofline_fn=None):
         try:
@@ -426,26 +502,54 @@ def main():
         except Exception as exc:   # the headline path must not depend on the other legs
             return {"error": str(exc)}
 
-    fp64_leg = leg("fp64", "gms_set_mode(GMS_MODE_DENSE): the FP64 DMMA contraction north_star describes; any symmetric matrix",
-                   fp64_roofline) if head["resolved_mode"] != "fp64_dmma" else None
-    map_scan = leg("map_scan", "gms_set_mode(GMS_MODE_MAP_SCAN): map-structured prefix-sum path, map-derived recombFreqMat only; opt-in")
-    eng.set_mode("auto")
+    fp64_leg = map_scan = None
+    if "fp64" in modes[1:] and head["resolved_mode"] != "fp64_dmma":
+        fp64_leg = leg("fp64", "gms_set_mode(GMS_MODE_DENSE): the FP64 DMMA contraction north_star describes; any symmetric matrix",
+                       fp64_roofline)
+    if "map_scan" in modes[1:]:
+        map_scan = leg("map_scan", "gms_set_mode(GMS_MODE_MAP_SCAN): map-structured prefix-sum path, map-derived recombFreqMat only; opt-in")
+
+    # the cache: same effects again (a mate-selection loop re-scoring cross lists): operand images + parent tables reused
+    cached = None
+    try:
+        eng.set_mode(modes[0])
+        eng.set_cache(True)
+        stage(); compute(True)
+        stage(); compute(True)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(args.steps):
+            compute(False)
+        e1.record(stream)
+        barrier()
+        cms = max_over_ranks(e0.elapsed_time(e1))
+        cached = {"value": n_total * args.steps / (cms * 1e-3), "unit": UNIT, "ms_per_step": cms / args.steps,
+                  "cache_hit": int(eng.stats()["last_cache_hit"]),
+                  "note": "gms_set_cache(1) and unchanged effects: not the headline (work is skipped), reported for mate-selection loops"}
+        eng.set_cache(False)
+    except Exception as exc:
+        cached = {"error": str(exc)}
 
     if rank == 0:
-        cpu = None
+        cpu = parity = None
         if world == 1 and not args.no_cpu_baseline:
             cpu = cpu_reference_run(d, args.model, args.cpu_sample, 3, 1)
+            parity = {m_: parity_of(saved[m_][0], saved[m_][1], cpu["samples"], T) for m_ in saved}
             cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
-        pk = measured_peaks()
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-                "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
-                "vs_baseline": None,
-                "dtype": "f64 results; " + ("exact int8 digit planes on tcgen05 + f64 recombination" if head["resolved_mode"] == "int8_tensor" else "f64 DMMA"),
-                "data": "synthetic", "config": dict(config, mode=head["resolved_mode"]), "clocks": clocks,
-                "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu,
-                "stages_ms": head["stages_ms"], "fp64_dmma": fp64_leg, "map_scan": map_scan,
+                "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+                "scaling": "strong" if strong else "weak", "vs_baseline": None,
+                "dtype": "f64 results; " + ("int8 digit planes on tcgen05 (49-bit row-scaled fixed point, a-posteriori error bound, "
+                                            "FP64 re-evaluation of failing units) + f64 recombination"
+                                            if head["resolved_mode"] == "int8_tensor" else "f64 DMMA"),
+                "data": "synthetic", "config": config, "resolved_mode": head["resolved_mode"], "clocks": clocks,
+                "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu, "parity": parity,
+                "fallback": {"units_failing_int8_bound": int(st["last_fallback_units"]), "overflow": int(st["last_fallback_overflow"])},
+                "stages_ms": head["stages_ms"], "fp64_dmma": fp64_leg, "map_scan": map_scan, "cached": cached,
                 "setup_s": setup_s, "hbm_tile_bytes": int(st["tile_bytes"]),
-                "measured_peaks": {"hbm_gbs": pk.get("hbm_gbs"), "fp64_dgemm_tflops": fp64_peak, "int8_gemm_tops": int8_peak}}
+                "measured_peaks": {"hbm_gbs": pk.get("hbm_gbs"), "bf16_tflops_burst": bf16_burst, "fp64_dgemm_tflops": fp64_peak,
+                                   "int8_gemm_tops_library_in_run": int8_lib}}
         emit(line)
     eng.close()
     if world > 1:

@@ -26,7 +26,8 @@ class Stats(C.Structure):
                 ("last_ms_parent_stage", C.c_float), ("last_ms_cross_stage", C.c_float),
                 ("last_ms_cross_kernel", C.c_float), ("last_ms_assemble", C.c_float),
                 ("last_ms_total", C.c_float), ("last_flops_cross", C.c_double),
-                ("last_flops_parent", C.c_double)]
+                ("last_flops_parent", C.c_double), ("last_fallback_units", C.c_int64),
+                ("last_parents_computed", C.c_int64), ("last_fallback_overflow", C.c_int32), ("last_cache_hit", C.c_int32)]
 
     def asdict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -45,6 +46,15 @@ _SIGS = {
     "gms_set_haplotypes_u8rm": (C.c_int, [_P, C.c_int64, C.c_int64, _P]),
     "gms_set_chromosome_shard": (C.c_int, [_P, C.c_int, C.c_int]),
     "gms_set_mode": (C.c_int, [_P, C.c_int]),
+    "gms_set_int8_tolerance": (C.c_int, [_P, C.c_double]),
+    "gms_set_cache": (C.c_int, [_P, C.c_int]),
+    "gms_set_parent_shard": (C.c_int, [_P, C.c_int, C.c_int]),
+    "gms_stage_inputs_range": (C.c_int, [_P, C.c_int, C.c_int, _P, _P, _P, C.c_int64, _P, _P, C.c_int64, C.c_int64]),
+    "gms_compute_parents": (C.c_int, [_P]),
+    "gms_parent_exchange": (C.c_int, [_P, C.POINTER(_P), C.POINTER(C.c_int64), C.POINTER(C.c_int32)]),
+    "gms_compute_crosses": (C.c_int, [_P, C.c_int]),
+    "gms_device_outputs": (C.c_int, [_P, C.POINTER(_P), C.POINTER(_P), C.POINTER(C.c_int64)]),
+    "gms_predict_batched": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, _P, _P, _P, C.c_int64, _P, _P, _P, _P]),
     "gms_trait_pairs": (C.c_int, [C.c_int, _P, _P]),
     "gms_predict": (C.c_int, [_P, C.c_int, C.c_int, _P, _P, _P, C.c_int64, _P, _P, _P, _P]),
     "gms_predict_sharded": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, _P, _P, _P, C.c_int64, _P, _P, _P, _P]),

@@ -7,7 +7,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libgms_b200.so")
-SOURCES = ["api.cu", "contract.cu", "kernels.cu", "scan.cu", "i8path.cu", "i8v2.cu"]
+SOURCES = ["api.cu", "contract.cu", "kernels.cu", "scan.cu", "i8path.cu", "verify.cu"]
 HEADERS = ["common.cuh", "kernels.cuh", "i8ptx.cuh", os.path.join("..", "..", "include", "gms_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden"]

@@ -53,7 +53,9 @@ struct ContractParams {
     long long wpp;               // words per parent = mp_total / 32
     const int* unit_a;           // parent (DELTA/HET) or sire (XI) of each unit
     const int* unit_b;           // dam (XI)
-    long long n_units;
+    long long n_units;           // units (or, with n_units_dev, the capacity of the unit lists and of Z)
+    const int* n_units_dev;      // NULL, or the device-side unit count (<= n_units is enforced): the grid is then fixed and
+                                 // every CTA walks tiles blockIdx.x, blockIdx.x + gridDim.x, ...
     int T;
     int NU;                      // units per tile = BN / T
     int mode;

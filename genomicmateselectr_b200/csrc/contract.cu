@@ -176,15 +176,19 @@ __global__ void __launch_bounds__(NTHREADS, 1) contract_kernel(const ContractPar
     double* Bs = As + (size_t)S * CHUNK;
     double* Zacc = Bs + (size_t)S * BCHUNK;                       // [8 warps][40][T]
     unsigned long long* bars = reinterpret_cast<unsigned long long*>(Zacc + MATH_WARPS * 40 * T);
-    unsigned* emask = reinterpret_cast<unsigned*>(bars + 2 * S);  // [2 buffers][NU][4 words][nz, ng]
+    unsigned* emask = reinterpret_cast<unsigned*>(bars + 2 * S);  // [S + 1 buffers][NU][4 words][nz, ng]: the producers run at
+                                                                  // most S chunks = S row-tiles ahead of the consumers' epilogue
     const unsigned full0 = smem_u32(bars);
     const unsigned empty0 = smem_u32(bars + S);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const int g = lane >> 2, tig = lane & 3;
-    const long long u0 = (long long)blockIdx.x * NU;
     const int split = blockIdx.y;
+    // units: p.n_units of them, or - for the FP64 re-evaluation of the units that failed the int8 error bound (verify.cu) -
+    // a count that only the device knows; then the grid is fixed and every CTA walks the tiles it owns
+    const long long n_live = p.n_units_dev ? (long long)min(*p.n_units_dev, (int)p.n_units) : p.n_units;
+    if ((long long)blockIdx.x * NU >= n_live) return;
     const int rt_begin = p.split_begin[split], rt_end = p.split_begin[split + 1];
 
     if (threadIdx.x == 0) {
@@ -194,7 +198,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) contract_kernel(const ContractPar
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    for (int i = threadIdx.x; i < MATH_WARPS * 40 * T; i += NTHREADS) Zacc[i] = 0.0;
     __syncthreads();
 
     if (warp >= MATH_WARPS) {
@@ -208,15 +211,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) contract_kernel(const ContractPar
             else { colu[b] = -1; colt[b] = 0; }
         }
         const int ulo = (40 * pw) / T;
+        unsigned it = 0, rtc = 0;
+        for (long long u0 = (long long)blockIdx.x * NU; u0 < n_live; u0 += (long long)gridDim.x * NU) {
         // lane keeps the parents of units ulo+lane and ulo+32+lane of this tile
         int pa0 = -1, pb0 = -1, pa1 = -1, pb1 = -1;
         {
             const int ua = ulo + lane, ub = ulo + 32 + lane;
-            if (ua < NU && u0 + ua < p.n_units) { pa0 = p.unit_a[u0 + ua]; pb0 = (p.mode == MASK_XI) ? p.unit_b[u0 + ua] : 0; }
-            if (ub < NU && u0 + ub < p.n_units) { pa1 = p.unit_a[u0 + ub]; pb1 = (p.mode == MASK_XI) ? p.unit_b[u0 + ub] : 0; }
+            if (ua < NU && u0 + ua < n_live) { pa0 = p.unit_a[u0 + ua]; pb0 = (p.mode == MASK_XI) ? p.unit_b[u0 + ua] : 0; }
+            if (ub < NU && u0 + ub < n_live) { pa1 = p.unit_a[u0 + ub]; pb1 = (p.mode == MASK_XI) ? p.unit_b[u0 + ub] : 0; }
         }
-        unsigned it = 0;
-        for (int rt = rt_begin; rt < rt_end; ++rt) {
+        for (int rt = rt_begin; rt < rt_end; ++rt, ++rtc) {
             const RowTile tile = p.rowtiles[rt];
             const ChromDesc cd = p.chrom[tile.c];
             const int nkc = rowtile_nkc(cd, tile.I);
@@ -231,12 +235,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) contract_kernel(const ContractPar
                 if (kc == 0) {
                     // masks of this row-tile's 128 rows for the consumers' epilogue (published by the
                     // arrive on this stage's full barrier; double-buffered by row-tile parity)
-                    unsigned* em = emask + ((rt - rt_begin) & 1) * (NU * 8);
+                    unsigned* em = emask + (rtc % (unsigned)(S + 1)) * (NU * 8);
                     const long long wbase = (cd.pad_off >> 5) + 4 * tile.I;
                     for (int idx = pw * 32 + lane; idx < NU * 4; idx += PROD_WARPS * 32) {
                         const int u = idx >> 2, w4 = idx & 3;
                         int pa = -1, pb = 0;
-                        if (u0 + u < p.n_units) { pa = p.unit_a[u0 + u]; pb = (p.mode == MASK_XI) ? p.unit_b[u0 + u] : 0; }
+                        if (u0 + u < n_live) { pa = p.unit_a[u0 + u]; pb = (p.mode == MASK_XI) ? p.unit_b[u0 + u] : 0; }
                         unsigned nz, ng;
                         unit_mask(p, pa, pb, wbase + w4, nz, ng);
                         em[idx * 2] = nz;
@@ -274,14 +278,18 @@ __global__ void __launch_bounds__(NTHREADS, 1) contract_kernel(const ContractPar
                 if (lane == 0) mbar_arrive(full0 + 8 * slot);
             }
         }
+        }
     } else {
         // ------------------------------------------------------------------ consumers
         // warp (wm, wn): rows of the 16-row blocks mb = wm and wm + 4 (interleaved so that the padding
         // blocks of a chromosome's last row-tile are spread over the 4 SM sub-partitions), columns 40 wn ..
         const int wm = warp & 3, wn = warp >> 2;
         double acc[2][5][4];
-        unsigned it = 0;
-        for (int rt = rt_begin; rt < rt_end; ++rt) {
+        unsigned it = 0, rtc = 0;
+        for (long long u0 = (long long)blockIdx.x * NU; u0 < n_live; u0 += (long long)gridDim.x * NU) {
+        for (int i = threadIdx.x; i < MATH_WARPS * 40 * T; i += MATH_WARPS * 32) Zacc[i] = 0.0;
+        asm volatile("bar.sync 1, %0;" ::"n"(MATH_WARPS * 32) : "memory");
+        for (int rt = rt_begin; rt < rt_end; ++rt, ++rtc) {
             const RowTile tile = p.rowtiles[rt];
             const ChromDesc cd = p.chrom[tile.c];
             const int nkc = rowtile_nkc(cd, tile.I);
@@ -309,7 +317,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) contract_kernel(const ContractPar
             }
 
             // ---- row-tile epilogue: Zacc[col][t] += sum_rows e_t[row] * mask_u(col)[row] * acc[row][col]
-            const unsigned* em = emask + ((rt - rt_begin) & 1) * (NU * 8);
+            const unsigned* em = emask + (rtc % (unsigned)(S + 1)) * (NU * 8);
             const int bit0 = 16 * (wm & 1) + g;            // row 16 (wm + 4 mi) + 8 h + g -> word (wm>>1) + 2 mi, bit bit0 + 8 h
 #pragma unroll
             for (int ni = 0; ni < 5; ++ni) {
@@ -372,7 +380,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) contract_kernel(const ContractPar
 #pragma unroll
             for (int m4 = 0; m4 < 4; ++m4) v += Zacc[(size_t)((wn2 * 4 + m4) * 40 + cl) * T + t];
             const long long unit = u0 + u;
-            if (unit < p.n_units) p.Z[((long long)split * p.n_units + unit) * TT + rem] = v;
+            if (unit < n_live) p.Z[((long long)split * p.n_units + unit) * TT + rem] = v;
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(MATH_WARPS * 32) : "memory");     // Zacc is re-zeroed for the CTA's next tile
         }
     }
 }
@@ -380,7 +390,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) contract_kernel(const ContractPar
 size_t contract_smem_bytes(int T, int stages) {
     const int NU = BN / T;
     return (size_t)stages * (CHUNK + BCHUNK) * 8 + (size_t)MATH_WARPS * 40 * T * 8 + (size_t)2 * stages * 8 +
-           (size_t)2 * NU * 8 * 4;
+           (size_t)(stages + 1) * NU * 8 * 4;
 }
 
 int contract_pick_stages(int T, size_t smem_limit) {

@@ -3,15 +3,17 @@
 //
 // FP64 has no tcgen05 kind, but this contraction has a special shape: one operand is TERNARY.
 //     C_s[j,x] = sum_k G_s[j,k] xi_x[k],   G_s[j,k] = L'[j,k] d_s[k]  (FP64),   xi in {-1,0,+1}
-// xi is exact in int8. G_s is split row-wise into 7 signed radix-128 digits with a shared power-of-two
-// row scale 2^E(j,s):  G = 2^E sum_i g_i 128^-(i+1) + r,  |r| <= 2^(E-49)  (exact FP64 operations).
-// Each digit plane times xi is an int8 x int8 -> int32 product whose sum over k <= 1920 terms is EXACT in
-// int32 (|sum| < 2^18), so the 5th-generation tensor cores (tcgen05.mma kind::i8, accumulators in TMEM)
-// do the O(m^2) work at int8 rate and the result differs from exact arithmetic only by the 2^-49 digit
-// truncation - tighter than a rounded FP64 dot product. The epilogue recombines the seven digit sums exactly in 64-bit
-// integer arithmetic, converts once to FP64 (i8ptx.cuh: v2_combine / v2_scaled), applies xi_x[j] d_t[j] and accumulates
-// the T x T quadratic forms per cross in registers (TMEM lane = cross, so the reduction over SNPs j is thread-local:
-// no shuffles, no atomics).
+// xi is exact in int8. G_s is rounded row-wise to 49 fractional bits of a shared power-of-two row scale 2^E(j,s) > max_k |G_s[j,k]|
+// and split into 7 sign-magnitude radix-128 digits:  G = 2^E sum_i g_i 128^-(i+1) + r,  |r| <= 2^(E-50) (round to nearest
+// even, unbiased; 2^(E-49) is what the error bound assumes). Each digit plane times xi is an int8 x int8 -> int32 product
+// whose sum over the k of a row is EXACT in int32 for any chromosome length this library accepts (|sum| <= 127 n for n
+// non-zero xi entries), so the 5th-generation tensor cores (tcgen05.mma kind::i8, accumulators in TMEM) do the O(m^2)
+// work at int8 rate. The epilogue recombines the seven digit sums exactly in 64-bit integer arithmetic (exact while
+// n < 2^14 non-zero mask entries per chromosome and unit - verify.cu sends larger units to the FP64 path), converts once
+// to FP64 (i8ptx.cuh: v2_combine / v2_scaled), applies xi_x[j] d_t[j] and accumulates the T x T quadratic forms per cross
+// in registers (TMEM lane = cross, so the reduction over SNPs j is thread-local: no shuffles, no atomics).
+// THE RESULT IS FIXED POINT RELATIVE TO THE ROW SCALE, not floating point: verify.cu bounds the error of every unit
+// a posteriori and api.cu re-evaluates the units that fail the bound with the FP64 contraction (contract.cu).
 //
 // Orientation: D[M = 128 crosses (TMEM lanes)][N = 64 SNP rows j] += Xi[128 x K] * Gdigit_i[64 x K]^T,
 // both operands K-major, no swizzle, pre-tiled in HBM in the UMMA canonical "interleaved" layout
@@ -21,6 +23,13 @@
 // behind every choice.
 #include "kernels.cuh"
 #include "i8ptx.cuh"
+
+// profiling switches (results are garbage): only in a -DGMS_PROFILE build, never in the shipped library
+#ifdef GMS_PROFILE
+#define I8_DBG(bit) (p.debug & (bit))
+#else
+#define I8_DBG(bit) false
+#endif
 
 namespace gms {
 
@@ -152,7 +161,10 @@ __global__ void i8_scale_kernel(double* __restrict__ scale, long long n) {
     if (i >= n) return;
     const double v = scale[i];
     int e = 0;
-    if (v > 0x1p-900) (void)frexp(v, &e);           // v = f * 2^e, f in [0.5, 1)  =>  v < 2^e
+    if (v > 0x1p-900) {
+        const double f = frexp(v, &e);              // v = f * 2^e, f in [0.5, 1)  =>  v < 2^e
+        if (f >= 1.0 - 0x1p-50) ++e;                // so that rn(|G| 2^(49 - e)) < 2^49 for every entry: no digit ever clamps
+    }
     scale[i] = ldexp(1.0, e);
 }
 
@@ -189,13 +201,16 @@ __global__ void i8_build_digits_kernel(const double* __restrict__ tiles, const C
         signed char d[I8_DIG][16];
 #pragma unroll
         for (int b = 0; b < 16; ++b) {
-            double rr = (lp[b] * ecol[(long long)s * mp_total + b]) * inv;             // |rr| < 1
+            // |x| < 1 - 2^-50 (i8_scale_kernel); round-to-nearest-even to 49 fractional bits (unbiased, |error| <= 2^-50; the
+            // clamp never bites), then seven 7-bit sign-magnitude digits: integer arithmetic only
+            const double x = (lp[b] * ecol[(long long)s * mp_total + b]) * inv;
+            long long w = __double2ll_rn(fabs(x) * 0x1p49);                   // the product is exact
+            w = w > 0x1FFFFFFFFFFFFll ? 0x1FFFFFFFFFFFFll : w;
+            const int neg = x < 0.0;
 #pragma unroll
             for (int i = 0; i < I8_DIG; ++i) {
-                rr *= 128.0;                               // exact
-                const double t = trunc(rr);                // |t| <= 127
-                d[i][b] = (signed char)(int)t;
-                rr -= t;                                   // exact
+                const int dg = (int)((w >> (7 * (I8_DIG - 1 - i))) & 127);
+                d[i][b] = (signed char)(neg ? -dg : dg);
             }
         }
 #pragma unroll
@@ -204,19 +219,13 @@ __global__ void i8_build_digits_kernel(const double* __restrict__ tiles, const C
             int off;
             if (layout == 0) {
                 off = ((cc * (I8_DIG * 8) + (i * 8 + r1)) * 8 + r0) * 16;             // one 448-row operand
-            } else if (layout == 1) {
+            } else {
                 // cta_group::2: the N = 256 MMA takes rows 0-127 from the leader and 128-255 from the peer, the N = 192
                 // MMA rows 0-95 / 96-191; each CTA's half is a 224-row operand [128 rows | 96 rows], halves back to back
                 const int g = i * 64 + r;                                           // row of the 448-row operand
                 const int h = g < 256 ? g / 128 : (g - 256) / 96;
                 const int lr = g < 256 ? g % 128 : 128 + (g - 256) % 96;
                 off = h * (I8_B_ALL / 2) + ((cc * 28 + (lr >> 3)) * 8 + (lr & 7)) * 16;
-            } else {
-                // i8v2.cu: the images of block row J are ordered [trait s][row half h][kb <= J], so that the k-blocks of one
-                // (32-row tile, trait) are contiguous; operand = 224 rows (digit i x 32 rows)
-                const int h = r >> 5, g = i * 32 + (r & 31);
-                img = G + gbase + (long long)(J * (J + 1) / 2) * T * I8_B_ALL + ((long long)(s * 2 + h) * (J + 1) + kb) * (I8_B_ALL / 2);
-                off = ((cc * 28 + (g >> 3)) * 8 + (g & 7)) * 16;
             }
             *reinterpret_cast<uint4*>(img + off) = *reinterpret_cast<const uint4*>(d[i]);
         }
@@ -364,7 +373,7 @@ __global__ void __launch_bounds__(32 * (EW + 2), 1) i8_contract_kernel(const I8P
                         const unsigned long long das = da0 + ((slot * I8_STAGE_BYTES) >> 4), dbs = db0 + ((slot * I8_STAGE_BYTES) >> 4);
 #pragma unroll
                         for (int kk = 0; kk < I8_KB / 32; ++kk) {
-                            if (p.debug & 2) continue;
+                            if (I8_DBG(2)) continue;
                             const unsigned long long da = das + ((kk * 2 * (I8_M * 16)) >> 4);
                             const unsigned long long dbA = dbs + ((kk * 2 * B_LBO) >> 4), dbB = dbs + ((B_SECOND + kk * 2 * B_LBO) >> 4);
                             if (CG2) {
@@ -440,7 +449,7 @@ __global__ void __launch_bounds__(32 * (EW + 2), 1) i8_contract_kernel(const I8P
                 for (int s = 0; s < TT; ++s, ++acc_it) {               // unrolled: Z[t][s] must stay in registers
                     i8_mbar_wait(accfull, acc_it & 1u);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    if (p.debug & 1) {
+                    if (I8_DBG(1)) {
                         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                         __syncwarp();
                         if (lane == 0) { if (CG2) i8_mbar_arrive_remote(accempty, 0); else i8_mbar_arrive(accempty); }
@@ -490,12 +499,12 @@ __global__ void __launch_bounds__(32 * (EW + 2), 1) i8_contract_kernel(const I8P
                         load4(2 * cp + 1, dB);
                         math4(2 * cp, dA);
                         wait4(dB);
-                        if (2 * cp + 1 == NCH - 1 && !(p.debug & 512)) release();
+                        if (2 * cp + 1 == NCH - 1 && !(I8_DBG(512))) release();
                         if (cp + 1 < NCH / 2) load4(2 * cp + 2, dA);
                         math4(2 * cp + 1, dB);
                         if (cp + 1 < NCH / 2) wait4(dA);
                     }
-                    if (p.debug & 512) {       // profiling: release the accumulator only after ALL the FP64 work of the unit
+                    if (I8_DBG(512)) {       // profiling: release the accumulator only after ALL the FP64 work of the unit
                         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                         __syncwarp();
                         if (lane == 0) { if (CG2) i8_mbar_arrive_remote(accempty, 0); else i8_mbar_arrive(accempty); }
@@ -596,6 +605,7 @@ __global__ void __launch_bounds__(32 * (EW + 2), 1) i8_contract_kernel(const I8P
 // epilogue warps for T traits (see the kernel)
 int i8_epi_warps(int T) { (void)T; return 8; }    // 16 (96 registers per thread, x4 TMEM loads) measured 13 % slower at T = 5
 int i8_npart(int T) { return i8_epi_warps(T) / 4; }       // partial slabs per split: one per column group
+int i8_max_tiles_per_split() { return I8_TTAB; }
 static size_t i8_fixed_smem(int T) {
     const int rows = T <= 6 ? 3 * T : T + 2;          // per buffer: d_t[j] rows + (m, cm) pair rows (see the two epilogues)
     return (2 * I8_MAX_STAGES + 4) * 8 + (size_t)I8_TTAB * 16 + (size_t)2 * rows * 64 * 8;
@@ -621,13 +631,15 @@ cudaError_t launch_i8_build_xi(const unsigned* planeA, const unsigned* planeB, l
     return cudaGetLastError();
 }
 
-cudaError_t launch_i8_build_digits(const double* tiles, const ChromDesc* chrom_d, int c_begin, int c_end,
-                                   const int* rowpref_d, int nrows, const int* blkpref_d, int nblks, const double* emat,
-                                   long long mp_total, int T, double* scale, const long long* gbase_d, signed char* G,
-                                   int layout, cudaStream_t st) {
-    if (nrows == 0) return cudaSuccess;
-    // `scale` arrives zeroed (cudaMemsetAsync in gms_compute)
+cudaError_t launch_i8_build_digits(const double* tiles, const ChromDesc* chrom_d, int c_begin, int c_end, int C,
+                                   const int* blkpref_d, int nblks, const double* emat, long long mp_total, int T,
+                                   double* scale, double* smax, const long long* gbase_d, signed char* G, int layout,
+                                   cudaStream_t st) {
+    if (nblks == 0) return cudaSuccess;
+    // `scale` arrives zeroed (cudaMemsetAsync in api.cu); it holds the row maxima until i8_scale_kernel
     i8_rowmax_kernel<<<nblks, 256, 0, st>>>(tiles, chrom_d, c_begin, c_end, blkpref_d, emat, mp_total, T, reinterpret_cast<unsigned long long*>(scale));
+    cudaError_t e = launch_i8_smax(scale, chrom_d, c_begin, c_end, C, mp_total, T, smax, st);     // verify.cu: per-chromosome largest scale
+    if (e != cudaSuccess) return e;
     i8_scale_kernel<<<(unsigned)(((long long)T * mp_total + 255) / 256), 256, 0, st>>>(scale, (long long)T * mp_total);
     i8_build_digits_kernel<<<nblks, 256, 0, st>>>(tiles, chrom_d, c_begin, c_end, blkpref_d, emat, mp_total, T, scale, gbase_d, G, layout);
     return cudaGetLastError();

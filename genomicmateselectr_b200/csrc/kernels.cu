@@ -107,8 +107,9 @@ __device__ __forceinline__ bool word_to_snp(long long w, const ChromDesc* chrom,
 __global__ void pack_i32cm_kernel(const int32_t* __restrict__ hap, long long P, long long m,
                                   const ChromDesc* __restrict__ chrom, int C, unsigned* __restrict__ planeA,
                                   unsigned* __restrict__ planeB, long long wpp, int* __restrict__ bad_count) {
-    const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long long w = blockIdx.y;
+    const long long npb = (P + blockDim.x - 1) / blockDim.x;          // 1-D grid over (word, parent block)
+    const long long w = blockIdx.x / npb;
+    const long long p = (blockIdx.x - w * npb) * blockDim.x + threadIdx.x;
     if (p >= P) return;
     long long snp0; int nvalid;
     word_to_snp(w, chrom, C, snp0, nvalid);
@@ -128,8 +129,9 @@ __global__ void pack_i32cm_kernel(const int32_t* __restrict__ hap, long long P, 
 __global__ void pack_u8rm_kernel(const uint8_t* __restrict__ hap, long long P, long long m,
                                  const ChromDesc* __restrict__ chrom, int C, unsigned* __restrict__ planeA,
                                  unsigned* __restrict__ planeB, long long wpp, int* __restrict__ bad_count) {
-    const long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long long p = blockIdx.y;
+    const long long nwb = (wpp + blockDim.x - 1) / blockDim.x;       // 1-D grid over (parent, word block): P is not limited by gridDim.y
+    const long long p = blockIdx.x / nwb;
+    const long long w = (blockIdx.x - p * nwb) * blockDim.x + threadIdx.x;
     if (w >= wpp) return;
     long long snp0; int nvalid;
     word_to_snp(w, chrom, C, snp0, nvalid);
@@ -149,14 +151,16 @@ __global__ void pack_u8rm_kernel(const uint8_t* __restrict__ hap, long long P, l
 
 cudaError_t launch_pack_i32cm(const int32_t* hap_dev, long long P, long long m, const ChromDesc* chrom, int C,
                               unsigned* planeA, unsigned* planeB, long long wpp, int* bad_count, cudaStream_t st) {
-    dim3 grid((unsigned)((P + 127) / 128), (unsigned)wpp);
-    pack_i32cm_kernel<<<grid, 128, 0, st>>>(hap_dev, P, m, chrom, C, planeA, planeB, wpp, bad_count);
+    const long long blocks = ((P + 127) / 128) * wpp;
+    if (blocks > 0x7FFFFFFFll) return cudaErrorInvalidConfiguration;
+    pack_i32cm_kernel<<<(unsigned)blocks, 128, 0, st>>>(hap_dev, P, m, chrom, C, planeA, planeB, wpp, bad_count);
     return cudaGetLastError();
 }
 cudaError_t launch_pack_u8rm(const uint8_t* hap_dev, long long P, long long m, const ChromDesc* chrom, int C,
                              unsigned* planeA, unsigned* planeB, long long wpp, int* bad_count, cudaStream_t st) {
-    dim3 grid((unsigned)((wpp + 127) / 128), (unsigned)P);
-    pack_u8rm_kernel<<<grid, 128, 0, st>>>(hap_dev, P, m, chrom, C, planeA, planeB, wpp, bad_count);
+    const long long blocks = ((wpp + 127) / 128) * P;
+    if (blocks > 0x7FFFFFFFll) return cudaErrorInvalidConfiguration;
+    pack_u8rm_kernel<<<(unsigned)blocks, 128, 0, st>>>(hap_dev, P, m, chrom, C, planeA, planeB, wpp, bad_count);
     return cudaGetLastError();
 }
 
@@ -186,25 +190,65 @@ cudaError_t launch_scatter_effects(const double* eff_dev, long long m, int T, co
 }
 
 // ------------------------------------------------------------------------------------------
-__global__ void finalize_sym_kernel(const double* __restrict__ Z, int nsplit, long long n, int T,
+// Z partial slabs are [nsplit][zcap][T*T] (zcap units of capacity, n <= zcap of them live: n itself or *n_dev).
+// row_index: unit u is written to table row row_index[u] (per-parent tables are indexed by parent id; the FP64
+// re-evaluation of units that failed the int8 bound writes back to the rows verify.cu listed).
+__global__ void finalize_sym_kernel(const double* __restrict__ Z, int nsplit, long long zcap, long long n,
+                                    const int* __restrict__ n_dev, const int* __restrict__ row_index, int T,
                                     double* __restrict__ X, bool sym) {
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const int TT = T * T;
+    if (n_dev) n = min((long long)*n_dev, n);
     if (idx >= n * TT) return;
     const long long u = idx / TT;
     const int rem = (int)(idx - u * TT);
     const int t = rem / T, s = rem - t * T;
     double v = 0.0;
     for (int sp = 0; sp < nsplit; ++sp) {           // fixed order: bit-reproducible
-        const double* z = Z + ((long long)sp * n + u) * TT;
+        const double* z = Z + ((long long)sp * zcap + u) * TT;
         v += sym ? z[t * T + s] + z[s * T + t] : z[t * T + s];
     }
-    X[idx] = v;
+    const long long row = row_index ? (long long)row_index[u] : u;
+    X[row * TT + rem] = v;
 }
-cudaError_t launch_finalize_sym(const double* Z, int nsplit, long long n, int T, double* X, cudaStream_t st, bool sym) {
+cudaError_t launch_finalize_sym(const double* Z, int nsplit, long long n, int T, double* X, cudaStream_t st, bool sym,
+                                const int* row_index, const int* n_dev, long long zcap) {
     const long long total = n * T * T;
     if (total == 0) return cudaSuccess;
-    finalize_sym_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(Z, nsplit, n, T, X, sym);
+    finalize_sym_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(Z, nsplit, zcap > 0 ? zcap : n, n, n_dev, row_index, T, X, sym);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------
+// Exchange of per-parent table rows between ranks (parent-sharded per-parent stage): rows of up to 3 tables <-> one
+// contiguous buffer [row i][class k][T*T], i = position in the list of parents being computed.
+struct RowTabs { double* t[3]; };
+__global__ void pack_rows_kernel(RowTabs tabs, int ncls, int TT, const int* __restrict__ ids, long long n, double* __restrict__ buf) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n * ncls * TT) return;
+    const long long i = idx / (ncls * TT);
+    const int rem = (int)(idx - i * (ncls * TT)), k = rem / TT, e = rem - k * TT;
+    buf[idx] = tabs.t[k][(long long)ids[i] * TT + e];
+}
+__global__ void unpack_rows_kernel(const double* __restrict__ buf, int ncls, int TT, const int* __restrict__ ids, long long n, RowTabs tabs) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n * ncls * TT) return;
+    const long long i = idx / (ncls * TT);
+    const int rem = (int)(idx - i * (ncls * TT)), k = rem / TT, e = rem - k * TT;
+    tabs.t[k][(long long)ids[i] * TT + e] = buf[idx];
+}
+cudaError_t launch_pack_rows(const double* const* tabs, int ncls, int TT, const int* ids, long long n, double* buf, cudaStream_t st) {
+    const long long total = n * ncls * TT;
+    if (total == 0) return cudaSuccess;
+    RowTabs rt{{const_cast<double*>(tabs[0]), const_cast<double*>(tabs[1]), const_cast<double*>(tabs[2])}};
+    pack_rows_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(rt, ncls, TT, ids, n, buf);
+    return cudaGetLastError();
+}
+cudaError_t launch_unpack_rows(const double* buf, int ncls, int TT, const int* ids, long long n, double* const* tabs, cudaStream_t st) {
+    const long long total = n * ncls * TT;
+    if (total == 0) return cudaSuccess;
+    RowTabs rt{{tabs[0], tabs[1], tabs[2]}};
+    unpack_rows_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(buf, ncls, TT, ids, n, rt);
     return cudaGetLastError();
 }
 
@@ -246,7 +290,7 @@ __global__ void assemble_kernel(const AssembleParams p) {
     const int pr = (int)(idx - x * p.npairs);
     const int TT = p.T * p.T;
     const int i = p.pair_t1[pr] * p.T + p.pair_t2[pr];
-    const long long ss = (long long)p.sire_slot[x] * TT + i, ds = (long long)p.dam_slot[x] * TT + i;
+    const long long ss = (long long)p.sire[x] * TT + i, ds = (long long)p.dam[x] * TT + i;
     double* o = p.out + idx * p.ncomp;
     o[0] = 0.25 * (p.QA[ss] + p.QA[ds]);
     if (p.ncomp >= 2) o[1] = 0.0625 * (p.PD[ss] + p.PD[ds] + 2.0 * p.X[x * TT + i]);

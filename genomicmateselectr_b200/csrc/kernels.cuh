@@ -22,8 +22,14 @@ cudaError_t launch_scatter_effects(const double* eff_dev, long long m, int T, co
                                    double* emat, long long mp_total, cudaStream_t st);
 
 // X[n][t][s] = sum_split Z[split][n][t][s] + Z[split][n][s][t]   (sym)   or   sum_split Z[split][n][t][s]
+// row_index: unit u goes to row row_index[u] of X; n_dev: device-side unit count (<= n); zcap: unit capacity of Z (default n)
 cudaError_t launch_finalize_sym(const double* Z, int nsplit, long long n, int T, double* X, cudaStream_t st,
-                                bool sym = true);
+                                bool sym = true, const int* row_index = nullptr, const int* n_dev = nullptr,
+                                long long zcap = 0);
+
+// per-parent table rows <-> exchange buffer [row][class][T*T] (rows listed by parent id in `ids`)
+cudaError_t launch_pack_rows(const double* const* tabs, int ncls, int TT, const int* ids, long long n, double* buf, cudaStream_t st);
+cudaError_t launch_unpack_rows(const double* buf, int ncls, int TT, const int* ids, long long n, double* const* tabs, cudaStream_t st);
 
 // ---- map-structured fast path (scan.cu) ----
 struct ScanParams {
@@ -65,35 +71,50 @@ struct I8Params {
     int T;
     int mode;
     double* Zpart;               // [nsplit][n_units][T*T]
-    int stages;                  // i8path.cu: pipeline depth (set by launch_i8_contract)
-    const int4* qtab;            // i8v2 integer accumulation: [trait s][mp_total][trait t] fixed-point weights (q0, q1, q2, -)
-    const int* gexp;             // [T x T] their exponents
-    int debug;                   // profiling only (GMS_I8_DEBUG, bit mask; results are garbage): 1 no epilogue arithmetic, 2 no MMAs,
-                                 // 512 release the accumulator after all arithmetic of a unit (i8path.cu); i8v2.cu only: 4 no loads,
-                                 // 8 zero operands, 16 MMA warp does not wait for the FP64 burst, 32 TMEM loads only, 64 no TMEM
-                                 // loads, 128 tile-outer FP64 variant
+    int stages;                  // pipeline depth (set by launch_i8_contract)
+    int debug;                   // -DGMS_PROFILE builds only (GMS_I8_DEBUG bit mask; results are garbage): 1 no epilogue arithmetic,
+                                 // 2 no MMAs, 512 release the accumulator after all arithmetic of a unit
 };
 size_t i8_smem_bytes(int T, bool cg2);
 cudaError_t launch_i8_build_xi(const unsigned* planeA, const unsigned* planeB, long long wpp, const int* sire,
                                const int* dam, long long n_units, int mode, long long nkb_total, signed char* xi,
                                cudaStream_t st);
-cudaError_t launch_i8_build_digits(const double* tiles, const ChromDesc* chrom_d, int c_begin, int c_end,
-                                   const int* rowpref_d, int nrows, const int* blkpref_d, int nblks, const double* emat,
-                                   long long mp_total, int T, double* scale, const long long* gbase_d, signed char* G,
-                                   int layout, cudaStream_t st);     // layout: 0 / 1 = i8path.cu (plain / cta_group::2), 2 = i8v2.cu
+cudaError_t launch_i8_build_digits(const double* tiles, const ChromDesc* chrom_d, int c_begin, int c_end, int C,
+                                   const int* blkpref_d, int nblks, const double* emat, long long mp_total, int T,
+                                   double* scale, double* smax, const long long* gbase_d, signed char* G, int layout,
+                                   cudaStream_t st);     // layout: 0 / 1 = plain / cta_group::2; smax[T][C]: see verify.cu
 cudaError_t launch_i8_contract(const I8Params& p, int ntiles, int nsplit, bool pair, cudaStream_t st);
 int i8_npart(int T);        // partial slabs per split written by launch_i8_contract
-// i8v2.cu: 32-row tiles, two TMEM accumulators (epilogue overlapped with the next unit's MMAs), T <= 16; writes
-// i8v2_npart() partial slabs per split. mc: clusters of two CTAs share a cross tile and take one row half each (the grid
-// is then 2 x ntiles wide); mc = false runs both halves in one CTA
-int i8v2_npart(bool mc);
-int i8v2_max_tiles_per_split();       // the plan must cut the 64-row tile list into splits no longer than this
-size_t i8v2_smem_bytes(int T, bool ia);
-// ia: exact integer accumulation of the quadratic forms (T <= 8; needs p.qtab / p.gexp from launch_i8_build_qtab), so that
-// no floating-point instruction runs next to the MMAs
-cudaError_t launch_i8v2_contract(const I8Params& p, int ntiles, int nsplit, bool mc, bool ia, cudaStream_t st);
-cudaError_t launch_i8_build_qtab(const double* emat, const double* scale, long long mp_total, int T, int* gexp, int4* qtab,
-                                 cudaStream_t st);
+int i8_max_tiles_per_split();       // the plan must cut the 64-row tile list into splits no longer than this
+
+// ---- accuracy contract of the int8 path (verify.cu): a-posteriori error bound per unit, list of failing units ----
+struct VerifyParams {
+    const ChromDesc* chrom;
+    int c_begin, c_end, C;
+    const unsigned* planeA;
+    const unsigned* planeB;
+    long long wpp;
+    const int* unit_a;
+    const int* unit_b;
+    long long n_units;
+    int mode;                    // MASK_*
+    const double* emat;          // [T][mp_total] effects of the class
+    long long mp_total;
+    int T;
+    const double* smax;          // [T][C] largest row scale per trait and chromosome (0: all rows zero)
+    const double* table;         // [rows][T][T] symmetric table the units were written to
+    int rows_by_parent;          // table row of unit u: unit_a[u] (per-parent tables) or u (per-cross table)
+    double tau;                  // tolerance on |error| / sqrt(X[t,t] X[s,s])
+    int* counter;                // number of failing units (may exceed cap)
+    int cap;                     // capacity of the lists
+    int* list_a;                 // failing units: parents, table row
+    int* list_b;
+    int* list_row;
+    double* bound_out;           // optional [n_units]: the bound itself (tests, statistics)
+};
+cudaError_t launch_i8_smax(const double* rowmax, const ChromDesc* chrom_d, int c_begin, int c_end, int C, long long mp_total,
+                           int T, double* smax, cudaStream_t st);
+cudaError_t launch_i8_verify(const VerifyParams& p, cudaStream_t st);
 
 // Nsegsnps per cross over words [w_begin, w_end) of the padded axis.
 cudaError_t launch_nseg(const unsigned* planeA, const unsigned* planeB, long long wpp, long long w_begin,
@@ -101,12 +122,12 @@ cudaError_t launch_nseg(const unsigned* planeA, const unsigned* planeB, long lon
 
 // out[x][pair][comp] from the per-parent tables and the per-cross table.
 struct AssembleParams {
-    const double* QA;    // [P'][T][T] additive table of (add, R, delta)
-    const double* PD;    // [P'][T][T] dominance per-parent table of (dom, RoR, het) or NULL
-    const double* QB;    // [P'][T][T] additive table of asub (DirDom VarBV) or NULL
+    const double* QA;    // [P][T][T] additive table of (add, R, delta), indexed by parent id
+    const double* PD;    // [P][T][T] dominance per-parent table of (dom, RoR, het) or NULL
+    const double* QB;    // [P][T][T] additive table of asub (DirDom VarBV) or NULL
     const double* X;     // [N][T][T] per-cross dominance term or NULL
-    const int* sire_slot;  // [N] index into the tables
-    const int* dam_slot;
+    const int* sire;     // [N] parent ids
+    const int* dam;
     const int* pair_t1;  // [npairs]
     const int* pair_t2;
     long long N;

@@ -1,0 +1,149 @@
+// The accuracy contract of the int8 digit-plane path (GMS_MODE_INT8_TENSOR): an a-posteriori error bound per unit
+// (parent or cross), evaluated on the device right after each table, and a list of the units that fail it. The
+// failing units are re-evaluated by the FP64 contraction (contract.cu) in the same stream; see api.cu.
+//
+// Why a bound is needed. The int8 path rounds G_s[j,k] = L'[j,k] e_s[k] to 49 fractional bits RELATIVE TO THE ROW SCALE
+// scale_s[j] = 2^E > max_k |G_s[j,k]| (i8path.cu). That is fixed point, not floating point: a SNP with a huge effect sets the
+// scale of every row it reaches, and a unit in which that SNP does not segregate (mask 0) sums only small terms that
+// each carry the absolute error u * scale_s[j], u = 2^-50 (round to nearest; i8_scale_kernel picks E so that no digit
+// ever needs clamping). For unit x with mask mu in {-1,0,1}^m, row j of the lower block triangle sums over the non-zero
+// mask entries k of its chromosome with k < 64 (floor(j / 64) + 1), at most n_j = (non-zeros before j) + 128 of them, so
+//     |Z[t][s] - exact| <= u * sum_j |e_t[j] mu_j| * scale_s[j] * n_j  <=  u * Smax_s * B_t(x),
+//     B_t(x) = sum_j |e_t[j] mu_j| n_j,   Smax_s = largest row scale of trait s.
+// The table entry is X[t,s] = Z[t][s] + Z[s][t], so a unit PASSES when
+//     2 u * max_t (B_t / sqrt|X[t,t]|) * max_s (Smax_s / sqrt|X[s,s]|)  <=  tau              (tau = 2^-31 ~ 4.7e-10)
+// which implies |error of X[t,s]| <= tau * sqrt(X[t,t] X[s,s]) for every trait pair: every variance to tau relative,
+// every covariance to tau of its variance scale (the guard of tests/util.py:rel_err is 1e-6 of that scale at 1e-9).
+// By Cauchy-Schwarz the same then holds for VarA = (Q_S + Q_D) / 4 and VarD = (P_S + P_D + 2 X) / 16. It is a worst-case
+// bound (all rounding errors maximal and aligned); the error actually made is ~sqrt(n) times smaller. On N(0,1)
+// effects at cassava scale the bound sits at 0.7 % (crosses) - 1.5 % (parents) of tau: nothing fails.
+// A unit also fails when it has >= 16384 non-zero mask entries on one chromosome: beyond that the exact 64-bit
+// recombination of the digit sums (i8ptx.cuh: v2_combine) could overflow.
+#include "kernels.cuh"
+
+namespace gms {
+
+constexpr int VER_THREADS = 128;     // one thread = one unit
+constexpr int VER_TG = 8;            // traits per pass (accumulators in registers)
+constexpr int VER_CH = 512;          // SNPs of |e_t| staged in shared memory per step (8 x 512 doubles = 32 KiB)
+
+// Smax[s][c] = 2^E > max_j rowmax_s[j] over the rows of chromosome c (0 if every row is zero). Runs on the row-maximum
+// buffer BEFORE i8_scale_kernel turns it into scales, with the same frexp rule. grid (C_shard, T).
+__global__ void i8_smax_kernel(const double* __restrict__ rowmax, const ChromDesc* __restrict__ chrom, int c_begin, int C,
+                               long long mp_total, double* __restrict__ smax) {
+    const int c = c_begin + blockIdx.x, s = blockIdx.y;
+    const ChromDesc cd = chrom[c];
+    double mx = 0.0;
+    for (int j = threadIdx.x; j < cd.m; j += blockDim.x) mx = fmax(mx, rowmax[(long long)s * mp_total + cd.pad_off + j]);
+    __shared__ double sh[32];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = mx;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int i = 1; i < (int)(blockDim.x >> 5); ++i) mx = fmax(mx, sh[i]);
+        int e = 0;
+        double v = 0.0;
+        if (mx > 0x1p-900) { const double f = frexp(mx, &e); if (f >= 1.0 - 0x1p-50) ++e; v = ldexp(1.0, e); }   // = i8_scale_kernel's rule
+        smax[(long long)s * C + c] = v;
+    }
+}
+
+__global__ void __launch_bounds__(VER_THREADS) i8_verify_kernel(const VerifyParams p) {
+    __shared__ double se[VER_TG][VER_CH];
+    const long long unit = (long long)blockIdx.x * VER_THREADS + threadIdx.x;
+    const bool live = unit < p.n_units;
+    int pa = 0, pb = 0;
+    if (live) { pa = p.unit_a[unit]; pb = (p.mode == MASK_XI) ? p.unit_b[unit] : 0; }
+    const uint4* A1 = reinterpret_cast<const uint4*>(p.planeA + (long long)pa * p.wpp);
+    const uint4* B1 = reinterpret_cast<const uint4*>(p.planeB + (long long)pa * p.wpp);
+    const uint4* A2 = reinterpret_cast<const uint4*>(p.planeA + (long long)pb * p.wpp);
+    const uint4* B2 = reinterpret_cast<const uint4*>(p.planeB + (long long)pb * p.wpp);
+    const long long row = p.rows_by_parent ? (long long)pa : unit;
+    const double* X = p.table + row * (long long)(p.T * p.T);
+    double amax = 0.0, smax = 0.0;
+    int nnz_max = 0;
+    for (int t0 = 0; t0 < p.T; t0 += VER_TG) {
+        const int ng = min(VER_TG, p.T - t0);
+        double acc[VER_TG];
+#pragma unroll
+        for (int i = 0; i < VER_TG; ++i) acc[i] = 0.0;
+        for (int c = p.c_begin; c < p.c_end; ++c) {
+            const ChromDesc cd = p.chrom[c];
+            int nnz = 0;                                           // non-zero mask entries of this chromosome so far
+            for (int j0 = 0; j0 < cd.mp; j0 += VER_CH) {
+                const int nj = min(VER_CH, cd.mp - j0);            // multiple of 128
+                __syncthreads();
+                for (int i = threadIdx.x; i < VER_TG * nj; i += VER_THREADS) {
+                    const int t = i / nj, j = i - t * nj;
+                    se[t][j] = t < ng ? fabs(p.emat[(long long)(t0 + t) * p.mp_total + cd.pad_off + j0 + j]) : 0.0;
+                }
+                __syncthreads();
+                if (!live) continue;
+                const long long q0 = ((long long)cd.pad_off + j0) >> 7;          // uint4 index (128 SNPs)
+                for (int q = 0; q < nj / 128; ++q) {
+                    const uint4 a = __ldg(A1 + q0 + q), b = __ldg(B1 + q0 + q);
+                    unsigned nzw[4] = {a.x ^ b.x, a.y ^ b.y, a.z ^ b.z, a.w ^ b.w};
+                    if (p.mode == MASK_XI) {
+                        const uint4 a2 = __ldg(A2 + q0 + q), b2 = __ldg(B2 + q0 + q);
+                        nzw[0] &= a2.x ^ b2.x; nzw[1] &= a2.y ^ b2.y; nzw[2] &= a2.z ^ b2.z; nzw[3] &= a2.w ^ b2.w;
+                    }
+#pragma unroll
+                    for (int w = 0; w < 4; ++w) {
+                        unsigned nz = nzw[w];
+                        while (nz) {
+                            const int j = q * 128 + w * 32 + (__ffs(nz) - 1);
+                            nz &= nz - 1;
+                            const double nj_bound = (double)(nnz + 128);          // n_j <= non-zeros before j + 128
+                            ++nnz;
+#pragma unroll
+                            for (int i = 0; i < VER_TG; ++i) acc[i] = fma(se[i][j], nj_bound, acc[i]);
+                        }
+                    }
+                }
+            }
+            nnz_max = max(nnz_max, nnz);
+        }
+        if (live) {
+#pragma unroll
+            for (int i = 0; i < VER_TG; ++i)
+                if (i < ng) {
+                    double sm = 0.0;
+                    for (int c = p.c_begin; c < p.c_end; ++c) sm = fmax(sm, p.smax[(long long)(t0 + i) * p.C + c]);
+                    const double v = fabs(X[(t0 + i) * p.T + (t0 + i)]);
+                    const double r = v > 0.0 ? rsqrt(v) : 0.0;
+                    // zero variance: fine if the unit contributes nothing for this trait, otherwise fail (inf)
+                    amax = fmax(amax, acc[i] > 0.0 ? (v > 0.0 ? acc[i] * r : INFINITY) : 0.0);
+                    smax = fmax(smax, sm > 0.0 ? (v > 0.0 ? sm * r : INFINITY) : 0.0);
+                }
+        }
+    }
+    if (!live) return;
+    const double bound = 2.0 * 0x1p-50 * amax * smax;
+    // NaN-safe: anything that is not provably within tau fails
+    const bool ok = (bound <= p.tau || (amax == 0.0 || smax == 0.0)) && nnz_max < 16384;
+    if (p.bound_out) p.bound_out[unit] = bound;
+    if (!ok) {
+        const int slot = atomicAdd(p.counter, 1);
+        if (slot < p.cap) {
+            p.list_a[slot] = pa;
+            p.list_b[slot] = pb;
+            p.list_row[slot] = (int)row;
+        }
+    }
+}
+
+cudaError_t launch_i8_smax(const double* rowmax, const ChromDesc* chrom_d, int c_begin, int c_end, int C, long long mp_total,
+                           int T, double* smax, cudaStream_t st) {
+    if (c_end <= c_begin) return cudaSuccess;
+    i8_smax_kernel<<<dim3(c_end - c_begin, T), 256, 0, st>>>(rowmax, chrom_d, c_begin, C, mp_total, smax);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_i8_verify(const VerifyParams& p, cudaStream_t st) {
+    if (p.n_units == 0) return cudaSuccess;
+    i8_verify_kernel<<<(unsigned)((p.n_units + VER_THREADS - 1) / VER_THREADS), VER_THREADS, 0, st>>>(p);
+    return cudaGetLastError();
+}
+
+}  // namespace gms

@@ -111,11 +111,24 @@ class CrossVarEngine:
         return mask_ok
 
     def set_mode(self, mode):
-        """"auto" (default: "int8_tensor" when T <= 6, else "fp64"), "fp64" / "dense" (FP64 DMMA contraction),
-        "int8_tensor" (exact int8 digit planes on tcgen05), "map_scan" (map-structured prefix-sum fast
-        path; needs set_genmap() with sorted positions)."""
+        """"auto" (default: "int8_tensor" whenever its operand images fit in HBM, else "fp64"), "fp64" / "dense" (FP64
+        DMMA contraction), "int8_tensor" (int8 digit planes on tcgen05 with an a-posteriori error bound and FP64
+        re-evaluation of the units that fail it), "map_scan" (map-structured prefix-sum fast path; needs set_genmap()
+        with sorted positions)."""
         code = {"dense": 0, "fp64": 0, "map_scan": 1, "int8_tensor": 2, "auto": 3}[mode] if isinstance(mode, str) else int(mode)
         self._ck(self._lib.gms_set_mode(self._h, code))
+
+    def set_int8_tolerance(self, tau):
+        """tau of the int8 error bound (default 2**-33); <= 0 switches the verification off."""
+        self._ck(self._lib.gms_set_int8_tolerance(self._h, float(tau)))
+
+    def set_cache(self, enabled):
+        """Per-handle cache of operand images and per-parent table rows, keyed on a hash of the effects (default on)."""
+        self._ck(self._lib.gms_set_cache(self._h, 1 if enabled else 0))
+
+    def set_parent_shard(self, index, parts):
+        """This rank evaluates slice `index` of `parts` of the per-parent stage (see stage_range / exchange_parents)."""
+        self._ck(self._lib.gms_set_parent_shard(self._h, int(index), int(parts)))
 
     def set_chromosome_shard(self, c_begin, c_end):
         self._ck(self._lib.gms_set_chromosome_shard(self._h, int(c_begin), int(c_end)))
@@ -168,8 +181,65 @@ class CrossVarEngine:
         self._shape = (sire.size, T * (T + 1) // 2, model + 1)
         return self._shape
 
+    def stage_range(self, model, add, dom=None, asub=None, sire=None, dam=None, lo=0, hi=None):
+        """gms_stage_inputs_range: the WHOLE cross list plus this rank's range [lo, hi) of it."""
+        model = MODEL[model] if isinstance(model, str) else int(model)
+        add, T = self._eff(add, self.m)
+        dom, _ = self._eff(dom, self.m)
+        asub, _ = self._eff(asub, self.m)
+        sire = np.ascontiguousarray(sire, dtype=np.int32)
+        dam = np.ascontiguousarray(dam, dtype=np.int32)
+        hi = sire.size if hi is None else int(hi)
+        self._ck(self._lib.gms_stage_inputs_range(self._h, model, T, _ptr(add), _ptr(dom), _ptr(asub), sire.size,
+                                                  _ptr(sire), _ptr(dam), int(lo), hi))
+        self._shape = (hi - int(lo), T * (T + 1) // 2, model + 1)
+        return self._shape
+
     def compute(self, sync=True):
         self._ck(self._lib.gms_compute(self._h, 1 if sync else 0))
+
+    def compute_parents(self):
+        self._ck(self._lib.gms_compute_parents(self._h))
+
+    def parent_exchange(self):
+        """(device pointer, doubles per part, parts) of the exchange buffer of a parent-sharded handle; pointer 0 when
+        no table row had to be computed (all cached)."""
+        ptr, n, parts = C.c_void_p(), C.c_int64(), C.c_int32()
+        self._ck(self._lib.gms_parent_exchange(self._h, C.byref(ptr), C.byref(n), C.byref(parts)))
+        return (ptr.value or 0), int(n.value), int(parts.value)
+
+    def exchange_parents(self, dist, group=None):
+        """One all-gather (NCCL) of the per-parent table slices over `group`, in place in the engine's buffer."""
+        import torch
+        ptr, n, parts = self.parent_exchange()
+        if not ptr or parts <= 1:
+            return
+
+        class _Buf:        # a zero-copy torch view of the library's device buffer
+            __cuda_array_interface__ = {"shape": (parts * n,), "typestr": "<f8", "data": (ptr, False), "version": 3,
+                                        "strides": None}
+        full = torch.as_tensor(_Buf(), device=torch.device("cuda", self.device))
+        rank = dist.get_rank(group)
+        dist.all_gather_into_tensor(full, full[rank * n:(rank + 1) * n], group=group)
+
+    def device_outputs(self):
+        """Zero-copy torch views (float64 [N, npairs, ncomp], int32 [N]) of the result slab and Nsegsnps in HBM."""
+        import torch
+        o, s, n = C.c_void_p(), C.c_void_p(), C.c_int64()
+        self._ck(self._lib.gms_device_outputs(self._h, C.byref(o), C.byref(s), C.byref(n)))
+        N, npairs, ncomp = self._shape
+        dev = torch.device("cuda", self.device)
+        if not n.value:
+            return torch.empty((0, npairs, ncomp), dtype=torch.float64, device=dev), torch.empty(0, dtype=torch.int32, device=dev)
+
+        def view(ptr, shape, typestr):
+            class _Buf:
+                __cuda_array_interface__ = {"shape": shape, "typestr": typestr, "data": (ptr, False), "version": 3, "strides": None}
+            return torch.as_tensor(_Buf(), device=dev)
+        return view(o.value, (N, npairs, ncomp), "<f8"), view(s.value, (N,), "<i4")
+
+    def compute_crosses(self, sync=True):
+        self._ck(self._lib.gms_compute_crosses(self._h, 1 if sync else 0))
 
     def fetch(self, out=None, nseg=None):
         N, npairs, ncomp = self._shape
@@ -202,6 +272,29 @@ class CrossVarEngine:
         self._shape = (N, npairs, ncomp)
         self._ck(self._lib.gms_predict(self._h, model, T, _ptr(add), _ptr(dom), _ptr(asub), N,
                                        _ptr(sire), _ptr(dam), _ptr(out), _ptr(nseg)))
+        return out, nseg
+
+    def predict_batched(self, model, add_sets, dom_sets=None, asub_sets=None, sire=None, dam=None):
+        """gms_predict_batched: several effect sets (cross-validation folds) against one cross list.
+        add_sets: [nsets, m, T]. Returns (out[nsets, N, npairs, ncomp], Nsegsnps[N])."""
+        model = MODEL[model] if isinstance(model, str) else int(model)
+
+        def pack(sets):
+            if sets is None:
+                return None
+            a = np.asarray(sets, dtype=np.float64)
+            if a.ndim != 3 or a.shape[1] != self.m:
+                raise ValueError("effect sets must be [nsets, m, T]")
+            return np.ascontiguousarray(a.transpose(0, 2, 1))        # per set: m x T column-major
+        add, dom, asub = pack(add_sets), pack(dom_sets), pack(asub_sets)
+        nsets, T = add.shape[0], add.shape[1]
+        sire = np.ascontiguousarray(sire, dtype=np.int32)
+        dam = np.ascontiguousarray(dam, dtype=np.int32)
+        N, npairs, ncomp = sire.size, T * (T + 1) // 2, model + 1
+        out = np.empty((nsets, N, npairs, ncomp), np.float64)
+        nseg = np.empty(N, np.int32)
+        self._ck(self._lib.gms_predict_batched(self._h, model, nsets, T, _ptr(add), _ptr(dom), _ptr(asub), N,
+                                               _ptr(sire), _ptr(dam), _ptr(out), _ptr(nseg)))
         return out, nseg
 
     @staticmethod

@@ -62,6 +62,31 @@ class GridLayout:
         return [x * self.chrom_shards for x in range(self.cross_shards)]   # chromosome index 0 of every cross shard
 
 
+_GROUPS = {}
+
+
+def grid_groups(layout, dist):
+    """Process groups of a grid layout, created ONCE per (world, layout) and reused by every later call (new_group is a
+    collective over the whole world and must not sit in a loop). Returns (chromosome groups per cross shard, gather
+    group of the chromosome-index-0 ranks, cross-axis groups per chromosome index)."""
+    key = (dist.get_world_size(), layout.cross_shards, layout.chrom_shards, dist.get_backend())
+    g = _GROUPS.get(key)
+    if g is None:
+        # every rank creates every group, in the same order
+        chrom_groups = [dist.new_group(layout.chrom_group_ranks(x)) for x in range(layout.cross_shards)] \
+            if layout.chrom_shards > 1 else None
+        gather_group = dist.new_group(layout.gather_ranks()) if layout.chrom_shards > 1 else None
+        cross_groups = [dist.new_group([x * layout.chrom_shards + c for x in range(layout.cross_shards)])
+                        for c in range(layout.chrom_shards)] if (layout.chrom_shards > 1 and layout.cross_shards > 1) else None
+        g = _GROUPS[key] = (chrom_groups, gather_group, cross_groups)
+    return g
+
+
+def reset_groups():
+    """Forget cached groups (call after dist.destroy_process_group())."""
+    _GROUPS.clear()
+
+
 def combine(out, nseg, layout, n_total, dist, device=None):
     """Combine per-rank slabs: all-reduce over the chromosome axis, gather over the cross axis.
     `out` [n_local, npairs, ncomp] float64 and `nseg` [n_local] int32 are NumPy arrays; `dist` is
@@ -74,10 +99,7 @@ def combine(out, nseg, layout, n_total, dist, device=None):
     t_seg = torch.from_numpy(np.ascontiguousarray(nseg))
     if device is not None:
         t_out, t_seg = t_out.to(device), t_seg.to(device)
-    # every rank must create every group, in the same order
-    chrom_groups = [dist.new_group(layout.chrom_group_ranks(x)) for x in range(layout.cross_shards)] \
-        if layout.chrom_shards > 1 else None
-    gather_group = dist.new_group(layout.gather_ranks()) if layout.chrom_shards > 1 else None
+    chrom_groups, gather_group, _ = grid_groups(layout, dist)
     if layout.chrom_shards > 1:
         dist.all_reduce(t_out, op=dist.ReduceOp.SUM, group=chrom_groups[xi])
         dist.all_reduce(t_seg, op=dist.ReduceOp.SUM, group=chrom_groups[xi])
@@ -103,13 +125,50 @@ def combine(out, nseg, layout, n_total, dist, device=None):
     return res
 
 
-def predict_sharded(engine, model, add, dom, asub, sire, dam, layout, m_c, dist, device=None):
-    """The hot path on a cross x chromosome grid of ranks. Every rank calls this with the FULL cross list."""
-    rank = dist.get_rank()
+def stage_local(engine, model, add, dom, asub, sire, dam, layout, m_c, dist):
+    """Host -> device for this rank's part of a cross x chromosome grid: chromosome shard, cross range [lo, hi) of the
+    FULL cross list, and the split of the per-parent stage over the ranks that hold the same chromosomes."""
+    rank = dist.get_rank() if layout.world > 1 else 0
     xi, ci = layout.coords(rank)
     if layout.chrom_shards > 1:
         c0, c1 = balance_chromosomes(m_c, layout.chrom_shards)[ci]
         engine.set_chromosome_shard(c0, c1)
     lo, hi = shard_range(len(sire), xi, layout.cross_shards)
-    out, nseg = engine.predict(model, add, dom, asub, np.asarray(sire)[lo:hi], np.asarray(dam)[lo:hi])
+    engine.set_parent_shard(xi if layout.cross_shards > 1 else 0, layout.cross_shards)
+    engine.stage_range(model, add, dom, asub, sire, dam, lo, hi)
+    return lo, hi
+
+
+def compute_local(engine, layout, dist, sync=True, reduce_chromosomes=False):
+    """Device part on the staged inputs: per-parent stage (this rank's slice), ONE all-gather of the table slices over
+    the ranks with the same chromosome index, per-cross stage; optionally the all-reduce(sum) of the partial result
+    slabs over the chromosome axis, in place in the engine's device buffers."""
+    engine.compute_parents()
+    if layout.cross_shards > 1:
+        _, _, cross_groups = grid_groups(layout, dist)
+        ci = layout.coords(dist.get_rank())[1]
+        engine.exchange_parents(dist, cross_groups[ci] if cross_groups is not None else None)
+    engine.compute_crosses(sync=sync and not (reduce_chromosomes and layout.chrom_shards > 1))
+    if reduce_chromosomes and layout.chrom_shards > 1:
+        import torch
+        chrom_groups, _, _ = grid_groups(layout, dist)
+        xi = layout.coords(dist.get_rank())[0]
+        out, nseg = engine.device_outputs()
+        dist.all_reduce(out, op=dist.ReduceOp.SUM, group=chrom_groups[xi])
+        dist.all_reduce(nseg, op=dist.ReduceOp.SUM, group=chrom_groups[xi])
+        if sync:
+            torch.cuda.synchronize()
+
+
+def run_local(engine, model, add, dom, asub, sire, dam, layout, m_c, dist, sync=True):
+    """stage_local + compute_local. Every rank calls this with the FULL cross list. Returns (lo, hi)."""
+    lo, hi = stage_local(engine, model, add, dom, asub, sire, dam, layout, m_c, dist)
+    compute_local(engine, layout, dist, sync=sync)
+    return lo, hi
+
+
+def predict_sharded(engine, model, add, dom, asub, sire, dam, layout, m_c, dist, device=None):
+    """The hot path on a cross x chromosome grid of ranks. Every rank calls this with the FULL cross list."""
+    run_local(engine, model, add, dom, asub, sire, dam, layout, m_c, dist)
+    out, nseg = engine.fetch()
     return combine(out, nseg, layout, len(sire), dist, device)

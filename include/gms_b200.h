@@ -9,8 +9,8 @@
  * host buffers, int status codes, no exceptions across the boundary.
  *
  * Every function returns GMS_OK (0) or a negative GMS_E* code; gms_last_error() gives the text.
- * A handle is bound to ONE CUDA device.  Calls on one handle must be serialised by the caller;
- * different handles may be used from different host threads (one per GPU).
+ * A handle is bound to ONE CUDA device.  Entry points lock the handle (an internal mutex): calls on one
+ * handle from several host threads are serialised, different handles run concurrently (one per GPU).
  * There is NO CPU fallback: without a CUDA device gms_create fails.
  */
 #ifndef GMS_B200_H
@@ -83,19 +83,37 @@ GMS_API int gms_set_recomb_blocks(gms_handle* h, int C, const int64_t* m_c, cons
 GMS_API int gms_set_haplotypes_i32cm(gms_handle* h, int64_t P, int64_t m, const int32_t* hap);
 GMS_API int gms_set_haplotypes_u8rm(gms_handle* h, int64_t P, int64_t m, const uint8_t* hap);
 
-/* Optional: evaluation mode. The default, GMS_MODE_AUTO, uses GMS_MODE_INT8_TENSOR when its operand images fit
- * in HBM (a few GB at cassava scale) and GMS_MODE_DENSE otherwise; both are valid for any symmetric recombFreqMat and agree to FP64 rounding.
- * GMS_MODE_DENSE is the dense FP64 tensor (DMMA) contraction against the stored R / RoR blocks. GMS_MODE_MAP_SCAN is the map-structured
- * fast path: when the blocks came from gms_set_genmap() with positions sorted within each
- * chromosome, R[j,k] = exp(-2|x_j-x_k|/100) factorises and every quadratic form becomes a prefix-sum
- * scan over the non-zero SNPs of a unit (O(m T^2) per cross instead of O(m^2 T)); same results to ~1e-13.
- * Returns GMS_ESTATE if the handle's blocks did not come from a sorted map.
- * GMS_MODE_INT8_TENSOR (any symmetric matrix, any model, T <= 32): the per-cross dominance contraction runs
- * on the int8 tcgen05 tensor cores - RoR.d is split into 7 exact radix-128 int8 digit planes, xi is ternary,
- * int32 accumulation in TMEM is exact, digits are recombined in FP64 (error <= 2^-49 of the row maximum).
- * All tables (per parent and per cross) use it. Falls back to GMS_MODE_DENSE if the images would not fit. */
+/* Optional: evaluation mode.
+ * GMS_MODE_DENSE: the dense FP64 tensor (DMMA) contraction against the stored R / RoR blocks; any symmetric recombFreqMat.
+ * GMS_MODE_INT8_TENSOR (any symmetric matrix, any model, T <= 32): all contractions run on the int8 tcgen05 tensor cores.
+ *   G = (R or RoR) . diag(effects) is rounded, row by row, to 49 bits below a power-of-two ROW scale (>= the row's largest
+ *   |entry|) and split into 7 radix-128 int8 digit planes; the masks are ternary; int32 accumulation in TMEM is exact; the
+ *   digits are recombined exactly and scaled in FP64. This is FIXED POINT relative to the row maximum, so its accuracy
+ *   depends on the data: a SNP with a huge effect that does not segregate in a cross leaves an absolute error of
+ *   2^-50 x (row scale) on terms that may be many orders of magnitude smaller. THE CONTRACT: every table (per parent, per
+ *   cross) is followed on the device by a worst-case a-posteriori bound of that error (csrc/verify.cu); a unit passes when
+ *   the bound is at most tau x sqrt(X[t,t] X[s,s]) for every trait pair (tau = 2^-31 ~ 4.7e-10 by default,
+ *   gms_set_int8_tolerance), i.e. every variance is good to tau relative and every covariance to tau of its variance scale. Units that fail (and units with
+ *   >= 16384 non-zero mask entries on one chromosome, where the 64-bit digit recombination could overflow) are
+ *   re-evaluated by the FP64 contraction inside the same call, at most 16384 per table in-stream; if more fail, the whole
+ *   call is redone with GMS_MODE_DENSE (gms_stats.last_fallback_units / last_fallback_overflow report both). Results
+ *   therefore meet the 1e-9 contract for ANY finite input; only the speed is data dependent.
+ * GMS_MODE_AUTO (default): GMS_MODE_INT8_TENSOR when its operand images fit in HBM (a few GB at cassava scale), else
+ *   GMS_MODE_DENSE.
+ * GMS_MODE_MAP_SCAN: the map-structured fast path: when the blocks came from gms_set_genmap() with positions
+ *   sorted within each chromosome, R[j,k] = exp(-2|x_j-x_k|/100) factorises and every quadratic form becomes a prefix-sum
+ *   scan over the non-zero SNPs of a unit (O(m T^2) per cross instead of O(m^2 T)); same results to ~1e-13. Returns
+ *   GMS_ESTATE if the handle's blocks did not come from a sorted map. */
 enum { GMS_MODE_DENSE = 0, GMS_MODE_MAP_SCAN = 1, GMS_MODE_INT8_TENSOR = 2, GMS_MODE_AUTO = 3 };
 GMS_API int gms_set_mode(gms_handle* h, int mode);
+/* tau of the int8 error bound (see above). tau <= 0 switches the verification off (benchmarks of its cost only). */
+GMS_API int gms_set_int8_tolerance(gms_handle* h, double tau);
+
+/* Per-handle cache (default on). The handle remembers a hash of the last effects: a later call with the same effects,
+ * model, T and mode reuses the operand images in HBM and every per-parent table row it already has, and computes rows
+ * only for parents it has not seen (mate-selection loops evaluate many candidate cross lists against one set of marker
+ * effects; R/predCrossVar.R:44-46 subsets haploMat per call instead). enabled = 0: every call recomputes everything. */
+GMS_API int gms_set_cache(gms_handle* h, int enabled);
 
 /* Optional chromosome shard: this handle only sums over chromosomes [c_begin, c_end).  Outputs of
  * gms_predict are then PARTIAL sums (variances and Nsegsnps are additive over chromosomes); the
@@ -147,6 +165,33 @@ GMS_API int gms_stage_inputs(gms_handle* h, int model, int T,
 GMS_API int gms_compute(gms_handle* h, int sync);
 GMS_API int gms_fetch_outputs(gms_handle* h, double* out, int32_t* nseg);
 
+/* ---- multi-GPU, one process per GPU -----------------------------------------------
+ * Every rank passes the WHOLE cross list and its own contiguous range [x_begin, x_end) of it; outputs have
+ * x_end - x_begin rows. With gms_set_parent_shard(h, rank, nranks) the per-parent stage is split as well: the parents
+ * of the whole list (the same on every rank) are cut into nranks contiguous slices, gms_compute_parents evaluates this
+ * rank's slice and packs it into an exchange buffer, the host all-gathers the slices (one ncclAllGather of
+ * doubles_per_part doubles per rank, in place in *dev_buf; NULL / 0 when nothing had to be computed), and
+ * gms_compute_crosses unpacks them and runs the per-cross stage. gms_compute = both phases on an unsharded handle. */
+GMS_API int gms_stage_inputs_range(gms_handle* h, int model, int T,
+                     const double* add, const double* dom, const double* asub,
+                     int64_t N, const int32_t* sire, const int32_t* dam, int64_t x_begin, int64_t x_end);
+GMS_API int gms_set_parent_shard(gms_handle* h, int index, int parts);
+GMS_API int gms_compute_parents(gms_handle* h);
+GMS_API int gms_parent_exchange(gms_handle* h, void** dev_buf, int64_t* doubles_per_part, int32_t* parts);
+GMS_API int gms_compute_crosses(gms_handle* h, int sync);
+/* Device addresses of the result slab (N x npairs x ncomp doubles) and of Nsegsnps (N int32) of the last compute, valid
+ * until the next stage call: lets a multi-GPU host reduce chromosome-sharded partial slabs in place (ncclAllReduce)
+ * before gms_fetch_outputs copies them out. Work queued on the handle's stream may still be writing them. */
+GMS_API int gms_device_outputs(gms_handle* h, void** out_dev, void** nseg_dev, int64_t* n_rows);
+
+/* Cross-validation batching (R/parentWiseCrossVal.R:430-490 calls the path once per (Repeat, Fold) on the same haploMat,
+ * recombFreqMat and - per fold - the same crosses): nsets effect sets against ONE cross list in one call.
+ * add / dom / asub: nsets consecutive m x T column-major matrices; out: nsets consecutive N x npairs x ncomp slabs;
+ * nseg: N (the same for every set). Cross-side device state (cross lists, mask images) is staged once. */
+GMS_API int gms_predict_batched(gms_handle* h, int model, int nsets, int T,
+                     const double* add, const double* dom, const double* asub,
+                     int64_t N, const int32_t* sire, const int32_t* dam, double* out, int32_t* nseg);
+
 /* ---- "next" rows of the scope table ---------------------------------------------
  * gms_selind: selection-index variance w'Gw per cross and component from an `out` slab
  *   (R/gmsFunctions.R:825-853).  w[T]; si[N x ncomp].  Host-side O(N T^2).
@@ -180,6 +225,10 @@ typedef struct gms_stats {
     float   last_ms_total;        /* whole gms_compute                                     */
     double  last_flops_cross;     /* FP64 flops EXECUTED by the cross contraction launch   */
     double  last_flops_parent;    /* FP64 flops executed by the per-parent launches        */
+    int64_t last_fallback_units;  /* units (parents + crosses) that failed the int8 error bound and were re-evaluated in FP64 */
+    int64_t last_parents_computed;/* per-parent table rows this handle computed in the last call (cache, parent shard) */
+    int32_t last_fallback_overflow; /* 1: more units failed than the in-stream lists hold; the call was redone in GMS_MODE_DENSE */
+    int32_t last_cache_hit;       /* 1: same effects as the previous call: operand images and cached table rows reused */
 } gms_stats;
 GMS_API int gms_get_stats(gms_handle* h, gms_stats* s);
 

@@ -22,9 +22,13 @@
 #include <omp.h>
 #endif
 
-/* recombFreqMat access: either one dense column-major m x m matrix, or its diagonal blocks (entries
- * outside the blocks are exactly 0, as in 1-2*genmap2recombfreq()). */
+/* recombFreqMat access: one dense column-major m x m matrix, or its diagonal blocks (entries
+ * outside the blocks are exactly 0, as in 1-2*genmap2recombfreq()), or the genetic map itself: then an
+ * entry is what R/helpers.R:204-213 plus the caller's 1-(2*c1) (vignettes/start_here.Rmd:112) would have
+ * stored, evaluated on the fly in the same operation order (for chromosomes whose matrix does not fit). */
 typedef struct {
+    const double* cM;               /* map positions (with chr), or NULL */
+    const int32_t* chr;
     const double* dense;            /* m x m column-major, or NULL */
     int C;                          /* number of blocks */
     const int64_t* off;             /* C+1 block boundaries on the SNP axis */
@@ -33,6 +37,12 @@ typedef struct {
 } rmat;
 
 static inline double r_at(const rmat* R, const int32_t* blk, int64_t j, int64_t k) {
+    if (R->cM) {
+        if (R->chr[j] != R->chr[k]) return 1.0 - (2.0 * 0.5);            /* c1 = 0.5 across chromosomes  :208-211 */
+        const double d = fabs(R->cM[j] - R->cM[k]);                       /* dist(m, "manhattan")          :205 */
+        const double c1 = 0.5 * (1.0 - exp(-2.0 * (d / 100.0)));          /*                               :206 */
+        return 1.0 - (2.0 * c1);
+    }
     if (R->dense) return R->dense[j + R->m * k];
     const int32_t c = blk[j];
     if (c != blk[k]) return 0.0;
@@ -45,14 +55,15 @@ static inline double r_at(const rmat* R, const int32_t* blk, int64_t j, int64_t 
  * Returns 0, or -1 on allocation failure. */
 int gmsref_pred_one_cross(int64_t m, const uint8_t* s0, const uint8_t* s1, const uint8_t* d0, const uint8_t* d1,
                           const double* Rdense, int C, const int64_t* off, const double* const* blocks,
+                          const double* cM, const int32_t* chr,
                           int model_ad, int T, const double* add, const double* dom,
                           double* out, int32_t* nseg_out, int nthreads) {
-    rmat R = {Rdense, C, off, blocks, m};
+    rmat R = {cM, chr, Rdense, C, off, blocks, m};
     const int npairs = T * (T + 1) / 2, ncomp = model_ad ? 2 : 1;
     int64_t* seg = (int64_t*)malloc(sizeof(int64_t) * (size_t)m);
     int32_t* blk = (int32_t*)malloc(sizeof(int32_t) * (size_t)m);
     if (!seg || !blk) { free(seg); free(blk); return -1; }
-    for (int c = 0; c < C && !Rdense; ++c)
+    for (int c = 0; c < C && !Rdense && !cM; ++c)
         for (int64_t j = off[c]; j < off[c + 1]; ++j) blk[j] = c;
     int64_t ns = 0;
     for (int64_t j = 0; j < m; ++j) {                       /* R/predCrossVar.R:111-113 */

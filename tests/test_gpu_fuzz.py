@@ -108,15 +108,11 @@ def test_one_engine_many_calls():
 @pytest.mark.parametrize("env", [
     {"GMS_I8_CG2": "0"},                                            # one CTA per 128 crosses
     {"GMS_I8_CG2": "1"},                                            # the default: tcgen05 cta_group::2 pairs (M = 256)
-    {"GMS_I8_V2": "1", "GMS_I8_IA": "0"},                           # i8v2.cu, FP64 burst in an MMA gap, xi multicast
-    {"GMS_I8_V2": "1", "GMS_I8_IA": "0", "GMS_I8_MC": "0"},         # the same without clusters
-    {"GMS_I8_V2": "1", "GMS_I8_IA": "1"},                           # i8v2.cu, exact integer accumulation
-], ids=["plain", "cta_group2", "v2_fp64", "v2_fp64_nomc", "v2_int"])
+], ids=["plain", "cta_group2"])
 @pytest.mark.parametrize("T", [1, 3, 5, 6, 7])
 def test_int8_kernel_variants(monkeypatch, env, T):
-    """Every variant of the int8 tcgen05 kernel (environment switches read at gms_create) against the oracle: the default
-    (cta_group::2 pairs, each CTA staging half of the digit operand), the single-CTA kernel, and the opt-in second-generation
-    kernel (32-row tiles, two TMEM accumulators) in its FP64 and integer-accumulating forms."""
+    """Both launch forms of the int8 tcgen05 kernel (environment switch read at gms_create) against the oracle: the default
+    (cta_group::2 pairs, each CTA staging half of the digit operand) and the single-CTA form."""
     import genomicmateselectr_b200 as g
     for k, v in env.items():
         monkeypatch.setenv(k, v)
@@ -155,10 +151,12 @@ def test_int8_cross_chunking(monkeypatch):
 
 def test_int8_long_work_list():
     """One 40,000-SNP chromosome (625 64-row tiles) and enough crosses that the plan would use ONE range of tiles per CTA:
-    the kernels keep their range of the work list in shared memory (512 entries), so the plan must cut it. No CPU oracle at
-    this size (a 12.8 GB matrix): the int8 tensor path must agree with the map-structured scan, which shares none of its code,
-    and a sample of crosses must not depend on how many crosses are predicted with them (different plan)."""
+    the kernels keep their range of the work list in shared memory (512 entries), so the plan must cut it. A sample of
+    crosses is checked against the oracle's C restatement with the matrix entries evaluated from the map (the 12.8 GB
+    matrix itself is never formed), in the default mode and in FP64; the sample must also not depend on how many crosses
+    are predicted with it (different plan)."""
     import genomicmateselectr_b200 as g
+    from tests.util import oracle_slab_c
     rng = np.random.default_rng(11)
     m, P, T, N = 40000, 24, 2, 38400
     cM = np.sort(rng.uniform(0, 300, m))
@@ -166,16 +164,19 @@ def test_int8_long_work_list():
     add, dom = rng.standard_normal((m, T)), rng.standard_normal((m, T))
     sire = rng.integers(0, P, N).astype(np.int32)
     dam = rng.integers(0, P, N).astype(np.int32)
+    pick = np.array([0, 299, 17000, N - 1])
+    want, wseg = oracle_slab_c("AD", H, add, dom, None, sire[pick], dam[pick], cM=cM, chrom=np.ones(m, np.int32))
     with g.CrossVarEngine(0) as eng:
         eng.set_genmap(cM, np.array([m]))
         eng.set_haplotypes(H)
         eng.set_mode("int8_tensor")
         out, nseg = eng.predict("AD", add, dom, None, sire, dam)
-        assert eng.stats()["last_mode"] == 2
+        st = eng.stats()
+        assert st["last_mode"] == 2 and st["last_fallback_overflow"] == 0
         few, nfew = eng.predict("AD", add, dom, None, sire[:300], dam[:300])
-        eng.set_mode("map_scan")
-        ref, nref = eng.predict("AD", add, dom, None, sire, dam)
-    assert np.array_equal(nseg, nref) and np.array_equal(nfew, nseg[:300])
-    assert rel_err(out, ref) < 1e-9
+        eng.set_mode("fp64")
+        o64, n64 = eng.predict("AD", add, dom, None, sire[pick], dam[pick])
+    assert np.array_equal(nseg[pick], wseg) and np.array_equal(nfew, nseg[:300]) and np.array_equal(n64, wseg)
+    assert rel_err(out[pick], want) < 1e-9
+    assert rel_err(o64, want) < 1e-9
     assert rel_err(few, out[:300]) < 1e-12
-

@@ -244,31 +244,88 @@ def test_invariances(gms, mode):
 
 
 # ---------------------------------------------------------------- BASELINE.json full size
-def test_cassava_scale_against_blockwise_oracle(gms, mode):
-    """configs[3]: 1000 parents, 33k SNPs / 18 chromosomes, 5 traits, AD.  A handful of crosses is
-    checked against the oracle evaluated chromosome by chromosome; the whole batch is checked through
-    invariants (self-cross rows = twice the gametic part, duplicate rows identical)."""
+@pytest.fixture(scope="module")
+def cassava():
+    """configs[3]: 1000 parents, 33k SNPs / 18 chromosomes, 5 traits, AD. 40 crosses of the benchmark's own 50,000
+    (32 random ones, the first, the last, and the first selfs) evaluated by the oracle's C restatement of the reference
+    algorithm (dense m_seg x m_seg cross LD matrix; matrix entries from the map, R/helpers.R:204-213)."""
     from genomicmateselectr_b200 import synth as S
-    d = S.make("cassava", N=2000)
+    from tests.util import oracle_slab_c
+    d = S.make("cassava")
+    rng = np.random.default_rng(2026)
+    selfs = np.flatnonzero(d["sire"] == d["dam"])[:6]
+    pick = np.unique(np.concatenate([rng.choice(d["N"], 32, replace=False), [0, d["N"] - 1], selfs]))
+    offs = np.concatenate([[0], np.cumsum(d["m_c"])])
+    blocks = [O.recombfreq_to_ld_decay(O.genmap2recombfreq(d["cM"][a:b], np.ones(b - a))) for a, b in zip(offs[:-1], offs[1:])]
+    want, wseg = oracle_slab_c("AD", d["H"], d["add"], d["dom"], None, d["sire"][pick], d["dam"][pick], blocks=blocks)
+    return d, pick, want, wseg
+
+
+def test_cassava_scale_against_the_oracle(gms, cassava, mode):
+    """The whole 50,000-cross batch of the benchmark in both modes; the sampled crosses against the oracle, the whole
+    batch through invariants (finite, positive variances, duplicates of a sampled cross identical)."""
+    d, pick, want, wseg = cassava
+    assert len(pick) >= 34
     eng = gms.CrossVarEngine(0)
     eng.set_mode(mode)
     eng.set_genmap(d["cM"], d["m_c"])
     eng.set_haplotypes(d["H"])
-    out, nseg = eng.predict("AD", d["add"], d["dom"], None, d["sire"], d["dam"])
+    N = d["N"] if mode == "auto" else 4000                  # the FP64 contraction is 12x slower: a 4,000-cross batch
+    idx = np.concatenate([pick, np.setdiff1d(np.arange(N), pick)[: N - len(pick)]])
+    out, nseg = eng.predict("AD", d["add"], d["dom"], None, d["sire"][idx], d["dam"][idx])
+    st = eng.stats()
     assert np.all(np.isfinite(out)) and np.all(nseg > 0)
     assert np.all(out[:, :5, :] > 0)                       # variances are positive
-    pick = [0, 1, 1999]
-    offs = np.concatenate([[0], np.cumsum(d["m_c"])])
-    blocks, ranges = [], []
-    for c in range(len(d["m_c"])):
-        a, b = int(offs[c]), int(offs[c + 1])
-        cm = d["cM"][a:b]
-        blocks.append(O.recombfreq_to_ld_decay(O.genmap2recombfreq(cm, np.ones(b - a))))
-        ranges.append((a, b))
-    want, wseg = oracle_slab_blockwise("AD", d["H"], blocks, ranges, d["add"], d["dom"], None,
-                                       d["sire"][pick], d["dam"][pick])
-    assert np.array_equal(nseg[pick], wseg)
-    assert rel_err(out[pick], want) < TOL
+    assert np.array_equal(nseg[: len(pick)], wseg)
+    assert rel_err(out[: len(pick)], want) < TOL
+    from tests.util import strict_rel_err
+    assert strict_rel_err(out[: len(pick)], want) < TOL
+    if mode == "auto":
+        assert st["last_mode"] == 2 and st["last_fallback_units"] == 0     # N(0,1) effects: nothing fails the error bound
+    eng.close()
+
+
+@pytest.fixture(scope="module")
+def large_geometry():
+    """configs[4] geometry: chromosomes of 5,556 and 5,555 SNPs (87 k-blocks per row), T = 10 (the trait-outer kernel
+    template), parent ids spread over a 5,000-parent index space; 10 crosses against the oracle's C restatement."""
+    from tests.util import oracle_slab_c
+    rng = np.random.default_rng(20261119)
+    m_c = np.array([5556, 5555])
+    m, P, T = int(m_c.sum()), 5000, 10
+    cM = np.concatenate([np.sort(rng.uniform(0.0, 130.0, int(k))) for k in m_c])
+    chrom = np.repeat([1, 2], m_c).astype(np.int32)
+    p = rng.uniform(0.05, 0.95, m).astype(np.float32)
+    H = np.empty((2 * P, m), np.uint8)
+    for a in range(0, 2 * P, 500):
+        H[a:a + 500] = rng.random((500, m), dtype=np.float32) < p[None, :]
+    add = rng.standard_normal((m, T))
+    dom = 0.5 * rng.standard_normal((m, T))
+    sire = np.array([0, 17, 2500, 4999, 4999, 1234, 77, 3001, 4242, 9], np.int32)
+    dam = np.array([4999, 17, 2501, 0, 4999, 4321, 78, 3001, 13, 4998], np.int32)
+    blocks = [O.recombfreq_to_ld_decay(O.genmap2recombfreq(cM[a:b], np.ones(b - a))) for a, b in ((0, 5556), (5556, m))]
+    want, wseg = oracle_slab_c("AD", H, add, dom, None, sire, dam, blocks=blocks)
+    return dict(m_c=m_c, cM=cM, H=H, add=add, dom=dom, sire=sire, dam=dam, P=P), want, wseg
+
+
+def test_large_config_geometry_against_the_oracle(gms, large_geometry, mode):
+    s, want, wseg = large_geometry
+    eng = gms.CrossVarEngine(0)
+    eng.set_mode(mode)
+    eng.set_genmap(s["cM"], s["m_c"])
+    eng.set_haplotypes(s["H"])
+    out, nseg = eng.predict("AD", s["add"], s["dom"], None, s["sire"], s["dam"])
+    st = eng.stats()
+    assert st["last_mode"] == (2 if mode == "auto" else 0)
+    assert np.array_equal(nseg, wseg)
+    from tests.util import strict_rel_err
+    assert rel_err(out, want) < TOL and strict_rel_err(out, want) < TOL
+    # the same crosses inside a larger batch (more cross tiles, another plan) give the same numbers
+    rng = np.random.default_rng(5)
+    sire = np.concatenate([s["sire"], rng.integers(0, s["P"], 500).astype(np.int32)])
+    dam = np.concatenate([s["dam"], rng.integers(0, s["P"], 500).astype(np.int32)])
+    big, nbig = eng.predict("AD", s["add"], s["dom"], None, sire, dam)
+    assert np.array_equal(nbig[:10], wseg) and rel_err(big[:10], want) < TOL
     eng.close()
 
 

@@ -45,3 +45,24 @@ def test_c_oracle_block_form_equals_dense_form(model):
         o2, n2 = blk.one_cross(s, d, model, nthreads=3)
         assert n1 == n2 == wseg[x]
         assert np.allclose(o1, want[x], rtol=1e-12, atol=0) and np.allclose(o2, want[x], rtol=1e-12, atol=0)
+
+
+@pytest.mark.parametrize("model", ["A", "AD", "DirDom"])
+def test_c_oracle_map_form_equals_numpy_oracle(model):
+    """recombFreqMat given as the genetic map (entries of 1-2*genmap2recombfreq() evaluated on the fly): what the
+    full-size parity tests use where the m x m matrix would not fit."""
+    from tests.util import oracle_slab_c
+    rng = np.random.default_rng(4)
+    m_c = [120, 75, 33]
+    m = sum(m_c)
+    cM = np.concatenate([np.sort(rng.uniform(0, 100, k)) for k in m_c])
+    chrom = np.repeat([1, 2, 3], m_c)
+    R = O.recombfreq_to_ld_decay(O.genmap2recombfreq(cM, chrom))
+    H = (rng.random((12, m)) < 0.5).astype(np.uint8)
+    add, dom = rng.standard_normal((m, 3)), rng.standard_normal((m, 3))
+    asub = add + 0.2 * dom
+    sire, dam = [0, 1, 5, 2], [3, 1, 2, 2]
+    want, wseg = oracle_slab(model, H, R, add, dom if model != "A" else None, asub if model == "DirDom" else None, sire, dam)
+    got, nseg = oracle_slab_c(model, H, add, dom, asub, sire, dam, cM=cM, chrom=chrom, nthreads=2)
+    assert np.array_equal(nseg, wseg)
+    assert np.allclose(got, want, rtol=1e-12, atol=0)

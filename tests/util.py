@@ -52,6 +52,37 @@ def oracle_slab_blockwise(model, H, blocks, offs, add, dom, asub, sire, dam):
     return tot, nseg
 
 
+def oracle_slab_c(model, H, add, dom, asub, sire, dam, R=None, blocks=None, cM=None, chrom=None, nthreads=0):
+    """out[N, npairs, ncomp], nseg[N] from the oracle's C restatement (oracle/crossvar_ref.c: the reference's dense
+    m_seg x m_seg formulation, OpenMP) - for problem sizes where the NumPy oracle would take minutes per cross."""
+    from oracle import crossvar_ref as CR
+    ad = model != "A"
+    prob = CR.RefProblem(H, add, dom if ad else None, R=R, blocks=blocks, cM=cM, chrom=chrom)
+    prob2 = CR.RefProblem(H, asub, None, R=R, blocks=blocks, cM=cM, chrom=chrom) if model == "DirDom" else None
+    T = add.shape[1]
+    ncomp = {"A": 1, "AD": 2, "DirDom": 3}[model]
+    out = np.zeros((len(sire), T * (T + 1) // 2, ncomp))
+    nseg = np.zeros(len(sire), np.int32)
+    for x, (s, d) in enumerate(zip(sire, dam)):
+        o, n = prob.one_cross(int(s), int(d), "AD" if ad else "A", nthreads)
+        out[x, :, : o.shape[1]] = o
+        nseg[x] = n
+        if prob2 is not None:      # second predCrossVars call of R/gmsFunctions.R:712-718
+            o2, _ = prob2.one_cross(int(s), int(d), "A", nthreads)
+            out[x, :, 2] = o2[:, 0]
+    return out, nseg
+
+
+def strict_rel_err(got, want):
+    """max |got-want| / |want| over the VARIANCES (the first T pairs of every cross): no guard at all."""
+    got = np.asarray(got, dtype=np.float64)
+    want = np.asarray(want, dtype=np.float64)
+    T = int((np.sqrt(8 * want.shape[1] + 1) - 1) / 2)
+    g, w = got[:, :T, :], want[:, :T, :]
+    denom = np.where(w == 0, 1.0, np.abs(w))
+    return float(np.max(np.abs(g - w) / denom))
+
+
 def rel_err(got, want):
     """max |got-want| / |want| with the guard the north-star tolerance implies: entries that are
     tiny by cancellation are measured against sqrt(var_t1 * var_t2) of the same cross/component."""
