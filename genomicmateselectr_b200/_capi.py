@@ -62,6 +62,7 @@ _SIGS = {
     "gms_compute": (C.c_int, [_P, C.c_int]),
     "gms_fetch_outputs": (C.c_int, [_P, _P, _P]),
     "gms_selind": (C.c_int, [C.c_int, C.c_int, C.c_int64, _P, _P, _P]),
+    "gms_tidy": (C.c_int, [_P, _P, C.c_double, _P]),
     "gms_cross_means": (C.c_int, [_P, C.c_int, _P, _P, C.c_int64, _P, _P, _P, _P, _P]),
     "gms_get_stats": (C.c_int, [_P, C.POINTER(Stats)]),
 }

@@ -99,7 +99,7 @@ struct gms_handle {
     long long N = 0;                   // crosses of THIS handle (its range of the staged list)
     EffClass cls[3];
     DevBuf<int> sire_d, dam_d, pair1_d, pair2_d, split_par_d, split_x_d, split_fb_d, flag_d;
-    DevBuf<double> Z, Zfb, X, out_d, gebv_d, mean_d, cm_add, cm_dom, cm_raw;
+    DevBuf<double> Z, Zfb, X, out_d, gebv_d, mean_d, cm_add, cm_dom, cm_raw, tidy_d;
     DevBuf<int> nseg_d;
     Plan plan_par, plan_x, plan_fb;
     int stages = 0;
@@ -132,7 +132,8 @@ struct gms_handle {
     bool xi_image_valid = false;       // the per-cross xi image in xi_d belongs to the staged cross list (single pass only)
     double tau = 0x1p-31;              // int8 error-bound tolerance (gms_set_int8_tolerance); <= 0: no verification
     int fb_cap = 0;
-    DevBuf<int> fb_counter, fb_a, fb_b, fb_row;
+    DevBuf<int> fb_counter, fb_a, fb_b, fb_row, ver_n;
+    DevBuf<double> ver_b;
     int n_counters = 0;
     std::vector<int> counters_h;
     int i8_debug = 0;
@@ -404,8 +405,9 @@ int verify_and_repair(gms_handle* h, const EffClass& cl, const double* tiles, in
     v.table = table; v.rows_by_parent = rows_by_parent ? 1 : 0; v.tau = h->tau;
     v.counter = h->fb_counter.p + counter_idx; v.cap = h->fb_cap;
     v.list_a = h->fb_a.p; v.list_b = h->fb_b.p; v.list_row = h->fb_row.p;
+    v.part_b = h->ver_b.p; v.part_n = h->ver_n.p;
     CU(launch_i8_verify(v, h->stream));
-    h->st.last_launches += 1;
+    h->st.last_launches += 2;
     return run_contract(h, tiles, cl.emat.p, mode, h->fb_a.p, h->fb_b.p, h->fb_cap, h->plan_fb, h->split_fb_d.p, h->Zfb.p, table,
                         h->fb_row.p, h->fb_counter.p + counter_idx);
 }
@@ -683,6 +685,8 @@ int stage_impl(gms_handle* h, int model, int T, const double* add, const double*
         if (int rc = upload_plan(h, h->plan_fb, h->split_fb_d)) return rc;
         CU(h->Zfb.ensure((size_t)h->plan_fb.nsplit * h->fb_cap * TT));
         CU(h->fb_a.ensure(h->fb_cap)); CU(h->fb_b.ensure(h->fb_cap)); CU(h->fb_row.ensure(h->fb_cap));
+        CU(h->ver_b.ensure(i8_verify_scratch_doubles(most, h->c_end - h->c_begin, T)));
+        CU(h->ver_n.ensure((size_t)most * (h->c_end - h->c_begin)));
         const long long npass = model >= GMS_MODEL_AD && N > 0 ? (N + chunk - 1) / chunk : 0;
         h->n_counters = 3 + (int)npass;
         CU(h->fb_counter.ensure(h->n_counters));
@@ -963,10 +967,10 @@ void gms_destroy(gms_handle* h) {
         h->rowtiles_d.release(); h->sire_d.release(); h->dam_d.release(); h->pair1_d.release(); h->pair2_d.release();
         h->split_par_d.release(); h->split_x_d.release(); h->split_fb_d.release(); h->flag_d.release();
         h->Z.release(); h->Zfb.release(); h->X.release(); h->out_d.release(); h->gebv_d.release(); h->mean_d.release();
-        h->cm_add.release(); h->cm_dom.release(); h->cm_raw.release(); h->nseg_d.release(); h->todo_d.release(); h->xbuf.release();
+        h->cm_add.release(); h->cm_dom.release(); h->cm_raw.release(); h->tidy_d.release(); h->nseg_d.release(); h->todo_d.release(); h->xbuf.release();
         h->jtiles_d.release(); h->gbase_d.release(); h->xi_d.release(); h->xi_het_d.release(); h->xi_delta_d.release();
         h->split_i8_d.release(); h->split_i8_par_d.release(); h->split_i8_tail_d.release(); h->i8_blkpref_d.release();
-        h->fb_counter.release(); h->fb_a.release(); h->fb_b.release(); h->fb_row.release();
+        h->fb_counter.release(); h->fb_a.release(); h->fb_b.release(); h->fb_row.release(); h->ver_n.release(); h->ver_b.release();
         h->scan_ab.release(); h->split_scan_par_d.release(); h->split_scan_x_d.release();
         for (auto& ev : h->ev) if (ev) cudaEventDestroy(ev);
         if (h->own_stream) cudaStreamDestroy(h->own_stream);
@@ -1404,6 +1408,40 @@ int gms_cross_means(gms_handle* h, int T, const double* add, const double* dom, 
         for (int64_t x = 0; x < N; ++x)
             for (int t = 0; t < T; ++t)
                 mean_bv[x * T + t] = (g[(size_t)sire[x] * T + t] + g[(size_t)dam[x] * T + t]) / 2.0;   // R/predCrossVar.R:369
+    return GMS_OK;
+}
+
+int gms_tidy(gms_handle* h, const double* si_weights, double std_sel_int, double* tidy) {
+    if (!h) return GMS_EINVAL;
+    LOCK(h);
+    if (!h->computed) return fail(h, GMS_ESTATE, "gms_compute has not been called");
+    if (!tidy && h->N > 0) return fail(h, GMS_EINVAL, "tidy is NULL");
+    if (int rc = bind(h)) return rc;
+    CU(cudaStreamSynchronize(h->stream));
+    if (int rc = settle(h)) return rc;
+    if (h->N == 0) return GMS_OK;
+    const int T = h->T, nof = h->model == GMS_MODEL_A ? 1 : 2, ntr = T + (si_weights ? 1 : 0);
+    // means from the effects already in HBM: MeanBV from the allele-substitution class, MeanTGV (DirDom) from (add, dom)
+    const EffClass& bvc = h->cls[h->model == GMS_MODEL_DIRDOM ? 2 : 0];
+    CU(h->gebv_d.ensure((size_t)h->P * T));
+    CU(launch_gebv(h->planeA.p, h->planeB.p, h->wpp, nullptr, h->P, bvc.emat.p, h->mp_total, T, h->gebv_d.p, h->stream));
+    if (h->model == GMS_MODEL_DIRDOM) {
+        CU(h->mean_d.ensure((size_t)h->N * T));
+        CU(launch_tgv_mean(h->planeA.p, h->planeB.p, h->wpp, h->sire_d.p, h->dam_d.p, h->N, h->cls[0].emat.p, h->cls[1].emat.p,
+                           h->mp_total, T, h->mean_d.p, h->stream));
+    }
+    CU(h->cm_raw.ensure((size_t)std::max<long long>(h->m * T, T)));     // scratch: the weights
+    if (si_weights) CU(cudaMemcpyAsync(h->cm_raw.p, si_weights, sizeof(double) * T, cudaMemcpyHostToDevice, h->stream));
+    const size_t n = (size_t)h->N * nof * ntr * 4;
+    CU(h->tidy_d.ensure(n));
+    TidyParams tp{};
+    tp.out = h->out_d.p; tp.gebv = h->gebv_d.p; tp.mean_tgv = h->model == GMS_MODEL_DIRDOM ? h->mean_d.p : nullptr;
+    tp.sire = h->sire_d.p; tp.dam = h->dam_d.p; tp.pair_t1 = h->pair1_d.p; tp.pair_t2 = h->pair2_d.p;
+    tp.w = si_weights ? h->cm_raw.p : nullptr; tp.std_sel_int = std_sel_int;
+    tp.N = h->N; tp.T = T; tp.npairs = h->npairs; tp.ncomp = h->ncomp; tp.model = h->model; tp.tidy = h->tidy_d.p;
+    CU(launch_tidy(tp, h->stream));
+    CU(cudaMemcpyAsync(tidy, h->tidy_d.p, n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
     return GMS_OK;
 }
 

@@ -304,6 +304,50 @@ cudaError_t launch_assemble(const AssembleParams& p, cudaStream_t st) {
 }
 
 // ------------------------------------------------------------------------------------------
+// predictCrosses() tidy output per cross (R/gmsFunctions.R:764-871), fused: predOf in {BV [, TGV]} x Trait in {[SELIND,] traits}
+// -> (predMean, predVar, predSD, predUsefulness). VarBV = VarA (A, AD) or the asub component (DirDom); VarTGV = VarBV + VarDD
+// (AD, :777-787) or VarA + VarD (DirDom, :788-799); MeanTGV = MeanBV for AD (:737-741); SELIND: w'Gw with G symmetrised from
+// the upper triangle (:835-843) and w'mean (:812-822); usefulness = mean + stdSelInt * sd (:855-864).
+__global__ void tidy_kernel(const TidyParams p) {
+    const int nof = p.model == 0 ? 1 : 2;
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= p.N * nof) return;
+    const long long x = idx / nof;
+    const int of = (int)(idx - x * nof);
+    const int ntr = p.T + (p.w ? 1 : 0);
+    const double* o = p.out + x * (long long)p.npairs * p.ncomp;
+    const double* gs = p.gebv + (long long)p.sire[x] * p.T;
+    const double* gd = p.gebv + (long long)p.dam[x] * p.T;
+    const int bv = p.model == 2 ? 2 : 0;
+    auto var_of = [&](int pr) { return of == 0 ? o[pr * p.ncomp + bv] : o[pr * p.ncomp] + o[pr * p.ncomp + 1]; };
+    auto mean_of = [&](int t) {
+        return (of == 1 && p.model == 2) ? p.mean_tgv[x * p.T + t] : (gs[t] + gd[t]) / 2.0;     // R/predCrossVar.R:369
+    };
+    double* dst = p.tidy + (idx * ntr) * 4;
+    if (p.w) {
+        double v = 0.0, mu = 0.0;
+        for (int pr = 0; pr < p.npairs; ++pr) {
+            const int a = p.pair_t1[pr], b = p.pair_t2[pr];
+            v += (a == b ? 1.0 : 2.0) * p.w[a] * p.w[b] * var_of(pr);
+        }
+        for (int t = 0; t < p.T; ++t) mu += p.w[t] * mean_of(t);
+        const double sd = sqrt(v);
+        dst[0] = mu; dst[1] = v; dst[2] = sd; dst[3] = mu + p.std_sel_int * sd;
+        dst += 4;
+    }
+    for (int t = 0; t < p.T; ++t, dst += 4) {
+        const double v = var_of(t), mu = mean_of(t), sd = sqrt(v);
+        dst[0] = mu; dst[1] = v; dst[2] = sd; dst[3] = mu + p.std_sel_int * sd;
+    }
+}
+cudaError_t launch_tidy(const TidyParams& p, cudaStream_t st) {
+    const long long total = p.N * (p.model == 0 ? 1 : 2);
+    if (total == 0) return cudaSuccess;
+    tidy_kernel<<<(unsigned)((total + 127) / 128), 128, 0, st>>>(p);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------
 // predCrossMeans (R/predCrossVar.R:336-399).
 __device__ __forceinline__ double block_sum(double v, double* sh) {
 #pragma unroll

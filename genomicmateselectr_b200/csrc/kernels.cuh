@@ -111,7 +111,10 @@ struct VerifyParams {
     int* list_b;
     int* list_row;
     double* bound_out;           // optional [n_units]: the bound itself (tests, statistics)
+    double* part_b;              // scratch [chromosomes of the shard][n_units][T]: per-chromosome partial sums of B_t
+    int* part_n;                 // scratch [chromosomes of the shard][n_units]: non-zero mask entries per chromosome
 };
+size_t i8_verify_scratch_doubles(long long n_units, int nchrom, int T);
 cudaError_t launch_i8_smax(const double* rowmax, const ChromDesc* chrom_d, int c_begin, int c_end, int C, long long mp_total,
                            int T, double* smax, cudaStream_t st);
 cudaError_t launch_i8_verify(const VerifyParams& p, cudaStream_t st);
@@ -135,6 +138,23 @@ struct AssembleParams {
     double* out;         // [N][npairs][ncomp]
 };
 cudaError_t launch_assemble(const AssembleParams& p, cudaStream_t st);
+
+// predictCrosses() tidy table on the device: tidy[x][predOf][trait slot][predMean, predVar, predSD, predUsefulness]
+struct TidyParams {
+    const double* out;       // [N][npairs][ncomp] result slab
+    const double* gebv;      // [P][T] parent GEBVs from the allele-substitution effects
+    const double* mean_tgv;  // [N][T] Falconer-MacKay TGV means (DirDom) or NULL
+    const int* sire;
+    const int* dam;
+    const int* pair_t1;
+    const int* pair_t2;
+    const double* w;         // [T] selection-index weights (device) or NULL
+    double std_sel_int;
+    long long N;
+    int T, npairs, ncomp, model;
+    double* tidy;
+};
+cudaError_t launch_tidy(const TidyParams& p, cudaStream_t st);
 
 // predCrossMeans: gebv[p][t] = sum_j dose_pj add_t[j]; TGV mean per cross (Falconer-MacKay 14.6).
 cudaError_t launch_gebv(const unsigned* planeA, const unsigned* planeB, long long wpp, const int* plist,

@@ -331,6 +331,19 @@ class CrossVarEngine:
                                            _ptr(gebv), _ptr(mbv), _ptr(mtgv)))
         return gebv, mbv, mtgv
 
+    def tidy(self, si_weights=None, std_sel_int=2.67):
+        """gms_tidy: predictCrosses()' tidy table for the last predict / compute, computed on the device.
+        Returns tidy[N, nof, nslots, 4] = (predMean, predVar, predSD, predUsefulness); predOf axis: BV [, TGV];
+        slot axis: [SELIND,] traits."""
+        N, npairs, ncomp = self._shape
+        T = int((np.sqrt(8 * npairs + 1) - 1) / 2)
+        w = None if si_weights is None else np.ascontiguousarray(si_weights, dtype=np.float64)
+        if w is not None and w.size != T:
+            raise ValueError("si_weights must have one weight per trait")
+        out = np.empty((N, 1 if ncomp == 1 else 2, T + (w is not None), 4), np.float64)
+        self._ck(self._lib.gms_tidy(self._h, _ptr(w), float(std_sel_int), _ptr(out)))
+        return out
+
     @staticmethod
     def selind(model, out, w):
         """Selection-index variance per cross and component (R/gmsFunctions.R:825-853)."""

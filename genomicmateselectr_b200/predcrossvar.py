@@ -185,13 +185,36 @@ def _run(session, CrossesToPredict, model, AddEffectList, DomEffectList=None, Al
     return traits, out, nseg
 
 
+def _pair_labels(traits, comp_names):
+    """(Trait1, Trait2, predOf) of one cross's rows in the reference's order: T variances then combn(traits, 2), the
+    components of a pair adjacent (R/predCrossVar.R:128-151, :231-246)."""
+    p1, p2 = trait_pairs(len(traits))
+    t1 = np.array([traits[i] for i in p1 for _ in comp_names], dtype=object)
+    t2 = np.array([traits[i] for i in p2 for _ in comp_names], dtype=object)
+    of = np.array([c for _ in p1 for c in comp_names], dtype=object)
+    return t1, t2, of
+
+
+def _long(CrossesToPredict, traits, out, nseg, comp_names, elapsed):
+    """tidyr::unnest(predVars) of the reference's result, built in one piece: one row per (cross with >= 1 segregating
+    SNP, trait pair, component). No per-cross objects, so it scales to millions of crosses."""
+    t1, t2, of = _pair_labels(traits, comp_names)
+    k = len(t1)
+    keep = np.flatnonzero(nseg > 0)
+    res = CrossesToPredict.iloc[np.repeat(keep, k)].reset_index(drop=True).copy()
+    res["Nsegsnps"] = np.repeat(nseg[keep].astype(np.int64), k)
+    res["ComputeTime"] = elapsed / max(1, len(CrossesToPredict))
+    res["Trait1"] = np.tile(t1, len(keep))
+    res["Trait2"] = np.tile(t2, len(keep))
+    res["predOf"] = np.tile(of, len(keep))
+    res["predVar"] = out[keep].reshape(-1)
+    return res
+
+
 def _tidy(CrossesToPredict, traits, out, nseg, comp_names, elapsed):
     """One row per cross with >= 1 segregating SNP (R/predCrossVar.R:152-160,70-71); predVars holds
     (Trait1, Trait2, predOf, predVar) in the reference's row order (:128-151, :231-246)."""
-    p1, p2 = trait_pairs(len(traits))
-    t1 = [traits[i] for i in p1 for _ in comp_names]
-    t2 = [traits[i] for i in p2 for _ in comp_names]
-    of = [c for _ in p1 for c in comp_names]
+    t1, t2, of = _pair_labels(traits, comp_names)
     keep = np.flatnonzero(nseg > 0)
     res = CrossesToPredict.iloc[keep].reset_index(drop=True).copy()
     res["Nsegsnps"] = nseg[keep].astype(np.int64)
@@ -202,10 +225,12 @@ def _tidy(CrossesToPredict, traits, out, nseg, comp_names, elapsed):
 
 
 def predCrossVars(CrossesToPredict, modelType, AddEffectList, DomEffectList=None, predType="VPM",
-                  haploMat=None, recombFreqMat=None, ncores=1, nBLASthreads=None, session=None, **kwargs):
+                  haploMat=None, recombFreqMat=None, ncores=1, nBLASthreads=None, session=None, nest=True, **kwargs):
     """Drop-in for R/predCrossVar.R:24-78.  Same arguments; `ncores` / `nBLASthreads` are accepted
     and ignored (the crosses are batched on the GPU); `session=` optionally reuses device state.
-    Returns a DataFrame: sireID, damID, [extra columns], Nsegsnps, ComputeTime, predVars."""
+    Returns a DataFrame: sireID, damID, [extra columns], Nsegsnps, ComputeTime, predVars (one small frame per cross,
+    the reference's nested schema). `nest=False` returns the unnested long form (Trait1, Trait2, predOf, predVar as
+    columns) in one piece - use it for large cross lists, where a Python object per cross would dominate."""
     start = time.perf_counter()
     if predType != "VPM":
         raise ValueError("predType='PMV' is not supported (it is broken in the reference as well: "
@@ -224,8 +249,9 @@ def predCrossVars(CrossesToPredict, modelType, AddEffectList, DomEffectList=None
         if own:
             session.close()
     elapsed = time.perf_counter() - start
-    res = _tidy(CrossesToPredict, traits, out, nseg, ["VarA", "VarD"][: 2 if model == "AD" else 1], elapsed)
-    print(f"Done predicting fam vars. Took {round(elapsed / 60, 2)} mins for {len(res)} crosses")   # :74-76
+    comps = ["VarA", "VarD"][: 2 if model == "AD" else 1]
+    res = (_tidy if nest else _long)(CrossesToPredict, traits, out, nseg, comps, elapsed)
+    print(f"Done predicting fam vars. Took {round(elapsed / 60, 2)} mins for {int(np.sum(nseg > 0))} crosses")   # :74-76
     return res
 
 
@@ -304,7 +330,7 @@ def predictCrosses(modelType, stdSelInt=2.67, selInd=False, SIwts=None, CrossesT
     try:
         asub = _effect_lists(snpeffs, "allelesubsnpeff")
         raw = {}
-        predictedvars = predictedmeans = None
+        predictedvars = predictedmeans = fused = None
         if predTheVars:
             print("Predicting cross variance parameters")
             start = time.perf_counter()
@@ -320,9 +346,12 @@ def predictCrosses(modelType, stdSelInt=2.67, selInd=False, SIwts=None, CrossesT
                 # reference row order: all VarBV rows of a cross first, then VarA/VarD (R/gmsFunctions.R:719-723)
                 comps = ["VarA", "VarD", "VarBV"]
             elapsed = time.perf_counter() - start
-            tid = _tidy(CrossesToPredict, traits, out, nseg, comps, elapsed)
-            print(f"Done predicting fam vars. Took {round(elapsed / 60, 2)} mins for {len(tid)} crosses")
-            predictedvars = _unnest(tid)
+            print(f"Done predicting fam vars. Took {round(elapsed / 60, 2)} mins for {int(np.sum(nseg > 0))} crosses")
+            predictedvars = _long(CrossesToPredict, traits, out, nseg, comps, elapsed)
+            if predTheMeans:
+                # the tidy table (TGV, SELIND, predSD, usefulness) fused on the device from the slab that is still in HBM
+                w = None if not selInd else pd.Series(SIwts, dtype=np.float64).reindex(traits).fillna(0.0).to_numpy()
+                fused = (session.engine.tidy(w, stdSelInt), nseg, traits)
             if modelType == "DirDom":
                 bv = predictedvars[predictedvars.predOf == "VarBV"]
                 predictedvars = pd.concat([bv, predictedvars[predictedvars.predOf != "VarBV"]], ignore_index=True)
@@ -342,6 +371,22 @@ def predictCrosses(modelType, stdSelInt=2.67, selInd=False, SIwts=None, CrossesT
             session.close()
 
     # ---- tidy (R/gmsFunctions.R:764-871)
+    if predTheMeans and predTheVars:
+        tab, nseg, traits = fused            # [N, predOf, slot, (mean, var, sd, usefulness)] from gms_tidy
+        keep = np.flatnonzero(nseg > 0)
+        ofs = ["BV"] if modelType == "A" else ["BV", "TGV"]
+        slots = (["SELIND"] if selInd else []) + list(traits)
+        base = CrossesToPredict.iloc[np.repeat(keep, len(slots))][["sireID", "damID"]].reset_index(drop=True)
+        parts = []
+        for oi, of in enumerate(ofs):         # the reference binds all BV rows, then all TGV rows (:777-799)
+            blk = base.copy()
+            blk["Nsegsnps"] = np.repeat(nseg[keep].astype(np.int64), len(slots))
+            blk["predOf"] = of
+            blk["Trait"] = np.tile(np.array(slots, dtype=object), len(keep))
+            v = tab[keep, oi].reshape(-1, 4)
+            blk["predMean"], blk["predVar"], blk["predSD"], blk["predUsefulness"] = v[:, 0], v[:, 1], v[:, 2], v[:, 3]
+            parts.append(blk)
+        return {"tidyPreds": pd.concat(parts, ignore_index=True), "rawPreds": raw}
     if predTheMeans:
         pm = predictedmeans.copy()
         pm["predOf"] = pm["predOf"].str.replace("Mean", "", regex=False)
@@ -400,37 +445,52 @@ def predictCrossVars(modelType, snpeffs, parentfolds, haploMat, recombFreqMat, n
     """R/parentWiseCrossVal.R:386-493: the cross-validation entry.  `snpeffs`: DataFrame with columns
     Repeat, Fold and `effects` (a DataFrame with Dataset, Trait and *snpeff list-columns);
     `parentfolds`: DataFrame with Repeat, Fold, CrossesToPredict.  All (Repeat, Fold) sets run against
-    ONE device-resident session (haploMat / recombFreqMat are uploaded once)."""
+    ONE device-resident session (haploMat / recombFreqMat are uploaded once), and the sets that are to be
+    predicted for the SAME cross list go through one gms_predict_batched call (cross-side device state staged once)."""
+    if modelType not in ("A", "AD", "DirDom"):
+        raise ValueError("modelType must be 'A', 'AD' or 'DirDom'")
     pf = parentfolds.set_index(["Repeat", "Fold"])
     allparents = pd.unique(pd.concat([pd.concat([c["sireID"], c["damID"]]) for c in parentfolds["CrossesToPredict"]]).astype(str))
     session = CrossVarSession(haploMat, recombFreqMat, parents=allparents)
-    out = []
+    comps = {"A": ["VarBV"], "AD": ["VarBV", "VarDD"], "DirDom": ["VarA", "VarD", "VarBV"]}[modelType]
+    cols = {"A": ("allelesubsnpeff", None, None), "AD": ("allelesubsnpeff", "domdevsnpeff", None),
+            "DirDom": ("addsnpeff", "domsnpeff", "allelesubsnpeff")}[modelType]
+    jobs = []
+    for pos, (_, row) in enumerate(snpeffs.iterrows()):
+        eff = row["effects"]
+        eff = eff[eff["Dataset"] == "trainset"]
+        crosses = pf.loc[(row["Repeat"], row["Fold"]), "CrossesToPredict"]
+        mats, traits = [], None
+        for c in cols:
+            if c is None:
+                mats.append(None)
+                continue
+            t, mat = _effect_matrix(_effect_lists(eff, c), session.snp_names)
+            if traits is not None and t != traits:
+                raise ValueError("effect classes must name the same traits in the same order")
+            traits = t
+            mats.append(mat)
+        sire, dam = session.indices(crosses["sireID"]), session.indices(crosses["damID"])
+        jobs.append(dict(pos=pos, row=row, crosses=crosses, traits=traits, mats=mats, sire=sire, dam=dam,
+                         key=(tuple(traits), sire.tobytes(), dam.tobytes())))
+    out = [None] * len(jobs)
     try:
-        for _, row in snpeffs.iterrows():
-            eff = row["effects"]
-            eff = eff[eff["Dataset"] == "trainset"]
-            crosses = pf.loc[(row["Repeat"], row["Fold"]), "CrossesToPredict"]
+        groups = {}
+        for j in jobs:
+            groups.setdefault(j["key"], []).append(j)
+        for grp in groups.values():
             start = time.perf_counter()
-            asub = _effect_lists(eff, "allelesubsnpeff")
-            if modelType == "A":
-                traits, o, nseg = _run(session, crosses, "A", asub)
-                comps = ["VarBV"]
-            elif modelType == "AD":
-                traits, o, nseg = _run(session, crosses, "AD", asub, _effect_lists(eff, "domdevsnpeff"))
-                comps = ["VarBV", "VarDD"]
-            elif modelType == "DirDom":
-                traits, o, nseg = _run(session, crosses, "DirDom", _effect_lists(eff, "addsnpeff"),
-                                       _effect_lists(eff, "domsnpeff"), asub)
-                comps = ["VarA", "VarD", "VarBV"]
-            else:
-                raise ValueError("modelType must be 'A', 'AD' or 'DirDom'")
-            tid = _tidy(crosses, traits, o, nseg, comps, time.perf_counter() - start)
-            if modelType == "DirDom":      # VarBV rows first (R/parentWiseCrossVal.R:484-488)
-                tid["predVars"] = [pd.concat([p[p.predOf == "VarBV"], p[p.predOf != "VarBV"]], ignore_index=True)
-                                   for p in tid["predVars"]]
-            print(f"Done predicting fam vars. Took {round((time.perf_counter() - start) / 60, 2)} mins for {len(tid)} crosses")
-            out.append({"Repeat": row["Repeat"], "Fold": row["Fold"], "modelType": row.get("modelType", modelType),
-                        "predVars": tid})
+            stack = lambda i: None if grp[0]["mats"][i] is None else np.stack([j["mats"][i] for j in grp])
+            o, nseg = session.engine.predict_batched(modelType, stack(0), stack(1), stack(2), grp[0]["sire"], grp[0]["dam"])
+            elapsed = (time.perf_counter() - start) / len(grp)
+            for si, j in enumerate(grp):
+                tid = _tidy(j["crosses"], j["traits"], o[si], nseg, comps, elapsed)
+                if modelType == "DirDom":      # VarBV rows first (R/parentWiseCrossVal.R:484-488)
+                    tid["predVars"] = [pd.concat([p[p.predOf == "VarBV"], p[p.predOf != "VarBV"]], ignore_index=True)
+                                       for p in tid["predVars"]]
+                print(f"Done predicting fam vars. Took {round(elapsed / 60, 2)} mins for {len(tid)} crosses")
+                out[j["pos"]] = {"Repeat": j["row"]["Repeat"], "Fold": j["row"]["Fold"],
+                                 "modelType": j["row"].get("modelType", modelType), "predVars": tid}
     finally:
         session.close()
     return pd.DataFrame(out)

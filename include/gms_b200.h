@@ -200,6 +200,15 @@ GMS_API int gms_predict_batched(gms_handle* h, int model, int nsets, int T,
  *   if dom != NULL also the Falconer-MacKay eqn 14.6 TGV mean.  mean_bv, mean_tgv: N x T
  *   cross-major (mean_tgv may be NULL iff dom is NULL); gebv: P x T parent-major or NULL. */
 GMS_API int gms_selind(int model, int T, int64_t N, const double* out, const double* w, double* si);
+/* gms_tidy: the tidy table of predictCrosses() (R/gmsFunctions.R:726-871) for the crosses of the last gms_compute /
+ *   gms_predict on this handle, computed on the device from the result slab and the effects already in HBM:
+ *   tidy[x][predOf][slot][4] = (predMean, predVar, predSD, predUsefulness = predMean + std_sel_int * predSD);
+ *   predOf: BV [, TGV]  (1 for model A, else 2; TGV = VarBV + VarDD for AD, VarA + VarD for DirDom, :772-800);
+ *   slot: [SELIND (only if si_weights != NULL; w'Gw and w'mean, :805-853),] trait 0 .. T-1.
+ *   Means: MeanBV = mid-parent GEBV from the allele-substitution effects (add for A / AD, asub for DirDom);
+ *   MeanTGV = MeanBV for AD (:737-741), Falconer-MacKay 14.6 from (add, dom) for DirDom (R/predCrossVar.R:379-396).
+ *   The model fixes which effects predictCrosses passes, so no effect arrays are needed here. */
+GMS_API int gms_tidy(gms_handle* h, const double* si_weights, double std_sel_int, double* tidy);
 GMS_API int gms_cross_means(gms_handle* h, int T, const double* add, const double* dom,
                     int64_t N, const int32_t* sire, const int32_t* dam,
                     double* gebv, double* mean_bv, double* mean_tgv);

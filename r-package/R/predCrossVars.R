@@ -1,6 +1,7 @@
 # Drop-in replacement of genomicMateSelectR::predCrossVars (R/predCrossVar.R:24-78 of the reference)
 # backed by libgms_b200.so through .Call. Same arguments, same return tibble.
-# NOT executable in this repository's build image (no R there); the Python module
+# NOT executable in this repository's build image (no R there): this R code has never been run. The .Call shim
+# under it IS executed on the GPU box against a stand-in for R's C API (r-package/tests/fakeR), and the Python module
 # genomicmateselectr_b200/predcrossvar.py is the executable twin of this file and is what the tests run.
 #
 # NAMESPACE additions:  useDynLib(genomicMateSelectRb200, .registration = TRUE)
@@ -62,8 +63,10 @@ gms_session <- function(haploMat, recombFreqMat, parents = NULL, devices = 0L, m
 }
 
 .gms_effmat <- function(EffectList, snps) {
-  # 1 x m matrices with colnames = SNP ids (R/predCrossVar.R:32-43: for VPM the effects are the row itself)
-  do.call(cbind, lapply(EffectList, function(e) as.double(e[1, snps])))
+  # n x m matrices with colnames = SNP ids. predType = "VPM" uses the posterior MEAN effects: the reference centres
+  # each matrix and keeps the "scaled:center" attribute (R/predCrossVar.R:32-43), i.e. the column means - the row itself
+  # for the usual 1 x m matrix, the mean over posterior samples for an n x m one
+  do.call(cbind, lapply(EffectList, function(e) as.double(colMeans(e[, snps, drop = FALSE]))))
 }
 
 .gms_run <- function(session, CrossesToPredict, model, AddEffectList, DomEffectList = NULL, AlleleSubEffectList = NULL) {

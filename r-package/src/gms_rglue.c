@@ -2,7 +2,10 @@
  *
  * Compiles only where R's headers exist (R CMD INSTALL; link with -lgms_b200). R is not installed in
  * the build image of this repository, so the file is syntax-checked there against the stub headers in
- * r-package/tests/rstub (tests/test_rglue_cpu.py) and exercised for real only by a user with R.
+ * r-package/tests/rstub (tests/test_rglue_cpu.py) and EXECUTED on the GPU box against a minimal stand-in
+ * for R's C API (r-package/tests/fakeR: the ~30 API functions this file uses, implemented in plain C; the
+ * driver runs gmsr_create -> gmsr_set_* -> gmsr_predict / gmsr_tidy on the bundled data and
+ * tests/test_gpu_rshim.py checks the vignette values). Under real R it has still never run.
  *
  * Conventions: every entry point takes/returns SEXPs, touches R's API only on R's main thread,
  * unpacks INTEGER()/REAL() pointers without copying (R matrices are column-major, which is what the
@@ -143,6 +146,101 @@ SEXP gmsr_set_mode(SEXP ptr, SEXP mode) {
     return R_NilValue;
 }
 
+SEXP gmsr_set_cache(SEXP ptr, SEXP enabled) {
+    gms_handle* h = gmsr_get(ptr);
+    gmsr_check(h, gms_set_cache(h, Rf_asInteger(enabled)));
+    return R_NilValue;
+}
+
+static SEXP gmsr_array(int type, R_xlen_t n, int nd, const int* dims) {
+    SEXP a = PROTECT(Rf_allocVector(type, n));
+    SEXP dim = PROTECT(Rf_allocVector(INTSXP, nd));
+    for (int i = 0; i < nd; ++i) INTEGER(dim)[i] = dims[i];
+    Rf_setAttrib(a, R_DimSymbol, dim);
+    UNPROTECT(2);
+    return a;
+}
+
+/* several effect sets (cross-validation folds) against ONE cross list: add/dom/asub are m x T x nsets arrays.
+ * Returns list(out = double[ncomp, npairs, N, nsets], nseg = integer[N]). */
+SEXP gmsr_predict_batched(SEXP ptr, SEXP model, SEXP nsets, SEXP ntraits, SEXP add, SEXP dom, SEXP asub, SEXP sire, SEXP dam) {
+    gms_handle* h = gmsr_get(ptr);
+    const int mdl = Rf_asInteger(model), S = Rf_asInteger(nsets), T = Rf_asInteger(ntraits);
+    const R_xlen_t N = XLENGTH(sire);
+    const int npairs = T * (T + 1) / 2, ncomp = mdl + 1;
+    if (XLENGTH(dam) != N) Rf_error("gms_b200: sire and dam differ in length");
+    const int dims[4] = {ncomp, npairs, (int)N, S};
+    SEXP out = PROTECT(gmsr_array(REALSXP, (R_xlen_t)ncomp * npairs * N * S, 4, dims));
+    SEXP nseg = PROTECT(Rf_allocVector(INTSXP, N));
+    int rc = gms_predict_batched(h, mdl, S, T, REAL(add), Rf_isNull(dom) ? NULL : REAL(dom), Rf_isNull(asub) ? NULL : REAL(asub),
+                                 (int64_t)N, INTEGER(sire), INTEGER(dam), REAL(out), INTEGER(nseg));
+    if (rc != GMS_OK) { UNPROTECT(2); Rf_error("gms_b200: %s", gms_last_error(h)); }
+    SEXP res = PROTECT(Rf_allocVector(VECSXP, 2));
+    SET_VECTOR_ELT(res, 0, out);
+    SET_VECTOR_ELT(res, 1, nseg);
+    SEXP nm = PROTECT(Rf_allocVector(STRSXP, 2));
+    SET_STRING_ELT(nm, 0, Rf_mkChar("out"));
+    SET_STRING_ELT(nm, 1, Rf_mkChar("nseg"));
+    Rf_setAttrib(res, R_NamesSymbol, nm);
+    UNPROTECT(4);
+    return res;
+}
+
+/* predictCrosses()' tidy table for the crosses of the last gmsr_predict on this handle (gms_tidy; R/gmsFunctions.R:726-871):
+ * ntraits = T, siwts = double[T] or NULL, stdselint = numeric(1). Returns double[4, nslots, nof, N]:
+ * (predMean, predVar, predSD, predUsefulness) x ([SELIND,] traits) x (BV [, TGV]) x cross. */
+SEXP gmsr_tidy(SEXP ptr, SEXP model, SEXP ntraits, SEXP ncross, SEXP siwts, SEXP stdselint) {
+    gms_handle* h = gmsr_get(ptr);
+    const int mdl = Rf_asInteger(model), T = Rf_asInteger(ntraits), N = Rf_asInteger(ncross);
+    const int nof = mdl == GMS_MODEL_A ? 1 : 2, nslots = T + (Rf_isNull(siwts) ? 0 : 1);
+    if (!Rf_isNull(siwts) && LENGTH(siwts) != T) Rf_error("gms_b200: SIwts needs one weight per trait");
+    const int dims[4] = {4, nslots, nof, N};
+    SEXP out = PROTECT(gmsr_array(REALSXP, (R_xlen_t)4 * nslots * nof * N, 4, dims));
+    int rc = gms_tidy(h, Rf_isNull(siwts) ? NULL : REAL(siwts), REAL(stdselint)[0], REAL(out));
+    if (rc != GMS_OK) { UNPROTECT(1); Rf_error("gms_b200: %s", gms_last_error(h)); }
+    UNPROTECT(1);
+    return out;
+}
+
+/* selection-index variance w'Gw per cross and component from a gmsr_predict slab (gms_selind; R/gmsFunctions.R:825-853).
+ * out: double[ncomp, npairs, N]; w: double[T]. Returns double[ncomp, N]. */
+SEXP gmsr_selind(SEXP model, SEXP out, SEXP w) {
+    const int mdl = Rf_asInteger(model), T = LENGTH(w), ncomp = mdl + 1, npairs = T * (T + 1) / 2;
+    const R_xlen_t N = XLENGTH(out) / ((R_xlen_t)ncomp * npairs);
+    const int dims[2] = {ncomp, (int)N};
+    SEXP si = PROTECT(gmsr_array(REALSXP, (R_xlen_t)ncomp * N, 2, dims));
+    if (gms_selind(mdl, T, (int64_t)N, REAL(out), REAL(w), REAL(si)) != GMS_OK) { UNPROTECT(1); Rf_error("gms_b200: gms_selind: bad arguments"); }
+    UNPROTECT(1);
+    return si;
+}
+
+/* predCrossMeans on the device-resident haplotypes (gms_cross_means; R/predCrossVar.R:336-399): add (and dom, or NULL):
+ * m x T. Returns list(gebv = double[T, P], mean_bv = double[T, N], mean_tgv = double[T, N] or NULL). */
+SEXP gmsr_cross_means(SEXP ptr, SEXP nparents, SEXP add, SEXP dom, SEXP sire, SEXP dam) {
+    gms_handle* h = gmsr_get(ptr);
+    const int T = Rf_ncols(add), P = Rf_asInteger(nparents);
+    const R_xlen_t N = XLENGTH(sire);
+    if (XLENGTH(dam) != N) Rf_error("gms_b200: sire and dam differ in length");
+    const int dg[2] = {T, P}, dn[2] = {T, (int)N};
+    SEXP gebv = PROTECT(gmsr_array(REALSXP, (R_xlen_t)T * P, 2, dg));
+    SEXP mbv = PROTECT(gmsr_array(REALSXP, (R_xlen_t)T * N, 2, dn));
+    SEXP mtgv = PROTECT(Rf_isNull(dom) ? R_NilValue : gmsr_array(REALSXP, (R_xlen_t)T * N, 2, dn));
+    int rc = gms_cross_means(h, T, REAL(add), Rf_isNull(dom) ? NULL : REAL(dom), (int64_t)N, INTEGER(sire), INTEGER(dam),
+                             REAL(gebv), REAL(mbv), Rf_isNull(dom) ? NULL : REAL(mtgv));
+    if (rc != GMS_OK) { UNPROTECT(3); Rf_error("gms_b200: %s", gms_last_error(h)); }
+    SEXP res = PROTECT(Rf_allocVector(VECSXP, 3));
+    SET_VECTOR_ELT(res, 0, gebv);
+    SET_VECTOR_ELT(res, 1, mbv);
+    SET_VECTOR_ELT(res, 2, mtgv);
+    SEXP nm = PROTECT(Rf_allocVector(STRSXP, 3));
+    SET_STRING_ELT(nm, 0, Rf_mkChar("gebv"));
+    SET_STRING_ELT(nm, 1, Rf_mkChar("mean_bv"));
+    SET_STRING_ELT(nm, 2, Rf_mkChar("mean_tgv"));
+    Rf_setAttrib(res, R_NamesSymbol, nm);
+    UNPROTECT(5);
+    return res;
+}
+
 static const R_CallMethodDef gmsr_calls[] = {
     {"gmsr_create", (DL_FUNC)&gmsr_create, 1},
     {"gmsr_close", (DL_FUNC)&gmsr_close, 1},
@@ -152,6 +250,11 @@ static const R_CallMethodDef gmsr_calls[] = {
     {"gmsr_predict", (DL_FUNC)&gmsr_predict, 7},
     {"gmsr_predict_sharded", (DL_FUNC)&gmsr_predict_sharded, 7},
     {"gmsr_set_mode", (DL_FUNC)&gmsr_set_mode, 2},
+    {"gmsr_set_cache", (DL_FUNC)&gmsr_set_cache, 2},
+    {"gmsr_predict_batched", (DL_FUNC)&gmsr_predict_batched, 9},
+    {"gmsr_tidy", (DL_FUNC)&gmsr_tidy, 6},
+    {"gmsr_selind", (DL_FUNC)&gmsr_selind, 3},
+    {"gmsr_cross_means", (DL_FUNC)&gmsr_cross_means, 6},
     {NULL, NULL, 0}};
 
 void R_init_genomicMateSelectRb200(DllInfo* dll) {
