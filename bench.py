@@ -51,6 +51,7 @@ def parse():
     ap.add_argument("--modes", default="auto,fp64,map_scan", help="evaluation modes to measure; the first is the headline")
     ap.add_argument("--cpu-sample", type=int, default=8, help="crosses per CPU-baseline step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-cached", action="store_true", help="skip the cache-on leg")
     return ap.parse_args()
 
 
@@ -512,6 +513,8 @@ def main():
     # the cache: same effects again (a mate-selection loop re-scoring cross lists): operand images + parent tables reused
     cached = None
     try:
+        if args.no_cached:
+            raise RuntimeError("skipped (--no-cached)")
         eng.set_mode(modes[0])
         eng.set_cache(True)
         stage(); compute(True)
