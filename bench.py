@@ -279,7 +279,9 @@ def main():
         raise SystemExit("bench.py: no CUDA device; the engine has no CPU fallback")
     torch.cuda.set_device(local_rank)
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        import datetime
+        # a mismatched collective must fail in minutes, not hold N GPUs for the default 10
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank), timeout=datetime.timedelta(seconds=180))
     layout = S.GridLayout(world, gx, gc)
     xi, ci = layout.coords(rank)
 
@@ -365,7 +367,9 @@ def main():
         if sampler:
             sampler.start()       # nvidia-smi needs ~0.3 s to start: run it through the warm-up, keep the timed window
             tw = time.time()
-            while len(sampler.lines) < 2 and time.time() - tw < 3.0:
+            # compute() holds collectives when the grid has more than one rank, so every rank must run the SAME number of
+            # them: the ranks agree on "one more" each time (a per-rank loop count deadlocked an 8-rank run)
+            while max_over_ranks(1.0 if (len(sampler.lines) < 2 and time.time() - tw < 3.0) else 0.0) > 0.0:
                 compute(True)
         barrier()
         w0 = time.time()
