@@ -99,6 +99,7 @@ struct gms_handle {
     long long N = 0;                   // crosses of THIS handle (its range of the staged list)
     EffClass cls[3];
     DevBuf<int> sire_d, dam_d, pair1_d, pair2_d, split_par_d, split_x_d, split_fb_d, flag_d;
+    DevBuf<int> sire_s_d, dam_s_d, perm_d;      // int8 path: the crosses of every pass ordered by sire, and where each one goes in X
     DevBuf<double> Z, Zfb, X, out_d, gebv_d, mean_d, cm_add, cm_dom, cm_raw, tidy_d;
     DevBuf<int> nseg_d;
     Plan plan_par, plan_x, plan_fb;
@@ -129,6 +130,8 @@ struct gms_handle {
     long long i8_chunk = 0;            // crosses per pass of the per-cross int8 kernel (bounds the xi image)
     bool use_i8 = false;
     bool i8_pair = true;               // tcgen05 cta_group::2: CTA pairs form one M = 256 tile (GMS_I8_CG2=0: one CTA per 128 crosses)
+    bool i8_sort = true;               // per-cross passes run in sire order (GMS_I8_SORT=0: list order), so that the crosses of a warp share a parent
+    bool i8_skip = true;               // ... and the epilogue skips the rows where none of a warp's crosses has a mask entry (GMS_I8_SKIP=0)
     bool xi_image_valid = false;       // the per-cross xi image in xi_d belongs to the staged cross list (single pass only)
     double tau = 0x1p-31;              // int8 error-bound tolerance (gms_set_int8_tolerance); <= 0: no verification
     int fb_cap = 0;
@@ -373,7 +376,7 @@ int run_scan(gms_handle* h, const double* S, int mode, const int* ua, const int*
 
 // int8 tcgen05 contraction of `n_units` units (their xi image in `xi`) into table rows
 int run_i8(gms_handle* h, const EffClass& cl, const signed char* xi, int mode, const int* ua, const int* ub, long long n_units,
-           const Plan& pl, const int* split_d, double* Xout, const int* row_index, cudaEvent_t e0 = nullptr,
+           const Plan& pl, const int* split_d, double* Xout, const int* row_index, bool skip, cudaEvent_t e0 = nullptr,
            cudaEvent_t e1 = nullptr) {
     if (n_units == 0) return GMS_OK;
     I8Params ip{};
@@ -385,7 +388,7 @@ int run_i8(gms_handle* h, const EffClass& cl, const signed char* xi, int mode, c
     ip.Zpart = h->Z.p;
     ip.debug = h->i8_debug;
     if (e0) CU(cudaEventRecord(e0, h->stream));
-    CU(launch_i8_contract(ip, pl.ntiles, pl.nsplit, h->i8_pair, h->stream));
+    CU(launch_i8_contract(ip, pl.ntiles, pl.nsplit, h->i8_pair, skip, h->stream));
     if (e1) CU(cudaEventRecord(e1, h->stream));
     CU(launch_finalize_sym(h->Z.p, i8_npart(h->T) * pl.nsplit, n_units, h->T, Xout, h->stream, true, row_index));
     h->st.last_launches += 2;
@@ -539,7 +542,7 @@ int stage_impl(gms_handle* h, int model, int T, const double* add, const double*
     double dig_bytes = 0;
     for (int c = h->c_begin; c < h->c_end; ++c) {
         const double nJ = (h->chrom[c].m + 63) / 64;
-        dig_bytes += nJ * (nJ + 1) / 2 * T * 7 * 4096.0;
+        dig_bytes += nJ * (nJ + 1) / 2 * T * (double)i8_block_bytes();
     }
     // int8 path: the parents' mask images (2 ppad x mp bytes) and up to 3 digit-plane sets must fit comfortably
     const bool i8_ok = Nall > 0 && (double)(2 * ppad_max) * (double)h->mp_total < 16e9 && dig_bytes * ncls < 60e9;
@@ -641,7 +644,7 @@ int stage_impl(gms_handle* h, int model, int T, const double* add, const double*
             if (c < h->c_begin || c >= h->c_end) continue;
             const int nJ = (h->chrom[c].m + 63) / 64;
             h->gbase[c] = gb;
-            gb += (long long)nJ * (nJ + 1) / 2 * T * 7 * 4096;
+            gb += (long long)nJ * (nJ + 1) / 2 * T * i8_block_bytes();
             blks += nJ * (nJ + 1) / 2;
             for (int J = 0; J < nJ; ++J) h->jtiles.push_back(RowTile{c, J});
         }
@@ -668,6 +671,38 @@ int stage_impl(gms_handle* h, int model, int T, const double* add, const double*
             const size_t xin = (size_t)std::min<long long>(chunk, std::max<long long>(256, npad)) * h->mp_total;
             if (xin > h->xi_d.cap) h->xi_image_valid = false;
             CU(h->xi_d.ensure(xin));
+        }
+        if (model >= GMS_MODEL_AD && N > 0 && h->i8_sort) {
+            // every pass of the per-cross kernel in sire order (stable: list order within a sire), so that the 32 crosses of an
+            // epilogue warp share one parent as far as the list allows and their non-zero xi rows coincide (i8path.cu: SKIP).
+            // xi = delta_sire o delta_dam is symmetric in the pair, so the key could be either parent; the sire it is.
+            std::vector<int32_t> ss((size_t)N), ds((size_t)N), pm((size_t)N);
+            std::vector<long long> cnt;
+            std::vector<int32_t> idx;
+            for (long long off = 0; off < N; off += chunk) {
+                const long long n = std::min<long long>(chunk, N - off);
+                const int32_t* sv = sire + xlo + off;
+                const int32_t* dv = dam + xlo + off;
+                if (h->P <= 4 * n + 4096) {            // counting sort
+                    cnt.assign((size_t)h->P + 1, 0);
+                    for (long long r = 0; r < n; ++r) ++cnt[(size_t)sv[r] + 1];
+                    for (long long q = 0; q < h->P; ++q) cnt[q + 1] += cnt[q];
+                    for (long long r = 0; r < n; ++r) {
+                        const long long pos = off + cnt[sv[r]]++;
+                        ss[pos] = sv[r]; ds[pos] = dv[r]; pm[pos] = (int32_t)r;
+                    }
+                } else {
+                    idx.resize((size_t)n);
+                    for (long long r = 0; r < n; ++r) idx[r] = (int32_t)r;
+                    std::stable_sort(idx.begin(), idx.end(), [&](int32_t a, int32_t b) { return sv[a] < sv[b]; });
+                    for (long long r = 0; r < n; ++r) { ss[off + r] = sv[idx[r]]; ds[off + r] = dv[idx[r]]; pm[off + r] = idx[r]; }
+                }
+            }
+            CU(h->sire_s_d.ensure((size_t)N)); CU(h->dam_s_d.ensure((size_t)N)); CU(h->perm_d.ensure((size_t)N));
+            CU(cudaMemcpyAsync(h->sire_s_d.p, ss.data(), sizeof(int) * N, cudaMemcpyHostToDevice, h->stream));
+            CU(cudaMemcpyAsync(h->dam_s_d.p, ds.data(), sizeof(int) * N, cudaMemcpyHostToDevice, h->stream));
+            CU(cudaMemcpyAsync(h->perm_d.p, pm.data(), sizeof(int) * N, cudaMemcpyHostToDevice, h->stream));
+            CU(cudaStreamSynchronize(h->stream));     // the host vectors are locals
         }
         const long long n_full = model >= GMS_MODEL_AD ? std::min<long long>(N, chunk) : 0;
         const long long n_tail = model >= GMS_MODEL_AD && N > chunk ? N % chunk : 0;
@@ -756,7 +791,7 @@ int compute_parents_impl(gms_handle* h) {
             for (int k = 0; k < ncls; ++k) {
                 const EffClass& cl = h->cls[k];
                 if (int rc = run_i8(h, cl, k == 1 ? h->xi_het_d.p : h->xi_delta_d.p, class_mask(k), units, nullptr, nun, h->plan_i8_par,
-                                    h->split_i8_par_d.p, h->cls[k].table.p, units)) return rc;
+                                    h->split_i8_par_d.p, h->cls[k].table.p, units, false)) return rc;
                 if (int rc = verify_and_repair(h, cl, class_tiles(h, k), class_mask(k), units, nullptr, nun, h->cls[k].table.p, true, k)) return rc;
             }
         } else {
@@ -799,18 +834,23 @@ int compute_crosses_impl(gms_handle* h, int sync) {
             // in passes of at most i8_chunk crosses (the xi mask image of a pass is chunk x mp bytes)
             const bool one_pass = h->N <= h->i8_chunk;          // then the events bracket the kernel alone
             if (!one_pass) CU(cudaEventRecord(h->ev[4], h->stream));
+            // the kernel walks every pass in sire order (stage_impl); finalize_sym puts row r of the pass where cross perm[r] of
+            // the pass belongs, so X - and everything after it - stays in list order
+            const int* ua = h->i8_sort ? h->sire_s_d.p : h->sire_d.p;
+            const int* ub = h->i8_sort ? h->dam_s_d.p : h->dam_d.p;
             int pass = 0;
             for (long long off = 0; off < h->N; off += h->i8_chunk, ++pass) {
                 const long long n = std::min<long long>(h->i8_chunk, h->N - off);
                 const bool tail = n < h->i8_chunk && h->N > h->i8_chunk;
                 if (!(one_pass && h->xi_image_valid)) {
-                    CU(launch_i8_build_xi(h->planeA.p, h->planeB.p, h->wpp, h->sire_d.p + off, h->dam_d.p + off, n, MASK_XI,
+                    CU(launch_i8_build_xi(h->planeA.p, h->planeB.p, h->wpp, ua + off, ub + off, n, MASK_XI,
                                           h->mp_total / 64, h->xi_d.p, h->stream));
                     h->st.last_launches += 1;
                 }
                 double* Xp = h->X.p + off * (long long)TT;
-                if (int rc = run_i8(h, dm, h->xi_d.p, MASK_XI, h->sire_d.p + off, h->dam_d.p + off, n,
-                                    tail ? h->plan_i8_tail : h->plan_i8, tail ? h->split_i8_tail_d.p : h->split_i8_d.p, Xp, nullptr,
+                if (int rc = run_i8(h, dm, h->xi_d.p, MASK_XI, ua + off, ub + off, n,
+                                    tail ? h->plan_i8_tail : h->plan_i8, tail ? h->split_i8_tail_d.p : h->split_i8_d.p, Xp,
+                                    h->i8_sort ? h->perm_d.p + off : nullptr, h->i8_skip,
                                     one_pass ? h->ev[4] : nullptr, one_pass ? h->ev[5] : nullptr)) return rc;
                 if (int rc = verify_and_repair(h, dm, h->R2.p, MASK_XI, h->sire_d.p + off, h->dam_d.p + off, n, Xp, false, 3 + pass)) return rc;
             }
@@ -948,6 +988,8 @@ int gms_create(gms_handle** out, int device) {
     }
     nh->stream = nh->own_stream;
     if (const char* ev = getenv("GMS_I8_CG2")) nh->i8_pair = atoi(ev) != 0;      // test hook: one CTA per 128 crosses
+    if (const char* ev = getenv("GMS_I8_SORT")) nh->i8_sort = atoi(ev) != 0;     // test hooks: list order / every row in the epilogue
+    if (const char* ev = getenv("GMS_I8_SKIP")) nh->i8_skip = atoi(ev) != 0;
 #ifdef GMS_PROFILE
     if (const char* ev = getenv("GMS_I8_DEBUG")) nh->i8_debug = atoi(ev);        // profiling builds only: results are garbage
 #endif
@@ -964,7 +1006,7 @@ void gms_destroy(gms_handle* h) {
         cudaStreamSynchronize(h->stream);
         for (auto& c : h->cls) c.release();
         h->chrom_d.release(); h->R.release(); h->R2.release(); h->planeA.release(); h->planeB.release();
-        h->rowtiles_d.release(); h->sire_d.release(); h->dam_d.release(); h->pair1_d.release(); h->pair2_d.release();
+        h->rowtiles_d.release(); h->sire_d.release(); h->dam_d.release(); h->sire_s_d.release(); h->dam_s_d.release(); h->perm_d.release(); h->pair1_d.release(); h->pair2_d.release();
         h->split_par_d.release(); h->split_x_d.release(); h->split_fb_d.release(); h->flag_d.release();
         h->Z.release(); h->Zfb.release(); h->X.release(); h->out_d.release(); h->gebv_d.release(); h->mean_d.release();
         h->cm_add.release(); h->cm_dom.release(); h->cm_raw.release(); h->tidy_d.release(); h->nseg_d.release(); h->todo_d.release(); h->xbuf.release();

@@ -1,17 +1,26 @@
-// Exact int8 tensor-core evaluation of the quadratic-form tables (per parent and per cross): GMS_MODE_INT8_TENSOR, what
+// Int8 tensor-core evaluation of the quadratic-form tables (per parent and per cross): GMS_MODE_INT8_TENSOR, what
 // GMS_MODE_AUTO resolves to.
 //
 // FP64 has no tcgen05 kind, but this contraction has a special shape: one operand is TERNARY.
 //     C_s[j,x] = sum_k G_s[j,k] xi_x[k],   G_s[j,k] = L'[j,k] d_s[k]  (FP64),   xi in {-1,0,+1}
-// xi is exact in int8. G_s is rounded row-wise to 49 fractional bits of a shared power-of-two row scale 2^E(j,s) > max_k |G_s[j,k]|
-// and split into 7 sign-magnitude radix-128 digits:  G = 2^E sum_i g_i 128^-(i+1) + r,  |r| <= 2^(E-50) (round to nearest
-// even, unbiased; 2^(E-49) is what the error bound assumes). Each digit plane times xi is an int8 x int8 -> int32 product
-// whose sum over the k of a row is EXACT in int32 for any chromosome length this library accepts (|sum| <= 127 n for n
-// non-zero xi entries), so the 5th-generation tensor cores (tcgen05.mma kind::i8, accumulators in TMEM) do the O(m^2)
-// work at int8 rate. The epilogue recombines the seven digit sums exactly in 64-bit integer arithmetic (exact while
-// n < 2^14 non-zero mask entries per chromosome and unit - verify.cu sends larger units to the FP64 path), converts once
-// to FP64 (i8ptx.cuh: v2_combine / v2_scaled), applies xi_x[j] d_t[j] and accumulates the T x T quadratic forms per cross
-// in registers (TMEM lane = cross, so the reduction over SNPs j is thread-local: no shuffles, no atomics).
+// xi is exact in int8. G_s is rounded row-wise to 47 fractional bits of a shared power-of-two row scale 2^E(j,s) with
+// max_k |G_s[j,k]| <= 0.996 * 2^E and split into 6 BALANCED radix-256 digits g_i in [-128, 127] (i8digits.cuh: every plane
+// carries a full 8 bits, so six planes hold what seven sign-magnitude radix-128 planes held less two bits - 14 % fewer
+// MMAs and operand bytes):  G = 2^(E+1) sum_i g_i 256^-(i+1) + r,  |r| <= 2^(E-48) (round to nearest). Each digit plane times xi
+// is an int8 x int8 -> int32 product whose sum over the k of a row is EXACT in int32 for any chromosome length this library
+// accepts (|sum| <= 128 n for n non-zero xi entries), so the 5th-generation tensor cores (tcgen05.mma kind::i8,
+// accumulators in TMEM) do the O(m^2) work at int8 rate. The epilogue recombines the six digit sums exactly in 64-bit
+// integer arithmetic (exact while n < 2^15; verify.cu sends units with n >= 2^14 on one chromosome to the FP64 path),
+// builds the FP64 bit pattern of xi_x[j] W 2^(E-47) with integer instructions (i8digits.cuh: i8_cvt_bits - FP64
+// instructions stall the MMAs of the SM, integer ones do not), multiplies by d_t[j] and accumulates the T x T quadratic
+// forms per cross in registers (TMEM lane = cross, so the reduction over SNPs j is thread-local: no shuffles, no atomics).
+// The only FP64 instructions left are those T FMAs per (cross, row, trait).
+// ROW SKIPPING (template parameter SKIP, used for the per-cross table): xi_x[j] is non-zero on ~13 % of a cross's SNPs, and
+// a warp only has to visit the rows j where ANY of its 32 crosses has a non-zero entry. api.cu orders the crosses of a pass
+// by sire, so the crosses of a warp share (mostly) one sire and the union of their non-zero rows is about that sire's
+// heterozygous SNPs: the warp ORs the masks (redux.sync), walks the set bits four at a time and loads exactly those
+// accumulator columns (tcgen05.ld .x1). That removes about half of the TMEM reads, the integer recombination and - what
+// matters - the FP64 FMAs, and shortens the time the next unit's MMAs wait for the accumulator.
 // THE RESULT IS FIXED POINT RELATIVE TO THE ROW SCALE, not floating point: verify.cu bounds the error of every unit
 // a posteriori and api.cu re-evaluates the units that fail the bound with the FP64 contraction (contract.cu).
 //
@@ -36,19 +45,24 @@ namespace gms {
 constexpr int I8_M = 128;        // crosses per tile (TMEM lanes)
 constexpr int I8_N = 64;         // SNP rows j per accumulator
 constexpr int I8_KB = 64;        // k per pipeline stage (bytes of int8)
-constexpr int I8_DIG = 7;        // radix-128 digits
+// I8_DIG = 6 balanced radix-256 digits (i8digits.cuh)
+constexpr int I8_NA = 4 * I8_N;                     // N of the first MMA of a k32-step: digits 0-3 (256 = the UMMA maximum)
+constexpr int I8_NB = (I8_DIG - 4) * I8_N;          // N of the second: digits 4-5
 constexpr int I8_A_BYTES = I8_M * I8_KB;            // 8 KiB
 constexpr int I8_B_BYTES = I8_N * I8_KB;            // 4 KiB per digit
-constexpr int I8_B_ALL = I8_DIG * I8_B_BYTES;       // 28 KiB: the 448-row digit operand of one k-block
+constexpr int I8_B_ALL = I8_DIG * I8_B_BYTES;       // 24 KiB: the 384-row digit operand of one k-block
+static_assert(I8_DIG == 6 && I8_NB % 32 == 0 && I8_NA + I8_NB <= 512, "accumulator layout");
 // per-variant stage geometry: single-CTA UMMA keeps the whole digit operand, a cta_group::2 pair keeps half per CTA
 template <bool CG2> struct I8Geo {
     static constexpr int B_STAGE = CG2 ? I8_B_ALL / 2 : I8_B_ALL;
-    static constexpr int STAGE_BYTES = I8_A_BYTES + B_STAGE;           // 36 KiB / 22 KiB
+    static constexpr int STAGE_BYTES = I8_A_BYTES + B_STAGE;           // 32 KiB / 20 KiB
 };
 constexpr int I8_MAX_STAGES = 10;
 constexpr int I8_TTAB = 512;        // 64-row tiles per split that fit the shared-memory copy of the work list (the host plan keeps splits below it)
-// epilogue warps EW (template parameter, 8 or 16): EW / 4 per TMEM lane quarter, each takes 256 / EW of the 64 SNP rows of a
-// tile. 8 everywhere: with 16 a 576-thread CTA gets 96 registers per thread and the kernel is 13 % slower (measured, T = 5)
+constexpr int I8_EPI_WARPS = 8;     // two per TMEM lane quarter, each takes 32 of the 64 SNP rows of a tile (16 warps: 96 registers
+                                    // per thread and x4 TMEM loads, measured 13 % slower at T = 5)
+constexpr int I8_RPT = 32;          // SNP rows per epilogue thread and tile = one word of the bit-planes
+constexpr int I8_THREADS = 32 * (I8_EPI_WARPS + 2);
 
 // ------------------------------------------------------------------------------------------ prep: xi images
 // image (X tile, global k-block) : [chunk cc (4)][r1 (16)][r0 (8)][16 bytes], row r = 8 r1 + r0, k = 16 cc + b
@@ -118,7 +132,7 @@ __device__ __forceinline__ double lprime64(const double* __restrict__ tiles, con
 // Row scales, two steps. (1) rowmax[s][pj] = max_k |G_s[j,k]| over row j's lower-triangle range: one CTA per 64 x 64 block
 // with the digit builder's access pattern (every L' element read once, coalesced, used for all T traits), reduced in shared
 // memory and merged with an atomic max on the bit pattern (non-negative doubles order like unsigned integers; the buffer
-// starts at zero). (2) scale = 2^E with rowmax < 2^E (1 for a zero row; a row below 2^-900 counts as zero), in place.
+// starts at zero). (2) scale = 2^E with rowmax <= 0.996 * 2^E (1 for a zero row; a row below 2^-900 counts as zero), in place.
 __global__ void i8_rowmax_kernel(const double* __restrict__ tiles, const ChromDesc* __restrict__ chrom, int c_begin, int c_end,
                                  const int* __restrict__ blkpref, const double* __restrict__ emat, long long mp_total, int T,
                                  unsigned long long* __restrict__ rowmax) {
@@ -160,15 +174,11 @@ __global__ void i8_scale_kernel(double* __restrict__ scale, long long n) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const double v = scale[i];
-    int e = 0;
-    if (v > 0x1p-900) {
-        const double f = frexp(v, &e);              // v = f * 2^e, f in [0.5, 1)  =>  v < 2^e
-        if (f >= 1.0 - 0x1p-50) ++e;                // so that rn(|G| 2^(49 - e)) < 2^49 for every entry: no digit ever clamps
-    }
-    scale[i] = ldexp(1.0, e);
+    // rowmax <= 0.996 * 2^e, so that rn(G 2^(47 - e)) fits six balanced radix-256 digits: no entry ever saturates
+    scale[i] = ldexp(1.0, v > 0x1p-900 ? i8_scale_exp(v) : 0);
 }
 
-// digit images: (c, J, kb <= J, s): one 448-row K-major operand per (block, trait); one thread = 16 consecutive k of a
+// digit images: (c, J, kb <= J, s): one 384-row K-major operand per (block, trait); one thread = 16 consecutive k of a
 // row, L' read once and reused for all T traits
 __global__ void i8_build_digits_kernel(const double* __restrict__ tiles, const ChromDesc* __restrict__ chrom, int c_begin,
                                        int c_end, const int* __restrict__ blkpref, const double* __restrict__ emat,
@@ -191,9 +201,9 @@ __global__ void i8_build_digits_kernel(const double* __restrict__ tiles, const C
         const int col = kb * 64 + cc * 16 + b;
         lp[b] = (row < cd.m && col < cd.m) ? lprime64(tiles, cd, row, col) : 0.0;
     }
-    // the 7 digit planes of one (block, trait) form ONE K-major operand of 7 x 64 = 448 rows:
-    // [chunk cc (4)][row group R1 = 8 i + r1 (56)][r0 (8)][16 bytes]  ->  LBO = 56 * 128 B, SBO = 128 B,
-    // so a k32-step needs two MMAs (N = 256: digits 0-3, N = 192: digits 4-6) instead of seven N = 64 ones
+    // the 6 digit planes of one (block, trait) form ONE K-major operand of 6 x 64 = 384 rows:
+    // [chunk cc (4)][row group R1 = 8 i + r1 (48)][r0 (8)][16 bytes]  ->  LBO = 48 * 128 B, SBO = 128 B,
+    // so a k32-step needs two MMAs (N = 256: digits 0-3, N = 128: digits 4-5) instead of six N = 64 ones
     const int r1 = r >> 3, r0 = r & 7;
     const double* ecol = emat + cd.pad_off + kb * 64 + cc * 16;
     for (int s = 0; s < T; ++s) {
@@ -201,31 +211,26 @@ __global__ void i8_build_digits_kernel(const double* __restrict__ tiles, const C
         signed char d[I8_DIG][16];
 #pragma unroll
         for (int b = 0; b < 16; ++b) {
-            // |x| < 1 - 2^-50 (i8_scale_kernel); round-to-nearest-even to 49 fractional bits (unbiased, |error| <= 2^-50; the
-            // clamp never bites), then seven 7-bit sign-magnitude digits: integer arithmetic only
-            const double x = (lp[b] * ecol[(long long)s * mp_total + b]) * inv;
-            long long w = __double2ll_rn(fabs(x) * 0x1p49);                   // the product is exact
-            w = w > 0x1FFFFFFFFFFFFll ? 0x1FFFFFFFFFFFFll : w;
-            const int neg = x < 0.0;
+            // |x| <= 0.996 (i8_scale_kernel); round to nearest to 47 fractional bits (|error| <= 2^-48 of the row scale, the
+            // clamp never bites), then six balanced radix-256 digits: integer arithmetic only (i8digits.cuh)
+            signed char dg[I8_DIG];
+            i8_split(i8_fixed((lp[b] * ecol[(long long)s * mp_total + b]) * inv), dg);
 #pragma unroll
-            for (int i = 0; i < I8_DIG; ++i) {
-                const int dg = (int)((w >> (7 * (I8_DIG - 1 - i))) & 127);
-                d[i][b] = (signed char)(neg ? -dg : dg);
-            }
+            for (int i = 0; i < I8_DIG; ++i) d[i][b] = dg[i];
         }
 #pragma unroll
         for (int i = 0; i < I8_DIG; ++i) {
             signed char* img = G + gbase + (((long long)blk * T + s) * (long long)I8_B_ALL);
             int off;
             if (layout == 0) {
-                off = ((cc * (I8_DIG * 8) + (i * 8 + r1)) * 8 + r0) * 16;             // one 448-row operand
+                off = ((cc * (I8_DIG * 8) + (i * 8 + r1)) * 8 + r0) * 16;             // one 384-row operand
             } else {
-                // cta_group::2: the N = 256 MMA takes rows 0-127 from the leader and 128-255 from the peer, the N = 192
-                // MMA rows 0-95 / 96-191; each CTA's half is a 224-row operand [128 rows | 96 rows], halves back to back
-                const int g = i * 64 + r;                                           // row of the 448-row operand
-                const int h = g < 256 ? g / 128 : (g - 256) / 96;
-                const int lr = g < 256 ? g % 128 : 128 + (g - 256) % 96;
-                off = h * (I8_B_ALL / 2) + ((cc * 28 + (lr >> 3)) * 8 + (lr & 7)) * 16;
+                // cta_group::2: the N = 256 MMA takes rows 0-127 from the leader and 128-255 from the peer, the N = 128
+                // MMA rows 0-63 / 64-127; each CTA's half is a 192-row operand [128 rows | 64 rows], halves back to back
+                const int g = i * 64 + r;                                           // row of the 384-row operand
+                const int h = g < I8_NA ? g / (I8_NA / 2) : (g - I8_NA) / (I8_NB / 2);
+                const int lr = g < I8_NA ? g % (I8_NA / 2) : I8_NA / 2 + (g - I8_NA) % (I8_NB / 2);
+                off = h * (I8_B_ALL / 2) + ((cc * (I8_DIG * 4) + (lr >> 3)) * 8 + (lr & 7)) * 16;
             }
             *reinterpret_cast<uint4*>(img + off) = *reinterpret_cast<const uint4*>(d[i]);
         }
@@ -233,15 +238,20 @@ __global__ void i8_build_digits_kernel(const double* __restrict__ tiles, const C
 }
 
 // ------------------------------------------------------------------------------------------ main kernel
-// accumulator columns per tcgen05.ld in the epilogue: x8, or x4 with 16 epilogue warps (registers)
-__device__ __forceinline__ void i8_tmem_ldc(unsigned taddr, int (&v)[8]) {
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
-                 : "r"(taddr) : "memory");
-}
-__device__ __forceinline__ void i8_tmem_ldc(unsigned taddr, int (&v)[4]) {
+__device__ __forceinline__ void i8_tmem_ld4(unsigned taddr, int (&v)[4]) {       // 4 consecutive accumulator columns
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];"
                  : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]) : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void i8_tmem_ld1(unsigned taddr, int& v) {            // one accumulator column
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(v) : "r"(taddr) : "memory");
+}
+// wait for the thread's TMEM loads; the destination registers are operands, so nothing that reads them moves above
+__device__ __forceinline__ void i8_tmem_wait(int (&d)[I8_DIG][4]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(d[0][0]), "+r"(d[0][1]), "+r"(d[0][2]), "+r"(d[0][3]), "+r"(d[1][0]), "+r"(d[1][1]), "+r"(d[1][2]), "+r"(d[1][3]),
+                   "+r"(d[2][0]), "+r"(d[2][1]), "+r"(d[2][2]), "+r"(d[2][3]), "+r"(d[3][0]), "+r"(d[3][1]), "+r"(d[3][2]), "+r"(d[3][3]),
+                   "+r"(d[4][0]), "+r"(d[4][1]), "+r"(d[4][2]), "+r"(d[4][3]), "+r"(d[5][0]), "+r"(d[5][1]), "+r"(d[5][2]), "+r"(d[5][3])
+                 :: "memory");
 }
 
 // TT = T (SOUTER = false, T <= 6: loop "64-row tile outer, trait s inner", the cross's whole T x T table in registers)
@@ -250,11 +260,9 @@ __device__ __forceinline__ void i8_tmem_ldc(unsigned taddr, int (&v)[4]) {
 // Each CTA stages its own xi tile and only HALF of every digit tile; the leader CTA's MMA thread issues the pair's MMAs once
 // both halves have landed (the peer relays its `full` phases to the leader), and its commits release the slot / publish the
 // accumulators in BOTH CTAs. This halves the shared-memory traffic per MAC, which is what bounds the single-CTA kernel.
-template <int TT, bool SOUTER, bool CG2, int EW>
-__global__ void __launch_bounds__(32 * (EW + 2), 1) i8_contract_kernel(const I8Params p) {
-    constexpr int I8_EPI_WARPS = EW, I8_THREADS = 32 * (EW + 2);
-    constexpr int RPT = 256 / EW;                    // SNP rows per epilogue thread and tile
-    constexpr int I8_EC = EW == 8 ? 8 : 4;
+// SKIP = true: the epilogue visits only the rows where some cross of the warp has a non-zero mask entry (see the header).
+template <int TT, bool SOUTER, bool CG2, bool SKIP>
+__global__ void __launch_bounds__(I8_THREADS, 1) i8_contract_kernel(const I8Params p) {
     const int T = SOUTER ? p.T : TT;
     extern __shared__ __align__(1024) unsigned char smem[];
     unsigned char* stage0 = smem;
@@ -263,7 +271,10 @@ __global__ void __launch_bounds__(32 * (EW + 2), 1) i8_contract_kernel(const I8P
     unsigned long long* bars = reinterpret_cast<unsigned long long*>(smem + I8_STAGES * I8_STAGE_BYTES);
     unsigned* tmem_slot = reinterpret_cast<unsigned*>(bars + 2 * I8_MAX_STAGES + 2);
     int4* ttab = reinterpret_cast<int4*>(bars + 2 * I8_MAX_STAGES + 4);        // this CTA's range of the 64-row tile list (I8_TTAB entries)
-    double* rowbuf = reinterpret_cast<double*>(ttab + I8_TTAB);                // [2 buffers][3 T (or T + 2)][64]: d_t[j], then m_s[j] = 2^-49 scale_s[j], -2^52 m_s[j]
+    // row data of a tile, double-buffered: d_t[j] for T traits x 64 rows (FP64), then eb_s[j] = exponent field of scale_s[j] + 15
+    // (int) for T traits (tile-outer loop) or for the current trait (trait-outer loop)
+    unsigned char* rowbuf = reinterpret_cast<unsigned char*>(ttab + I8_TTAB);
+    const int rowbuf_bytes = T * 64 * 8 + (SOUTER ? 1 : T) * 64 * 4;
     const unsigned full0 = i8_smem_u32(bars), empty0 = i8_smem_u32(bars + I8_MAX_STAGES);
     const unsigned accfull = i8_smem_u32(bars + 2 * I8_MAX_STAGES), accempty = i8_smem_u32(bars + 2 * I8_MAX_STAGES + 1);
     const unsigned crank = CG2 ? i8_cta_rank() : 0u;       // 0 = leader of the pair
@@ -352,12 +363,12 @@ __global__ void __launch_bounds__(32 * (EW + 2), 1) i8_contract_kernel(const I8P
         } else {
             // instruction descriptor: D = S32, A = B = signed 8 bit, K-major both; M = 128 (256 over a CTA pair)
             const unsigned idesc0 = (2u << 4) | (1u << 7) | (1u << 10) | ((unsigned)((CG2 ? 2 * I8_M : I8_M) >> 4) << 24);
-            const unsigned idescA = idesc0 | ((unsigned)((4 * I8_N) >> 3) << 17);      // N = 256: digits 0-3
-            const unsigned idescB = idesc0 | ((unsigned)((3 * I8_N) >> 3) << 17);      // N = 192: digits 4-6
-            // rows of the digit operand held in THIS CTA's shared memory: all 448, or 128 + 96 (the pair's halves)
+            const unsigned idescA = idesc0 | ((unsigned)(I8_NA >> 3) << 17);           // N = 256: digits 0-3
+            const unsigned idescB = idesc0 | ((unsigned)(I8_NB >> 3) << 17);           // N = 128: digits 4-5
+            // rows of the digit operand held in THIS CTA's shared memory: all 384, or 128 + 64 (the pair's halves)
             constexpr unsigned B_ROWS = CG2 ? (I8_DIG * I8_N) / 2 : I8_DIG * I8_N;
             constexpr unsigned B_LBO = (B_ROWS / 8) * 128;                           // chunk stride
-            constexpr unsigned B_SECOND = (CG2 ? (4 * I8_N) / 2 : 4 * I8_N) / 8 * 128;   // byte offset of the N = 192 part
+            constexpr unsigned B_SECOND = (CG2 ? I8_NA / 2 : I8_NA) / 8 * 128;       // byte offset of the N = 128 part
             // descriptors of slot 0, k32-step 0; everything else is an add on the 14-bit address field
             const unsigned long long da0 = i8_desc(i8_smem_u32(stage0), I8_M * 16, 128);
             const unsigned long long db0 = i8_desc(i8_smem_u32(stage0) + I8_A_BYTES, B_LBO, 128);
@@ -378,10 +389,10 @@ __global__ void __launch_bounds__(32 * (EW + 2), 1) i8_contract_kernel(const I8P
                             const unsigned long long dbA = dbs + ((kk * 2 * B_LBO) >> 4), dbB = dbs + ((B_SECOND + kk * 2 * B_LBO) >> 4);
                             if (CG2) {
                                 i8_mma_cg2(tmem_base, da, dbA, idescA, (kb | kk) != 0);
-                                i8_mma_cg2(tmem_base + 4 * I8_N, da, dbB, idescB, (kb | kk) != 0);
+                                i8_mma_cg2(tmem_base + I8_NA, da, dbB, idescB, (kb | kk) != 0);
                             } else {
                                 i8_mma(tmem_base, da, dbA, idescA, (kb | kk) != 0);
-                                i8_mma(tmem_base + 4 * I8_N, da, dbB, idescB, (kb | kk) != 0);
+                                i8_mma(tmem_base + I8_NA, da, dbB, idescB, (kb | kk) != 0);
                             }
                         }
                         if (CG2) i8_commit_cg2(empty0 + 8 * slot, 3);     // frees the slot in BOTH CTAs when these MMAs retire
@@ -398,125 +409,156 @@ __global__ void __launch_bounds__(32 * (EW + 2), 1) i8_contract_kernel(const I8P
             });
         }
     } else {
-        // ------------------------------------------------------------------ epilogue: thread = one cross x one half of the columns
-        const int quarter = warp & 3, half = warp >> 2;       // TMEM lane quarter is fixed by warp id % 4; `half`: column group
+        // ------------------------------------------------------------------ epilogue: thread = one cross x one half of the rows
+        const int quarter = warp & 3, half = warp >> 2;       // TMEM lane quarter is fixed by warp id % 4; `half`: rows 32 half .. + 31
         const int etid = threadIdx.x;                          // 0 .. 255
         const long long unit = X * I8_M + quarter * 32 + lane;
         const bool live = unit < p.n_units;
         int pa = 0, pb = 0;
         if (live) { pa = p.unit_a[unit]; pb = (p.mode == MASK_XI) ? p.unit_b[unit] : 0; }
-        const unsigned tlane = tmem_base + ((unsigned)(quarter * 32) << 16) + half * RPT;
+        const unsigned tlane = tmem_base + ((unsigned)(quarter * 32) << 16) + half * I8_RPT;
+
+        // this thread's mask entries of the tile's rows (one word of the bit-planes): nz = non-zero, ng = negative
+        auto load_mask = [&](long long prow, unsigned& nz, unsigned& ng) {
+            nz = ng = 0u;
+            if (live) {
+                const long long wi = (prow >> 5) + half;
+                const unsigned A = __ldg(p.planeA + (long long)pa * p.wpp + wi), B = __ldg(p.planeB + (long long)pa * p.wpp + wi);
+                if (p.mode == MASK_XI) {
+                    const unsigned A2 = __ldg(p.planeA + (long long)pb * p.wpp + wi), B2 = __ldg(p.planeB + (long long)pb * p.wpp + wi);
+                    nz = (A ^ B) & (A2 ^ B2);
+                    ng = ((~A & B) ^ (~A2 & B2)) & nz;
+                } else {
+                    nz = A ^ B;
+                    ng = (p.mode == MASK_DELTA) ? (~A & B) : 0u;
+                }
+            }
+        };
+        auto release = [&]() {                       // TMEM fully read: the next (tile, trait)'s MMAs may start
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) { if (CG2) i8_mbar_arrive_remote(accempty, 0); else i8_mbar_arrive(accempty); }
+        };
+        // value of row jr (0..31 within this warp's half) from the digit sums in d[.][q]: xi_x[jr] * W * 2^(E - 47)
+        auto row_value = [&](const int (&d)[I8_DIG][4], int q, int jr, const int* ebrow, unsigned nz, unsigned ng) -> double {
+            unsigned bh, bl;
+            i8_cvt_bits(i8_combine(d[0][q], d[1][q], d[2][q], d[3][q], d[4][q], d[5][q]), ebrow[jr], (nz >> jr) & 1u, (ng >> jr) & 1u, bh, bl);
+            return __hiloint2double((int)bh, (int)bl);
+        };
+        // One unit = the finished accumulator of one (tile, trait): acc(jr, v) for the rows jr of this warp's half; the
+        // accumulator is released as soon as the last digits are in registers. TMEM loads are software-pipelined over groups
+        // of 4 rows (two register sets A / B): the loads of the next group are in flight while this one is combined.
+        auto process_unit = [&](unsigned rows, unsigned nz, unsigned ng, const int* ebrow, auto&& acc) {
+            int dA[I8_DIG][4], dB[I8_DIG][4];
+            if constexpr (!SKIP) {
+                auto load4 = [&](int ch, int (&d)[I8_DIG][4]) {
+#pragma unroll
+                    for (int i = 0; i < I8_DIG; ++i) i8_tmem_ld4(tlane + i * I8_N + ch * 4, d[i]);
+                };
+                auto math4 = [&](int ch, const int (&d)[I8_DIG][4]) {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) acc(ch * 4 + q, row_value(d, q, ch * 4 + q, ebrow, nz, ng));
+                };
+                constexpr int NCH = I8_RPT / 4;              // 8 chunks of 4 rows (an even number)
+                load4(0, dA);
+                i8_tmem_wait(dA);
+#pragma unroll 1
+                for (int cp = 0; cp < NCH / 2; ++cp) {
+                    load4(2 * cp + 1, dB);
+                    math4(2 * cp, dA);
+                    i8_tmem_wait(dB);
+                    if (cp + 1 < NCH / 2) load4(2 * cp + 2, dA); else release();
+                    math4(2 * cp + 1, dB);
+                    if (cp + 1 < NCH / 2) i8_tmem_wait(dA);
+                }
+            } else {
+                // rows = OR of nz over the warp (warp-uniform): walk its set bits four at a time
+                auto take4 = [&](unsigned& mm, int (&j)[4]) -> int {        // mm != 0 on entry; unused slots repeat j[0]
+                    const int n = min(__popc(mm), 4);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) { j[q] = mm ? __ffs(mm) - 1 : j[0]; mm &= mm - 1u; }
+                    return n;
+                };
+                auto loadg = [&](const int (&j)[4], int (&d)[I8_DIG][4]) {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q)
+#pragma unroll
+                        for (int i = 0; i < I8_DIG; ++i) i8_tmem_ld1(tlane + i * I8_N + j[q], d[i][q]);
+                };
+                auto mathg = [&](const int (&j)[4], int n, const int (&d)[I8_DIG][4]) {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q)
+                        if (q < n) acc(j[q], row_value(d, q, j[q], ebrow, nz, ng));
+                };
+                unsigned mm = rows;
+                if (mm == 0u) {
+                    release();
+                } else {
+                    int jA[4], jB[4], nA, nB = 0;
+                    nA = take4(mm, jA);
+                    loadg(jA, dA);
+                    i8_tmem_wait(dA);
+#pragma unroll 1
+                    for (;;) {
+                        const bool moreB = mm != 0u;
+                        if (moreB) { nB = take4(mm, jB); loadg(jB, dB); } else release();
+                        mathg(jA, nA, dA);
+                        if (!moreB) break;
+                        i8_tmem_wait(dB);
+                        const bool moreA = mm != 0u;
+                        if (moreA) { nA = take4(mm, jA); loadg(jA, dA); } else release();
+                        mathg(jB, nB, dB);
+                        if (!moreA) break;
+                        i8_tmem_wait(dA);
+                    }
+                }
+            }
+        };
+        // eb = exponent field of the (power-of-two, >= 2^-900) row scale + 15: see i8_cvt_bits
+        auto scale_eb = [&](int s, long long prow_j) -> int {
+            return (__double2hiint(__ldg(p.scale + (long long)s * p.mp_total + prow_j)) >> 20) + (63 - I8_FRAC - 1);
+        };
+
         if constexpr (!SOUTER) {
             double Z[TT][TT];
-    #pragma unroll
+#pragma unroll
             for (int t = 0; t < TT; ++t)
-    #pragma unroll
+#pragma unroll
                 for (int s = 0; s < TT; ++s) Z[t][s] = 0.0;
             unsigned acc_it = 0;
             for (int jt = jt_begin; jt < jt_end; ++jt) {
                 const long long prow = ttab[jt - jt_begin].y;                    // padded index of the tile's first row
-                // stage d_t[j] and, per (s, j), the pair (m, cm) = (2^-49 scale_s[j], -2^52 m) of the 64 rows in shared memory
-                // (double-buffered by tile parity); scale is a power of two >= 2^-900, so the pair is made with integer adds
-                double* rb = rowbuf + ((jt - jt_begin) & 1) * (3 * T * 64);
+                unsigned char* rb = rowbuf + ((jt - jt_begin) & 1) * rowbuf_bytes;
+                double* erow_all = reinterpret_cast<double*>(rb);                 // d_t[j]: [t][64]
+                int* eb_all = reinterpret_cast<int*>(rb + T * 64 * 8);            // eb_s[j]: [s][64]
                 for (int i = etid; i < 2 * T * 64; i += 32 * I8_EPI_WARPS) {
                     const int which = i / (T * 64), rem = i - which * (T * 64), t = rem >> 6, j = rem & 63;
-                    const double v = __ldg((which ? p.scale : p.emat) + (long long)t * p.mp_total + prow + j);
-                    if (!which) rb[i] = v;
-                    else {
-                        const int hi = __double2hiint(v);
-                        reinterpret_cast<double2*>(rb + T * 64)[rem] =
-                            make_double2(__hiloint2double(hi - (49 << 20), 0), __hiloint2double((hi + (3 << 20)) | (int)0x80000000, 0));
-                    }
+                    if (!which) erow_all[rem] = __ldg(p.emat + (long long)t * p.mp_total + prow + j);
+                    else eb_all[rem] = scale_eb(t, prow + j);
                 }
-                unsigned nz = 0u, ng = 0u;                                       // this thread's RPT rows: (part of) one word
-                if (live) {
-                    const long long wi = (prow >> 5) + (half * RPT) / 32;
-                    const unsigned A = __ldg(p.planeA + (long long)pa * p.wpp + wi), B = __ldg(p.planeB + (long long)pa * p.wpp + wi);
-                    if (p.mode == MASK_XI) {
-                        const unsigned A2 = __ldg(p.planeA + (long long)pb * p.wpp + wi), B2 = __ldg(p.planeB + (long long)pb * p.wpp + wi);
-                        nz = (A ^ B) & (A2 ^ B2);
-                        ng = ((~A & B) ^ (~A2 & B2)) & nz;
-                    } else {
-                        nz = A ^ B;
-                        ng = (p.mode == MASK_DELTA) ? (~A & B) : 0u;
-                    }
-                }
-                if (RPT < 32) { nz >>= (half * RPT) % 32; ng >>= (half * RPT) % 32; }
+                unsigned nz, ng;
+                load_mask(prow, nz, ng);
+                const unsigned rows = SKIP ? __reduce_or_sync(0xffffffffu, nz) : 0xffffffffu;
                 asm volatile("bar.sync 1, %0;" ::"n"(32 * I8_EPI_WARPS) : "memory");
-                const double* erow = rb + half * RPT;                // d_t[j]:     erow[t * 64 + c]
-                const double2* mrow = reinterpret_cast<const double2*>(rb + T * 64) + half * RPT;     // (m, cm): mrow[s * 64 + c]
-    #pragma unroll
+                const double* erow = erow_all + half * I8_RPT;       // erow[t * 64 + jr]
+                const int* ebh = eb_all + half * I8_RPT;              // ebh[s * 64 + jr]
+#pragma unroll
                 for (int s = 0; s < TT; ++s, ++acc_it) {               // unrolled: Z[t][s] must stay in registers
                     i8_mbar_wait(accfull, acc_it & 1u);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    if (I8_DBG(1)) {
-                        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-                        __syncwarp();
-                        if (lane == 0) { if (CG2) i8_mbar_arrive_remote(accempty, 0); else i8_mbar_arrive(accempty); }
-                        continue;
-                    }
-                    // software-pipelined over chunks of 4 SNP rows: the TMEM loads of chunk c + 1 are in flight while chunk c is
-                    // combined and accumulated (two register sets, A / B); the accumulator is released when the last chunk's
-                    // digits are in registers
-                    auto load4 = [&](int ch, int (&d)[I8_DIG][4]) {
-    #pragma unroll
-                        for (int i = 0; i < I8_DIG; ++i) i8_tmem_ldc(tlane + i * I8_N + ch * 4, d[i]);
-                    };
-                    auto wait4 = [&](int (&d)[I8_DIG][4]) {      // the registers are operands: nothing that reads them moves above
-                        asm volatile("tcgen05.wait::ld.sync.aligned;"
-                                     : "+r"(d[0][0]), "+r"(d[0][1]), "+r"(d[0][2]), "+r"(d[0][3]), "+r"(d[1][0]), "+r"(d[1][1]), "+r"(d[1][2]),
-                                       "+r"(d[1][3]), "+r"(d[2][0]), "+r"(d[2][1]), "+r"(d[2][2]), "+r"(d[2][3]), "+r"(d[3][0]), "+r"(d[3][1]),
-                                       "+r"(d[3][2]), "+r"(d[3][3]), "+r"(d[4][0]), "+r"(d[4][1]), "+r"(d[4][2]), "+r"(d[4][3]), "+r"(d[5][0]),
-                                       "+r"(d[5][1]), "+r"(d[5][2]), "+r"(d[5][3]), "+r"(d[6][0]), "+r"(d[6][1]), "+r"(d[6][2]), "+r"(d[6][3])
-                                     :: "memory");
-                    };
-                    auto release = [&]() {                       // TMEM fully read: the next (tile, trait)'s MMAs may start
-                        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-                        __syncwarp();
-                        if (lane == 0) { if (CG2) i8_mbar_arrive_remote(accempty, 0); else i8_mbar_arrive(accempty); }
-                    };
-                    auto math4 = [&](int ch, const int (&d)[I8_DIG][4]) {
-                        const unsigned nzw = nz >> (4 * ch), ngw = ng >> (4 * ch);
-    #pragma unroll
-                        for (int c = 0; c < 4; ++c) {
-                            // sum_i S_i 128^(6-i) exactly as a 64-bit integer, then times 2^-49 scale: three FP64 instructions
-                            const double2 mc = mrow[s * 64 + ch * 4 + c];
-                            double v = v2_scaled(v2_combine(d[0][c], d[1][c], d[2][c], d[3][c], d[4][c], d[5][c], d[6][c]), mc.x, mc.y);
-                            long long bits = __double_as_longlong(v);
-                            if (!((nzw >> c) & 1u)) bits = 0ll;
-                            bits ^= (long long)((ngw >> c) & 1u) << 63;
-                            v = __longlong_as_double(bits);
-    #pragma unroll
-                            for (int t = 0; t < TT; ++t) Z[t][s] = fma(erow[t * 64 + ch * 4 + c], v, Z[t][s]);
-                        }
-                    };
-                    constexpr int NCH = RPT / 4;                 // 8 chunks of 4 rows (an even number)
-                    int dA[I8_DIG][4], dB[I8_DIG][4];
-                    load4(0, dA);
-                    wait4(dA);
-    #pragma unroll 1
-                    for (int cp = 0; cp < NCH / 2; ++cp) {
-                        load4(2 * cp + 1, dB);
-                        math4(2 * cp, dA);
-                        wait4(dB);
-                        if (2 * cp + 1 == NCH - 1 && !(I8_DBG(512))) release();
-                        if (cp + 1 < NCH / 2) load4(2 * cp + 2, dA);
-                        math4(2 * cp + 1, dB);
-                        if (cp + 1 < NCH / 2) wait4(dA);
-                    }
-                    if (I8_DBG(512)) {       // profiling: release the accumulator only after ALL the FP64 work of the unit
-                        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-                        __syncwarp();
-                        if (lane == 0) { if (CG2) i8_mbar_arrive_remote(accempty, 0); else i8_mbar_arrive(accempty); }
-                    }
+                    if (I8_DBG(1)) { release(); continue; }
+                    process_unit(rows, nz, ng, ebh + s * 64, [&](int jr, double v) {
+#pragma unroll
+                        for (int t = 0; t < TT; ++t) Z[t][s] = fma(erow[t * 64 + jr], v, Z[t][s]);
+                    });
                 }
             }
             if (live) {
-                // the two column halves of a cross go to two partial slabs (summed by finalize_sym)
-                double* out = p.Zpart + ((long long)(split * (EW / 4) + half) * p.n_units + unit) * (T * T);
-    #pragma unroll
+                // the two row halves of a cross go to two partial slabs (summed by finalize_sym)
+                double* out = p.Zpart + ((long long)(split * 2 + half) * p.n_units + unit) * (T * T);
+#pragma unroll
                 for (int t = 0; t < TT; ++t)
-    #pragma unroll
+#pragma unroll
                     for (int s = 0; s < TT; ++s) out[t * T + s] = Z[t][s];
             }
         } else {
@@ -528,63 +570,30 @@ __global__ void __launch_bounds__(32 * (EW + 2), 1) i8_contract_kernel(const I8P
                 for (int t = 0; t < TT; ++t) zs[t] = 0.0;
                 for (int jt = jt_begin; jt < jt_end; ++jt, ++acc_it) {
                     const long long prow = ttab[jt - jt_begin].y;
-                    double* rb = rowbuf + (acc_it & 1) * ((T + 2) * 64);           // [T][64] d_t[j], then [64] pairs (m, cm) of trait s
+                    unsigned char* rb = rowbuf + (acc_it & 1) * rowbuf_bytes;
+                    double* erow_all = reinterpret_cast<double*>(rb);             // d_t[j]: [t][64]
+                    int* eb_all = reinterpret_cast<int*>(rb + T * 64 * 8);        // eb_s[j] of trait s: [64]
                     for (int i = etid; i < (T + 1) * 64; i += 32 * I8_EPI_WARPS) {
                         const int t = i >> 6, j = i & 63;
-                        if (t < T) rb[i] = __ldg(p.emat + (long long)t * p.mp_total + prow + j);
-                        else {
-                            const int hi = __double2hiint(__ldg(p.scale + (long long)s * p.mp_total + prow + j));
-                            reinterpret_cast<double2*>(rb + T * 64)[j] =
-                                make_double2(__hiloint2double(hi - (49 << 20), 0), __hiloint2double((hi + (3 << 20)) | (int)0x80000000, 0));
-                        }
+                        if (t < T) erow_all[i] = __ldg(p.emat + (long long)t * p.mp_total + prow + j);
+                        else eb_all[j] = scale_eb(s, prow + j);
                     }
-                    unsigned nz = 0u, ng = 0u;
-                    if (live) {
-                        const long long wi = (prow >> 5) + (half * RPT) / 32;
-                        const unsigned A = __ldg(p.planeA + (long long)pa * p.wpp + wi), B = __ldg(p.planeB + (long long)pa * p.wpp + wi);
-                        if (p.mode == MASK_XI) {
-                            const unsigned A2 = __ldg(p.planeA + (long long)pb * p.wpp + wi), B2 = __ldg(p.planeB + (long long)pb * p.wpp + wi);
-                            nz = (A ^ B) & (A2 ^ B2);
-                            ng = ((~A & B) ^ (~A2 & B2)) & nz;
-                        } else {
-                            nz = A ^ B;
-                            ng = (p.mode == MASK_DELTA) ? (~A & B) : 0u;
-                        }
-                    }
-                    if (RPT < 32) { nz >>= (half * RPT) % 32; ng >>= (half * RPT) % 32; }
+                    unsigned nz, ng;
+                    load_mask(prow, nz, ng);
+                    const unsigned rows = SKIP ? __reduce_or_sync(0xffffffffu, nz) : 0xffffffffu;
                     asm volatile("bar.sync 1, %0;" ::"n"(32 * I8_EPI_WARPS) : "memory");
-                    const double* erow = rb + half * RPT;
-                    const double2* mrow = reinterpret_cast<const double2*>(rb + T * 64) + half * RPT;
+                    const double* erow = erow_all + half * I8_RPT;
                     i8_mbar_wait(accfull, acc_it & 1u);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-#pragma unroll 1
-                    for (int cb = 0; cb < RPT / I8_EC; ++cb) {
-                        int dig[I8_DIG][I8_EC];
+                    if (I8_DBG(1)) { release(); continue; }
+                    process_unit(rows, nz, ng, eb_all + half * I8_RPT, [&](int jr, double v) {
 #pragma unroll
-                        for (int i = 0; i < I8_DIG; ++i) i8_tmem_ldc(tlane + i * I8_N + cb * I8_EC, dig[i]);
-                        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                        if (cb == RPT / I8_EC - 1) {
-                            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-                            __syncwarp();
-                            if (lane == 0) { if (CG2) i8_mbar_arrive_remote(accempty, 0); else i8_mbar_arrive(accempty); }
-                        }
-                        const unsigned nzw = nz >> (I8_EC * cb), ngw = ng >> (I8_EC * cb);
-#pragma unroll
-                        for (int c = 0; c < I8_EC; ++c) {
-                            const double2 mc = mrow[cb * I8_EC + c];
-                            double v = v2_scaled(v2_combine(dig[0][c], dig[1][c], dig[2][c], dig[3][c], dig[4][c], dig[5][c], dig[6][c]), mc.x, mc.y);
-                            long long bits = __double_as_longlong(v);
-                            if (!((nzw >> c) & 1u)) bits = 0ll;
-                            bits ^= (long long)((ngw >> c) & 1u) << 63;
-                            v = __longlong_as_double(bits);
-#pragma unroll
-                            for (int t = 0; t < TT; ++t)
-                                if (t < T) zs[t] = fma(erow[t * 64 + cb * I8_EC + c], v, zs[t]);
-                        }
-                    }
+                        for (int t = 0; t < TT; ++t)
+                            if (t < T) zs[t] = fma(erow[t * 64 + jr], v, zs[t]);
+                    });
                 }
                 if (live) {
-                    double* out = p.Zpart + ((long long)(split * (EW / 4) + half) * p.n_units + unit) * (T * T);
+                    double* out = p.Zpart + ((long long)(split * 2 + half) * p.n_units + unit) * (T * T);
 #pragma unroll
                     for (int t = 0; t < TT; ++t)
                         if (t < T) out[t * T + s] = zs[t];
@@ -602,13 +611,12 @@ __global__ void __launch_bounds__(32 * (EW + 2), 1) i8_contract_kernel(const I8P
     }
 }
 
-// epilogue warps for T traits (see the kernel)
-int i8_epi_warps(int T) { (void)T; return 8; }    // 16 (96 registers per thread, x4 TMEM loads) measured 13 % slower at T = 5
-int i8_npart(int T) { return i8_epi_warps(T) / 4; }       // partial slabs per split: one per column group
+int i8_npart(int T) { (void)T; return 2; }                 // partial slabs per split: one per row half
 int i8_max_tiles_per_split() { return I8_TTAB; }
+long long i8_block_bytes() { return I8_B_ALL; }            // digit image of one (64 x 64 block, trait)
 static size_t i8_fixed_smem(int T) {
-    const int rows = T <= 6 ? 3 * T : T + 2;          // per buffer: d_t[j] rows + (m, cm) pair rows (see the two epilogues)
-    return (2 * I8_MAX_STAGES + 4) * 8 + (size_t)I8_TTAB * 16 + (size_t)2 * rows * 64 * 8;
+    const size_t rowbuf = (size_t)T * 64 * 8 + (size_t)(T <= 6 ? T : 1) * 64 * 4;          // per buffer (see the two epilogues)
+    return (2 * I8_MAX_STAGES + 4) * 8 + (size_t)I8_TTAB * 16 + 2 * rowbuf;
 }
 // pipeline stages: as many as fit in the 227 KiB a CTA may use (the kernel is bound by the latency of its operand stream)
 int i8_stages(int T, bool cg2) {
@@ -645,7 +653,7 @@ cudaError_t launch_i8_build_digits(const double* tiles, const ChromDesc* chrom_d
     return cudaGetLastError();
 }
 
-cudaError_t launch_i8_contract(const I8Params& p, int ntiles, int nsplit, bool pair, cudaStream_t st) {
+cudaError_t launch_i8_contract(const I8Params& p, int ntiles, int nsplit, bool pair, bool skip, cudaStream_t st) {
     if (ntiles == 0) return cudaSuccess;
     const size_t smem = i8_smem_bytes(p.T, pair);
     I8Params pp = p;
@@ -653,7 +661,7 @@ cudaError_t launch_i8_contract(const I8Params& p, int ntiles, int nsplit, bool p
     cudaError_t e = cudaSuccess;
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(pair ? (ntiles + 1) / 2 * 2 : ntiles, nsplit, 1);
-    cfg.blockDim = dim3(32 * (i8_epi_warps(p.T) + 2), 1, 1);
+    cfg.blockDim = dim3(I8_THREADS, 1, 1);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
@@ -661,27 +669,31 @@ cudaError_t launch_i8_contract(const I8Params& p, int ntiles, int nsplit, bool p
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = pair ? 1 : 0;
-#define GMS_I8_ONE(TV, SO, PR, EWV)                                                                                             \
+#define GMS_I8_ONE(TV, SO, PR, SK)                                                                                              \
     {                                                                                                                           \
-        e = cudaFuncSetAttribute(i8_contract_kernel<TV, SO, PR, EWV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);  \
+        e = cudaFuncSetAttribute(i8_contract_kernel<TV, SO, PR, SK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);   \
         if (e != cudaSuccess) return e;                                                                                         \
-        e = cudaLaunchKernelEx(&cfg, i8_contract_kernel<TV, SO, PR, EWV>, pp);                                                  \
+        e = cudaLaunchKernelEx(&cfg, i8_contract_kernel<TV, SO, PR, SK>, pp);                                                   \
         if (e != cudaSuccess) return e;                                                                                         \
     }
-#define GMS_I8(TV, SO, EWV) { if (pair) GMS_I8_ONE(TV, SO, true, EWV) else GMS_I8_ONE(TV, SO, false, EWV) }
+#define GMS_I8(TV, SO)                                                                                                          \
+    {                                                                                                                           \
+        if (pair) { if (skip) GMS_I8_ONE(TV, SO, true, true) else GMS_I8_ONE(TV, SO, true, false) }                             \
+        else { if (skip) GMS_I8_ONE(TV, SO, false, true) else GMS_I8_ONE(TV, SO, false, false) }                                \
+    }
     switch (p.T) {
-        case 1: GMS_I8(1, false, 8) break;
-        case 2: GMS_I8(2, false, 8) break;
-        case 3: GMS_I8(3, false, 8) break;
-        case 4: GMS_I8(4, false, 8) break;
-        case 5: GMS_I8(5, false, 8) break;
-        case 6: GMS_I8(6, false, 8) break;
+        case 1: GMS_I8(1, false) break;
+        case 2: GMS_I8(2, false) break;
+        case 3: GMS_I8(3, false) break;
+        case 4: GMS_I8(4, false) break;
+        case 5: GMS_I8(5, false) break;
+        case 6: GMS_I8(6, false) break;
         default:
-            if (p.T <= 8) GMS_I8(8, true, 8)
-            else if (p.T <= 12) GMS_I8(12, true, 8)
-            else if (p.T <= 16) GMS_I8(16, true, 8)
-            else if (p.T <= 24) GMS_I8(24, true, 8)
-            else if (p.T <= 32) GMS_I8(32, true, 8)
+            if (p.T <= 8) GMS_I8(8, true)
+            else if (p.T <= 12) GMS_I8(12, true)
+            else if (p.T <= 16) GMS_I8(16, true)
+            else if (p.T <= 24) GMS_I8(24, true)
+            else if (p.T <= 32) GMS_I8(32, true)
             else return cudaErrorInvalidValue;
     }
 #undef GMS_I8

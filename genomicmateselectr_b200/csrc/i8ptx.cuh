@@ -1,4 +1,4 @@
-// Inline PTX used by the int8 tcgen05 kernels (i8path.cu, i8v2.cu): mbarriers, bulk copies, UMMA descriptors, MMA issue /
+// Inline PTX used by the int8 tcgen05 kernel (i8path.cu): mbarriers, bulk copies, UMMA descriptors, MMA issue /
 // commit for cta_group::1 and ::2, cluster helpers.
 #pragma once
 #include <cuda_runtime.h>
@@ -88,35 +88,6 @@ __device__ __forceinline__ bool v2_elect() {
     unsigned pred;
     asm volatile("{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\nselp.u32 %0, 1, 0, p;\n}\n" : "=r"(pred));
     return pred != 0;
-}
-
-
-// W = sum_i S_i 128^(6 - i) of the seven digit sums as ONE 64-bit integer (|S_i| <= 127 k, so |W| < 2^60 up to k = 2^17):
-// integer instructions only - on B200 FP32 / FP64 instructions do not overlap with tcgen05 MMAs (tools/tc_contention_probe.cu:
-// their time ADDS to the tensor time), INT32 instructions do
-__device__ __forceinline__ long long v2_combine(int d0, int d1, int d2, int d3, int d4, int d5, int d6) {
-    const int w01 = d0 * 128 + d1, w23 = d2 * 128 + d3, w45 = d4 * 128 + d5;
-    long long w = (long long)w45 * 128 + (long long)d6;
-    w += (long long)w23 * 2097152;                         // 2^21
-    return w + ((long long)w01 << 35);
-}
-// vm = W * m for m = +-2^e given as (m, cm = -2^52 m): three FP64 instructions. W = hi 2^21 + lo (lo: 21 bits, >= 0);
-// hi (|hi| < 2^40) -> FP64 exactly by the 1.5 x 2^52 exponent-bias trick, lo by the 2^52 one, R = hi 2^21 + lo + 2^52
-// (rounded to 53 bits only if |W| > 2^52), vm = R m - 2^52 m
-__device__ __forceinline__ double v2_scaled(long long w, double m, double cm) {
-    const long long hi = w >> 21;
-    const int lo = (int)((unsigned)w & 0x1FFFFFu);
-    const double thi = __longlong_as_double(hi + 0x4338000000000000LL) - 6755399441055744.0;
-    const double r = fma(thi, 2097152.0, __hiloint2double(0x43300000, lo));
-    return fma(r, m, cm);
-}
-__device__ __forceinline__ long long v2_madw(int a, int b, long long c) {      // one IMAD.WIDE: a * b + c, 32 x 32 + 64 bit, signed
-    long long d;
-    asm("mad.wide.s32 %0, %1, %2, %3;" : "=l"(d) : "r"(a), "r"(b), "l"(c));
-    return d;
-}
-__device__ __forceinline__ double v2_flip(double x, unsigned sgn) {      // sgn = 0 or 0x80000000
-    return __hiloint2double((int)((unsigned)__double2hiint(x) ^ sgn), __double2loint(x));
 }
 
 

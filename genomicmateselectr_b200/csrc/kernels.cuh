@@ -1,6 +1,7 @@
 // Launchers of the small (HBM-bound) kernels around the contraction; see kernels.cu.
 #pragma once
 #include "common.cuh"
+#include "i8digits.cuh"
 
 namespace gms {
 
@@ -50,7 +51,7 @@ cudaError_t launch_scan_prepare(const double* emat, const double* apos, const do
                                 double* S, cudaStream_t st);
 cudaError_t launch_scan(const ScanParams& p, int nsplit, cudaStream_t st);
 
-// ---- exact int8 tensor-core path for the per-cross term (i8path.cu) ----
+// ---- int8 tensor-core path for the quadratic-form tables (i8path.cu) ----
 struct I8Params {
     const ChromDesc* chrom;
     const RowTile* jtiles;       // (c, J): 64-row tiles of the lower block triangle, ordered by (c, J)
@@ -72,8 +73,7 @@ struct I8Params {
     int mode;
     double* Zpart;               // [nsplit][n_units][T*T]
     int stages;                  // pipeline depth (set by launch_i8_contract)
-    int debug;                   // -DGMS_PROFILE builds only (GMS_I8_DEBUG bit mask; results are garbage): 1 no epilogue arithmetic,
-                                 // 2 no MMAs, 512 release the accumulator after all arithmetic of a unit
+    int debug;                   // -DGMS_PROFILE builds only (GMS_I8_DEBUG bit mask; results are garbage): 1 no epilogue arithmetic, 2 no MMAs
 };
 size_t i8_smem_bytes(int T, bool cg2);
 cudaError_t launch_i8_build_xi(const unsigned* planeA, const unsigned* planeB, long long wpp, const int* sire,
@@ -83,7 +83,9 @@ cudaError_t launch_i8_build_digits(const double* tiles, const ChromDesc* chrom_d
                                    const int* blkpref_d, int nblks, const double* emat, long long mp_total, int T,
                                    double* scale, double* smax, const long long* gbase_d, signed char* G, int layout,
                                    cudaStream_t st);     // layout: 0 / 1 = plain / cta_group::2; smax[T][C]: see verify.cu
-cudaError_t launch_i8_contract(const I8Params& p, int ntiles, int nsplit, bool pair, cudaStream_t st);
+// skip: the epilogue visits only rows where some cross of a warp has a non-zero mask entry (pays when the units of a warp share a parent)
+cudaError_t launch_i8_contract(const I8Params& p, int ntiles, int nsplit, bool pair, bool skip, cudaStream_t st);
+long long i8_block_bytes();         // bytes of the digit image of one (64 x 64 block, trait)
 int i8_npart(int T);        // partial slabs per split written by launch_i8_contract
 int i8_max_tiles_per_split();       // the plan must cut the 64-row tile list into splits no longer than this
 

@@ -2,11 +2,11 @@
 // (parent or cross), evaluated on the device right after each table, and a list of the units that fail it. The
 // failing units are re-evaluated by the FP64 contraction (contract.cu) in the same stream; see api.cu.
 //
-// Why a bound is needed. The int8 path rounds G_s[j,k] = L'[j,k] e_s[k] to 49 fractional bits RELATIVE TO THE ROW SCALE
-// scale_s[j] = 2^E > max_k |G_s[j,k]| (i8path.cu). That is fixed point, not floating point: a SNP with a huge effect sets the
-// scale of every row it reaches, and a unit in which that SNP does not segregate (mask 0) sums only small terms that
-// each carry the absolute error u * scale_s[j], u = 2^-50 (round to nearest; i8_scale_kernel picks E so that no digit
-// ever needs clamping). For unit x with mask mu in {-1,0,1}^m, row j of the lower block triangle sums over the non-zero
+// Why a bound is needed. The int8 path rounds G_s[j,k] = L'[j,k] e_s[k] to 47 fractional bits RELATIVE TO THE ROW SCALE
+// scale_s[j] = 2^E >= max_k |G_s[j,k]| / 0.996 (i8path.cu, i8digits.cuh). That is fixed point, not floating point: a SNP with
+// a huge effect sets the scale of every row it reaches, and a unit in which that SNP does not segregate (mask 0) sums only
+// small terms that each carry the absolute error u * scale_s[j], u = I8_U = 2^-48 (1 + 2^-4): 2^-48 from rounding to
+// nearest (i8_scale_kernel picks E so that no digit ever saturates) plus the 53-bit truncation of a row sum in the epilogue. For unit x with mask mu in {-1,0,1}^m, row j of the lower block triangle sums over the non-zero
 // mask entries k of its chromosome with k < 64 (floor(j / 64) + 1), at most n_j = (non-zeros before j) + 128 of them, so
 //     |Z[t][s] - exact| <= u * sum_j |e_t[j] mu_j| * scale_s[j] * n_j  <=  u * Smax_s * B_t(x),
 //     B_t(x) = sum_j |e_t[j] mu_j| n_j,   Smax_s = largest row scale of trait s.
@@ -16,9 +16,10 @@
 // every covariance to tau of its variance scale (the guard of tests/util.py:rel_err is 1e-6 of that scale at 1e-9).
 // By Cauchy-Schwarz the same then holds for VarA = (Q_S + Q_D) / 4 and VarD = (P_S + P_D + 2 X) / 16. It is a worst-case
 // bound (all rounding errors maximal and aligned); the error actually made is ~sqrt(n) times smaller. On N(0,1)
-// effects at cassava scale the bound sits at 0.7 % (crosses) - 1.5 % (parents) of tau: nothing fails.
-// A unit also fails when it has >= 16384 non-zero mask entries on one chromosome: beyond that the exact 64-bit
-// recombination of the digit sums (i8ptx.cuh: v2_combine) could overflow.
+// effects the bound sits at 3.5 % (crosses) - 6.5 % (parents) of tau at cassava scale and at 7 % - 18 % at the large
+// configuration (100k SNPs, T = 10): nothing fails.
+// A unit also fails when it has >= 16384 non-zero mask entries on one chromosome: from 32768 on the exact 64-bit
+// recombination of the digit sums (i8digits.cuh: i8_combine) could overflow; the limit keeps a factor of two in hand.
 #include "kernels.cuh"
 
 namespace gms {
@@ -44,7 +45,7 @@ __global__ void i8_smax_kernel(const double* __restrict__ rowmax, const ChromDes
         for (int i = 1; i < (int)(blockDim.x >> 5); ++i) mx = fmax(mx, sh[i]);
         int e = 0;
         double v = 0.0;
-        if (mx > 0x1p-900) { const double f = frexp(mx, &e); if (f >= 1.0 - 0x1p-50) ++e; v = ldexp(1.0, e); }   // = i8_scale_kernel's rule
+        if (mx > 0x1p-900) { e = i8_scale_exp(mx); v = ldexp(1.0, e); }   // = i8_scale_kernel's rule
         smax[(long long)s * C + c] = v;
     }
 }
@@ -143,7 +144,7 @@ __global__ void i8_verify_check_kernel(const VerifyParams p) {
         amax = fmax(amax, b > 0.0 ? (v > 0.0 ? b * r : INFINITY) : 0.0);
         smax = fmax(smax, sm > 0.0 ? (v > 0.0 ? sm * r : INFINITY) : 0.0);
     }
-    const double bound = 2.0 * 0x1p-50 * amax * smax;
+    const double bound = 2.0 * I8_U * amax * smax;
     // NaN-safe: anything that is not provably within tau fails
     const bool ok = (bound <= p.tau || (amax == 0.0 || smax == 0.0)) && nnz_max < 16384;
     if (p.bound_out) p.bound_out[unit] = bound;

@@ -1,0 +1,14 @@
+"""Known-answer test of the fixed-point arithmetic the int8 tensor path runs on the device (csrc/i8digits.cuh is shared
+between the kernels and this host build): balanced radix-256 digit split, exact 64-bit recombination of the digit sums for
+up to 32767 same-sign terms, and the integer-only FP64 conversion of the epilogue against exact arithmetic."""
+import os
+import subprocess
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_i8digits_known_answers(tmp_path):
+    exe = str(tmp_path / "i8digits_kat")
+    subprocess.run(["g++", "-O2", "-std=c++17", "-o", exe, os.path.join(ROOT, "tests", "csrc", "i8digits_kat.cpp")], check=True)
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and r.stdout.startswith("ok "), r.stdout + r.stderr

@@ -86,16 +86,26 @@ def test_prefix_sum_form_of_a_map_derived_matrix():
 
 
 def test_int8_digit_planes_are_an_error_free_split():
-    """Row-scaled radix-128 digits (csrc/i8path.cu): G = 2^E sum_i g_i 128^-(i+1) + r, |r| <= 2^(E-49), |g_i| <= 127."""
+    """Row-scaled balanced radix-256 digits (csrc/i8digits.cuh): with rowmax <= 0.996 * 2^E and w = rn(G 2^(47 - E)),
+    w = sum_i g_i 256^(5 - i), g_i in [-128, 127], |w 2^(E - 47) - G| <= 2^(E - 48); ternary dot products of the digit
+    planes recombine to the exact integer dot product."""
     rng = np.random.default_rng(4)
     G = rng.standard_normal((20, 300)) * np.exp(rng.normal(0, 3, (20, 1)))
-    E = np.frexp(np.abs(G).max(axis=1))[1]
-    r = G / np.ldexp(1.0, E)[:, None]
-    rec = np.zeros_like(G)
-    for i in range(7):
-        r = r * 128.0
-        d = np.trunc(r)
-        assert np.all(np.abs(d) <= 127)
-        rec += d * 128.0 ** -(i + 1)
-        r = r - d
-    assert np.all(np.abs(rec * np.ldexp(1.0, E)[:, None] - G) <= np.ldexp(1.0, E - 49)[:, None])
+    f, E = np.frexp(np.abs(G).max(axis=1))
+    E = E + (f > 0.996)
+    w = np.rint(G / np.ldexp(1.0, E)[:, None] * 2.0 ** 47).astype(np.int64)
+    assert np.all(np.abs(w) <= 127 * 0x010101010101)
+    digits, r = [], w.copy()
+    for _ in range(6):
+        g = ((r + 128) & 255) - 128
+        digits.append(g)
+        r = (r - g) >> 8
+    assert np.all(r == 0) and all(np.all((g >= -128) & (g <= 127)) for g in digits)
+    digits = digits[::-1]                                     # most significant first
+    rec = sum(g.astype(np.int64) << (8 * (5 - i)) for i, g in enumerate(digits))
+    assert np.array_equal(rec, w)
+    assert np.all(np.abs(rec * np.ldexp(1.0, E - 47)[:, None] - G) <= np.ldexp(1.0, E - 48)[:, None])
+    xi = rng.integers(-1, 2, 300)
+    S = [g @ xi for g in digits]                              # what the tensor cores accumulate, one plane at a time
+    W = [sum(int(S[i][j]) << (8 * (5 - i)) for i in range(6)) for j in range(20)]
+    assert W == [int(v) for v in (w @ xi)]
