@@ -33,7 +33,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 METRIC = "cross variance-covariance predictions/sec (A+AD, 5 traits)"
-NDIG = 6            # digit planes of the int8 path (csrc/i8digits.cuh: I8_DIG)
+NDIG = 7            # digit planes of the int8 path (csrc/i8digits.cuh: I8_DIG); main() reads the library's own value
 UNIT = "crosses/s"
 
 
@@ -304,6 +304,11 @@ def main():
     dom = d["dom"] if args.model != "A" else None
     asub = (d["add"] + d["dom"] * 0.1) if args.model == "DirDom" else None
 
+    global NDIG
+    import re
+    from genomicmateselectr_b200 import _capi
+    mt = re.search(r"digit planes: (\d+)", _capi.lib().gms_version().decode())
+    NDIG = int(mt.group(1)) if mt else NDIG
     eng = CrossVarEngine(local_rank)
     eng.set_cache(False)                  # the headline recomputes everything every step
     stream = torch.cuda.Stream()          # a real (non-default) stream: handle 0 would mean "engine's own stream"
@@ -431,13 +436,13 @@ def main():
                 "kernel_ms": r["kernel_ms"], "kernel_share_of_step": r["kernel_ms"] / r["step_ms_sync"]}
 
     def int8_roofline(r):
-        """int8 tensor (tcgen05) roofline of i8_contract_kernel: 6 digit planes x ternary xi, THIS rank's chromosomes."""
+        """int8 tensor (tcgen05) roofline of i8_contract_kernel: NDIG digit planes x ternary xi, THIS rank's chromosomes."""
         if args.model == "A" or r["kernel_ms"] <= 0:
             return None
         c0, c1 = S.balance_chromosomes(d["m_c"], gc)[ci] if gc > 1 else (0, len(d["m_c"]))
         mc = np.asarray(d["m_c"][c0:c1], dtype=np.float64)
         nJ = np.ceil(mc / 64.0)
-        alg = 2.0 * NDIG * T * n_loc * float(np.sum(mc * (mc + 1) / 2))                 # lower triangle incl. diagonal, 6 digits
+        alg = 2.0 * NDIG * T * n_loc * float(np.sum(mc * (mc + 1) / 2))                 # lower triangle incl. diagonal, NDIG digit planes
         exe = 2.0 * NDIG * T * (np.ceil(n_loc / 256.0) * 256) * float(np.sum(64 * 64 * nJ * (nJ + 1) / 2))
         ach = alg / (r["kernel_ms"] * 1e-3) / 1e12
         return {"bound": "tensor", "kernel": "i8_contract_kernel (tcgen05.mma kind::i8, int32 accumulators in TMEM, cp.async.bulk staged)",
@@ -450,9 +455,9 @@ def main():
                 "frac_of_library_int8_gemm_in_run": (ach / int8_lib) if int8_lib else None,
                 "algorithmic_ops_per_launch": alg, "executed_ops_per_launch": exe,
                 "executed_tops": exe / (r["kernel_ms"] * 1e-3) / 1e12,
-                "note": "algorithmic = 6 balanced radix-256 digit planes x the exact lower triangle (incl. diagonal) of every chromosome "
+                "note": f"algorithmic = {NDIG} balanced radix-256 digit planes x the exact lower triangle (incl. diagonal) of every chromosome "
                         "block of this rank's shard x T traits x crosses; executed adds 64-granular block and 256-cross tile-pair padding. "
-                        "Round 1 used 7 radix-128 planes: per cross the same kernel now does 6/7 of the operations. In FP64-flop terms "
+                        "In FP64-flop terms "
                         "(SURVEY 8d: 2 T S2 per cross) the kernel runs at "
                         f"{2.0 * T * float(np.sum(mc * mc)) * n_loc / (r['kernel_ms'] * 1e-3) / 1e12:.0f} TFLOP/s-equivalent, a speed-up over "
                         "the FP64 roofline, not a fraction of it",
@@ -550,7 +555,7 @@ def main():
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
                 "scaling": "strong" if strong else "weak", "vs_baseline": None,
-                "dtype": "f64 results; " + ("int8 digit planes on tcgen05 (6 balanced radix-256 planes = 47-bit row-scaled fixed point, a-posteriori error bound, "
+                "dtype": "f64 results; " + (f"int8 digit planes on tcgen05 ({NDIG} balanced radix-256 planes = {8 * NDIG - 1 - (6 if NDIG == 7 else 0)}-bit row-scaled fixed point, a-posteriori error bound, "
                                             "FP64 re-evaluation of failing units) + f64 recombination"
                                             if head["resolved_mode"] == "int8_tensor" else "f64 DMMA"),
                 "data": "synthetic", "config": config, "resolved_mode": head["resolved_mode"], "clocks": clocks,

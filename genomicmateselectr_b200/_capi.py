@@ -6,7 +6,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libgms_b200.so")
+# GMS_B200_LIB: profiling hook (tools/): load another build of the same library, e.g. one compiled with -DGMS_PROFILE
+LIB_PATH = os.environ.get("GMS_B200_LIB") or os.path.join(_HERE, "lib", "libgms_b200.so")
 
 GMS_OK, GMS_EINVAL, GMS_ECUDA, GMS_ENOMEM, GMS_ESTATE = 0, -1, -2, -3, -4
 MODEL = {"A": 0, "AD": 1, "DirDom": 2}

@@ -8,7 +8,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libgms_b200.so")
 SOURCES = ["api.cu", "contract.cu", "kernels.cu", "scan.cu", "i8path.cu", "verify.cu"]
-HEADERS = ["common.cuh", "kernels.cuh", "i8ptx.cuh", os.path.join("..", "..", "include", "gms_b200.h")]
+HEADERS = ["common.cuh", "kernels.cuh", "i8ptx.cuh", "i8digits.cuh", os.path.join("..", "..", "include", "gms_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden"]
 
@@ -26,6 +26,18 @@ def needs_build():
     t = os.path.getmtime(LIB)
     deps = [os.path.join(CSRC, s) for s in SOURCES + HEADERS] + [os.path.abspath(__file__)]
     return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build_variant(name, defines):
+    """Another build of the same library for tools/ (never the product): lib/<name>/libgms_b200.so, loaded through GMS_B200_LIB.
+    -DGMS_PROFILE compiles the profiling switches of csrc/i8path.cu in (GMS_I8_DEBUG then turns the MMAs, the copies or the
+    epilogue arithmetic off - results are garbage); -DGMS_I8_DIG=6 selects six digit planes."""
+    out = os.path.join(LIBDIR, name)
+    os.makedirs(out, exist_ok=True)
+    lib = os.path.join(out, "libgms_b200.so")
+    srcs = [os.path.join(CSRC, s) for s in SOURCES]
+    subprocess.run([_nvcc(), *NVCC_FLAGS, *defines, "-shared", "-o", lib, *srcs], check=True)
+    return lib
 
 
 def build_library(force=False, verbose=False):
@@ -47,4 +59,9 @@ def build_library(force=False, verbose=False):
 
 
 if __name__ == "__main__":
-    print(build_library(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    if "--variants" in sys.argv:
+        print(build_variant("profile7", ["-DGMS_PROFILE"]))
+        print(build_variant("profile6", ["-DGMS_PROFILE", "-DGMS_I8_DIG=6"]))
+        print(build_variant("dig6", ["-DGMS_I8_DIG=6"]))
+    else:
+        print(build_library(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -948,7 +948,9 @@ int settle(gms_handle* h) {
 extern "C" {
 
 const char* gms_version(void) {
-    return "gms_b200 0.2 (sm_100a; int8 digit-plane tcgen05 contraction with FP64 error-bound fallback; FP64 DMMA contraction; map scan)";
+    static const std::string v = std::string("gms_b200 0.3 (sm_100a; int8 tcgen05 contraction, digit planes: ") + std::to_string(I8_DIG) +
+                                 ", FP64 error-bound fallback; FP64 DMMA contraction; map scan)";
+    return v.c_str();
 }
 
 const char* gms_last_error(const gms_handle* h) {

@@ -45,17 +45,17 @@ namespace gms {
 constexpr int I8_M = 128;        // crosses per tile (TMEM lanes)
 constexpr int I8_N = 64;         // SNP rows j per accumulator
 constexpr int I8_KB = 64;        // k per pipeline stage (bytes of int8)
-// I8_DIG = 6 balanced radix-256 digits (i8digits.cuh)
+// I8_DIG = 7 (or 6) balanced radix-256 digits (i8digits.cuh)
 constexpr int I8_NA = 4 * I8_N;                     // N of the first MMA of a k32-step: digits 0-3 (256 = the UMMA maximum)
-constexpr int I8_NB = (I8_DIG - 4) * I8_N;          // N of the second: digits 4-5
+constexpr int I8_NB = (I8_DIG - 4) * I8_N;          // N of the second: the remaining digits (192 or 128)
 constexpr int I8_A_BYTES = I8_M * I8_KB;            // 8 KiB
 constexpr int I8_B_BYTES = I8_N * I8_KB;            // 4 KiB per digit
-constexpr int I8_B_ALL = I8_DIG * I8_B_BYTES;       // 24 KiB: the 384-row digit operand of one k-block
-static_assert(I8_DIG == 6 && I8_NB % 32 == 0 && I8_NA + I8_NB <= 512, "accumulator layout");
+constexpr int I8_B_ALL = I8_DIG * I8_B_BYTES;       // 28 (24) KiB: the 448- (384-) row digit operand of one k-block
+static_assert(I8_NB % 32 == 0 && I8_NA + I8_NB <= 512, "accumulator layout");
 // per-variant stage geometry: single-CTA UMMA keeps the whole digit operand, a cta_group::2 pair keeps half per CTA
 template <bool CG2> struct I8Geo {
     static constexpr int B_STAGE = CG2 ? I8_B_ALL / 2 : I8_B_ALL;
-    static constexpr int STAGE_BYTES = I8_A_BYTES + B_STAGE;           // 32 KiB / 20 KiB
+    static constexpr int STAGE_BYTES = I8_A_BYTES + B_STAGE;           // 36 / 22 KiB (7 planes), 32 / 20 KiB (6)
 };
 constexpr int I8_MAX_STAGES = 10;
 constexpr int I8_TTAB = 512;        // 64-row tiles per split that fit the shared-memory copy of the work list (the host plan keeps splits below it)
@@ -247,23 +247,40 @@ __device__ __forceinline__ void i8_tmem_ld1(unsigned taddr, int& v) {           
 }
 // wait for the thread's TMEM loads; the destination registers are operands, so nothing that reads them moves above
 __device__ __forceinline__ void i8_tmem_wait(int (&d)[I8_DIG][4]) {
+#if GMS_I8_DIG == 7
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(d[0][0]), "+r"(d[0][1]), "+r"(d[0][2]), "+r"(d[0][3]), "+r"(d[1][0]), "+r"(d[1][1]), "+r"(d[1][2]), "+r"(d[1][3]),
+                   "+r"(d[2][0]), "+r"(d[2][1]), "+r"(d[2][2]), "+r"(d[2][3]), "+r"(d[3][0]), "+r"(d[3][1]), "+r"(d[3][2]), "+r"(d[3][3]),
+                   "+r"(d[4][0]), "+r"(d[4][1]), "+r"(d[4][2]), "+r"(d[4][3]), "+r"(d[5][0]), "+r"(d[5][1]), "+r"(d[5][2]), "+r"(d[5][3]),
+                   "+r"(d[6][0]), "+r"(d[6][1]), "+r"(d[6][2]), "+r"(d[6][3])
+                 :: "memory");
+#else
     asm volatile("tcgen05.wait::ld.sync.aligned;"
                  : "+r"(d[0][0]), "+r"(d[0][1]), "+r"(d[0][2]), "+r"(d[0][3]), "+r"(d[1][0]), "+r"(d[1][1]), "+r"(d[1][2]), "+r"(d[1][3]),
                    "+r"(d[2][0]), "+r"(d[2][1]), "+r"(d[2][2]), "+r"(d[2][3]), "+r"(d[3][0]), "+r"(d[3][1]), "+r"(d[3][2]), "+r"(d[3][3]),
                    "+r"(d[4][0]), "+r"(d[4][1]), "+r"(d[4][2]), "+r"(d[4][3]), "+r"(d[5][0]), "+r"(d[5][1]), "+r"(d[5][2]), "+r"(d[5][3])
                  :: "memory");
+#endif
 }
 
-// TT = T (SOUTER = false, T <= 6: loop "64-row tile outer, trait s inner", the cross's whole T x T table in registers)
-// or TT >= T (SOUTER = true, any T <= 32: loop "trait s outer, tile inner", one column Z[:, s] in registers).
+// Loop order: trait s outer, 64-row tile inner; one unit = the accumulator of one (trait, tile). TT >= T is the compile-time
+// size of the column Z[:, s] an epilogue thread keeps in registers.
 // CG2 = true: launched as clusters of 2 CTAs = two adjacent cross tiles forming ONE M = 256 tile (tcgen05 cta_group::2).
 // Each CTA stages its own xi tile and only HALF of every digit tile; the leader CTA's MMA thread issues the pair's MMAs once
 // both halves have landed (the peer relays its `full` phases to the leader), and its commits release the slot / publish the
 // accumulators in BOTH CTAs. This halves the shared-memory traffic per MAC, which is what bounds the single-CTA kernel.
-// SKIP = true: the epilogue visits only the rows where some cross of the warp has a non-zero mask entry (see the header).
-template <int TT, bool SOUTER, bool CG2, bool SKIP>
+// SKIP = true: the epilogue arithmetic visits only the rows where some cross of the warp has a non-zero mask entry.
+//
+// The epilogue of a unit has two phases. DRAIN: tcgen05.ld of the warp's 32 rows x I8_DIG digit sums, recombined on the fly
+// into 32 exact 64-bit integers W[j] that stay in registers, then the accumulator is released - the next unit's MMAs wait
+// only for ~50 TMEM loads and ~300 integer instructions per warp (round 1 released after 7/8 of ALL the epilogue work of
+// the unit: its MMA warp spent 36 % of its time waiting for the accumulator, ncu source page of profiles/r1_i8_kernel_ncu_final).
+// MATH: conversion to FP64 and the T FMAs per row, overlapped with the next unit's MMAs. W[] needs compile-time register
+// indices, so the rows are a fully unrolled sequence of warp-uniform predicated blocks - affordable only with ONE copy of it,
+// hence the trait-outer loop for every T (the tile-outer loop of round 1 unrolled the epilogue T times to keep Z[T][T]).
+template <int TT, bool CG2, bool SKIP>
 __global__ void __launch_bounds__(I8_THREADS, 1) i8_contract_kernel(const I8Params p) {
-    const int T = SOUTER ? p.T : TT;
+    const int T = p.T;
     extern __shared__ __align__(1024) unsigned char smem[];
     unsigned char* stage0 = smem;
     constexpr int I8_STAGE_BYTES = I8Geo<CG2>::STAGE_BYTES, B_STAGE = I8Geo<CG2>::B_STAGE;
@@ -271,10 +288,10 @@ __global__ void __launch_bounds__(I8_THREADS, 1) i8_contract_kernel(const I8Para
     unsigned long long* bars = reinterpret_cast<unsigned long long*>(smem + I8_STAGES * I8_STAGE_BYTES);
     unsigned* tmem_slot = reinterpret_cast<unsigned*>(bars + 2 * I8_MAX_STAGES + 2);
     int4* ttab = reinterpret_cast<int4*>(bars + 2 * I8_MAX_STAGES + 4);        // this CTA's range of the 64-row tile list (I8_TTAB entries)
-    // row data of a tile, double-buffered: d_t[j] for T traits x 64 rows (FP64), then eb_s[j] = exponent field of scale_s[j] + 15
-    // (int) for T traits (tile-outer loop) or for the current trait (trait-outer loop)
+    // row data of a unit, double-buffered: d_t[j] for T traits x 64 rows (FP64), then eb[j] = exponent field of scale_s[j] + 63 -
+    // I8_FRAC - 1 (int) for the unit's trait s
     unsigned char* rowbuf = reinterpret_cast<unsigned char*>(ttab + I8_TTAB);
-    const int rowbuf_bytes = T * 64 * 8 + (SOUTER ? 1 : T) * 64 * 4;
+    const int rowbuf_bytes = T * 64 * 8 + 64 * 4;
     const unsigned full0 = i8_smem_u32(bars), empty0 = i8_smem_u32(bars + I8_MAX_STAGES);
     const unsigned accfull = i8_smem_u32(bars + 2 * I8_MAX_STAGES), accempty = i8_smem_u32(bars + 2 * I8_MAX_STAGES + 1);
     const unsigned crank = CG2 ? i8_cta_rank() : 0u;       // 0 = leader of the pair
@@ -292,15 +309,8 @@ __global__ void __launch_bounds__(I8_THREADS, 1) i8_contract_kernel(const I8Para
     }
     // every role walks the units (64-row tile, trait) in the same order: f(tile entry, s)
     auto for_units = [&](auto f) {
-        if (!SOUTER) {
-            for (int jt = jt_begin; jt < jt_end; ++jt) {
-                const int4 e = ttab[jt - jt_begin];
-                for (int s = 0; s < T; ++s) f(e, s);
-            }
-        } else {
-            for (int s = 0; s < T; ++s)
-                for (int jt = jt_begin; jt < jt_end; ++jt) f(ttab[jt - jt_begin], s);
-        }
+        for (int s = 0; s < T; ++s)
+            for (int jt = jt_begin; jt < jt_end; ++jt) f(ttab[jt - jt_begin], s);
     };
 
     if (threadIdx.x == 0) {
@@ -338,9 +348,15 @@ __global__ void __launch_bounds__(I8_THREADS, 1) i8_contract_kernel(const I8Para
                 i8_mbar_wait(empty0 + 8 * slot, ph ^ 1u);
                 if (v2_elect()) {
                     const unsigned dst = i8_smem_u32(stage0) + slot * I8_STAGE_BYTES, bar = full0 + 8 * slot;
-                    i8_mbar_expect_tx(bar, I8_STAGE_BYTES);
-                    i8_bulk_g2s(dst, abase + (long long)kb * I8_A_BYTES, I8_A_BYTES, bar);
-                    i8_bulk_g2s(dst + I8_A_BYTES, gb + (long long)kb * T * I8_B_ALL, B_STAGE, bar);
+                    if (I8_DBG(8 | 16)) {            // profiling: without the xi copy (8) / the digit copy (16)
+                        i8_mbar_expect_tx(bar, (I8_DBG(8) ? 0 : I8_A_BYTES) + (I8_DBG(16) ? 0 : B_STAGE));
+                        if (!I8_DBG(8)) i8_bulk_g2s(dst, abase + (long long)kb * I8_A_BYTES, I8_A_BYTES, bar);
+                        if (!I8_DBG(16)) i8_bulk_g2s(dst + I8_A_BYTES, gb + (long long)kb * T * I8_B_ALL, B_STAGE, bar);
+                    } else {
+                        i8_mbar_expect_tx(bar, I8_STAGE_BYTES);
+                        i8_bulk_g2s(dst, abase + (long long)kb * I8_A_BYTES, I8_A_BYTES, bar);
+                        i8_bulk_g2s(dst + I8_A_BYTES, gb + (long long)kb * T * I8_B_ALL, B_STAGE, bar);
+                    }
                 }
                 __syncwarp();
                 if (++slot == I8_STAGES) { slot = 0; ph ^= 1u; }
@@ -364,11 +380,11 @@ __global__ void __launch_bounds__(I8_THREADS, 1) i8_contract_kernel(const I8Para
             // instruction descriptor: D = S32, A = B = signed 8 bit, K-major both; M = 128 (256 over a CTA pair)
             const unsigned idesc0 = (2u << 4) | (1u << 7) | (1u << 10) | ((unsigned)((CG2 ? 2 * I8_M : I8_M) >> 4) << 24);
             const unsigned idescA = idesc0 | ((unsigned)(I8_NA >> 3) << 17);           // N = 256: digits 0-3
-            const unsigned idescB = idesc0 | ((unsigned)(I8_NB >> 3) << 17);           // N = 128: digits 4-5
-            // rows of the digit operand held in THIS CTA's shared memory: all 384, or 128 + 64 (the pair's halves)
+            const unsigned idescB = idesc0 | ((unsigned)(I8_NB >> 3) << 17);           // N = 192 / 128: the remaining digits
+            // rows of the digit operand held in THIS CTA's shared memory: all of them, or half of each MMA's (the pair's halves)
             constexpr unsigned B_ROWS = CG2 ? (I8_DIG * I8_N) / 2 : I8_DIG * I8_N;
             constexpr unsigned B_LBO = (B_ROWS / 8) * 128;                           // chunk stride
-            constexpr unsigned B_SECOND = (CG2 ? I8_NA / 2 : I8_NA) / 8 * 128;       // byte offset of the N = 128 part
+            constexpr unsigned B_SECOND = (CG2 ? I8_NA / 2 : I8_NA) / 8 * 128;       // byte offset of the second MMA's part
             // descriptors of slot 0, k32-step 0; everything else is an add on the 14-bit address field
             const unsigned long long da0 = i8_desc(i8_smem_u32(stage0), I8_M * 16, 128);
             const unsigned long long db0 = i8_desc(i8_smem_u32(stage0) + I8_A_BYTES, B_LBO, 128);
@@ -389,10 +405,10 @@ __global__ void __launch_bounds__(I8_THREADS, 1) i8_contract_kernel(const I8Para
                             const unsigned long long dbA = dbs + ((kk * 2 * B_LBO) >> 4), dbB = dbs + ((B_SECOND + kk * 2 * B_LBO) >> 4);
                             if (CG2) {
                                 i8_mma_cg2(tmem_base, da, dbA, idescA, (kb | kk) != 0);
-                                i8_mma_cg2(tmem_base + I8_NA, da, dbB, idescB, (kb | kk) != 0);
+                                if (!I8_DBG(4)) i8_mma_cg2(tmem_base + I8_NA, da, dbB, idescB, (kb | kk) != 0);
                             } else {
                                 i8_mma(tmem_base, da, dbA, idescA, (kb | kk) != 0);
-                                i8_mma(tmem_base + I8_NA, da, dbB, idescB, (kb | kk) != 0);
+                                if (!I8_DBG(4)) i8_mma(tmem_base + I8_NA, da, dbB, idescB, (kb | kk) != 0);
                             }
                         }
                         if (CG2) i8_commit_cg2(empty0 + 8 * slot, 3);     // frees the slot in BOTH CTAs when these MMAs retire
@@ -434,123 +450,79 @@ __global__ void __launch_bounds__(I8_THREADS, 1) i8_contract_kernel(const I8Para
                 }
             }
         };
-        auto release = [&]() {                       // TMEM fully read: the next (tile, trait)'s MMAs may start
+        auto release = [&]() {                       // TMEM fully read: the next unit's MMAs may start
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
             if (lane == 0) { if (CG2) i8_mbar_arrive_remote(accempty, 0); else i8_mbar_arrive(accempty); }
         };
-        // value of row jr (0..31 within this warp's half) from the digit sums in d[.][q]: xi_x[jr] * W * 2^(E - 47)
-        auto row_value = [&](const int (&d)[I8_DIG][4], int q, int jr, const int* ebrow, unsigned nz, unsigned ng) -> double {
-            unsigned bh, bl;
-            i8_cvt_bits(i8_combine(d[0][q], d[1][q], d[2][q], d[3][q], d[4][q], d[5][q]), ebrow[jr], (nz >> jr) & 1u, (ng >> jr) & 1u, bh, bl);
-            return __hiloint2double((int)bh, (int)bl);
+        auto load4 = [&](int ch, int (&d)[I8_DIG][4]) {        // rows 4 ch .. 4 ch + 3 of this warp's half, all digit planes
+#pragma unroll
+            for (int i = 0; i < I8_DIG; ++i) i8_tmem_ld4(tlane + i * I8_N + ch * 4, d[i]);
         };
-        // One unit = the finished accumulator of one (tile, trait): acc(jr, v) for the rows jr of this warp's half; the
-        // accumulator is released as soon as the last digits are in registers. TMEM loads are software-pipelined over groups
-        // of 4 rows (two register sets A / B): the loads of the next group are in flight while this one is combined.
-        auto process_unit = [&](unsigned rows, unsigned nz, unsigned ng, const int* ebrow, auto&& acc) {
-            int dA[I8_DIG][4], dB[I8_DIG][4];
-            if constexpr (!SKIP) {
-                auto load4 = [&](int ch, int (&d)[I8_DIG][4]) {
+        unsigned acc_it = 0;
+        for (int s = 0; s < T; ++s) {
+            double zs[TT];
 #pragma unroll
-                    for (int i = 0; i < I8_DIG; ++i) i8_tmem_ld4(tlane + i * I8_N + ch * 4, d[i]);
-                };
-                auto math4 = [&](int ch, const int (&d)[I8_DIG][4]) {
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) acc(ch * 4 + q, row_value(d, q, ch * 4 + q, ebrow, nz, ng));
-                };
-                constexpr int NCH = I8_RPT / 4;              // 8 chunks of 4 rows (an even number)
-                load4(0, dA);
-                i8_tmem_wait(dA);
-#pragma unroll 1
-                for (int cp = 0; cp < NCH / 2; ++cp) {
-                    load4(2 * cp + 1, dB);
-                    math4(2 * cp, dA);
-                    i8_tmem_wait(dB);
-                    if (cp + 1 < NCH / 2) load4(2 * cp + 2, dA); else release();
-                    math4(2 * cp + 1, dB);
-                    if (cp + 1 < NCH / 2) i8_tmem_wait(dA);
-                }
-            } else {
-                // rows = OR of nz over the warp (warp-uniform): walk its set bits four at a time
-                auto take4 = [&](unsigned& mm, int (&j)[4]) -> int {        // mm != 0 on entry; unused slots repeat j[0]
-                    const int n = min(__popc(mm), 4);
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) { j[q] = mm ? __ffs(mm) - 1 : j[0]; mm &= mm - 1u; }
-                    return n;
-                };
-                auto loadg = [&](const int (&j)[4], int (&d)[I8_DIG][4]) {
-#pragma unroll
-                    for (int q = 0; q < 4; ++q)
-#pragma unroll
-                        for (int i = 0; i < I8_DIG; ++i) i8_tmem_ld1(tlane + i * I8_N + j[q], d[i][q]);
-                };
-                auto mathg = [&](const int (&j)[4], int n, const int (&d)[I8_DIG][4]) {
-#pragma unroll
-                    for (int q = 0; q < 4; ++q)
-                        if (q < n) acc(j[q], row_value(d, q, j[q], ebrow, nz, ng));
-                };
-                unsigned mm = rows;
-                if (mm == 0u) {
-                    release();
-                } else {
-                    int jA[4], jB[4], nA, nB = 0;
-                    nA = take4(mm, jA);
-                    loadg(jA, dA);
-                    i8_tmem_wait(dA);
-#pragma unroll 1
-                    for (;;) {
-                        const bool moreB = mm != 0u;
-                        if (moreB) { nB = take4(mm, jB); loadg(jB, dB); } else release();
-                        mathg(jA, nA, dA);
-                        if (!moreB) break;
-                        i8_tmem_wait(dB);
-                        const bool moreA = mm != 0u;
-                        if (moreA) { nA = take4(mm, jA); loadg(jA, dA); } else release();
-                        mathg(jB, nB, dB);
-                        if (!moreA) break;
-                        i8_tmem_wait(dA);
-                    }
-                }
-            }
-        };
-        // eb = exponent field of the (power-of-two, >= 2^-900) row scale + 15: see i8_cvt_bits
-        auto scale_eb = [&](int s, long long prow_j) -> int {
-            return (__double2hiint(__ldg(p.scale + (long long)s * p.mp_total + prow_j)) >> 20) + (63 - I8_FRAC - 1);
-        };
-
-        if constexpr (!SOUTER) {
-            double Z[TT][TT];
-#pragma unroll
-            for (int t = 0; t < TT; ++t)
-#pragma unroll
-                for (int s = 0; s < TT; ++s) Z[t][s] = 0.0;
-            unsigned acc_it = 0;
-            for (int jt = jt_begin; jt < jt_end; ++jt) {
+            for (int t = 0; t < TT; ++t) zs[t] = 0.0;
+            for (int jt = jt_begin; jt < jt_end; ++jt, ++acc_it) {
                 const long long prow = ttab[jt - jt_begin].y;                    // padded index of the tile's first row
-                unsigned char* rb = rowbuf + ((jt - jt_begin) & 1) * rowbuf_bytes;
+                unsigned char* rb = rowbuf + (acc_it & 1) * rowbuf_bytes;
                 double* erow_all = reinterpret_cast<double*>(rb);                 // d_t[j]: [t][64]
-                int* eb_all = reinterpret_cast<int*>(rb + T * 64 * 8);            // eb_s[j]: [s][64]
-                for (int i = etid; i < 2 * T * 64; i += 32 * I8_EPI_WARPS) {
-                    const int which = i / (T * 64), rem = i - which * (T * 64), t = rem >> 6, j = rem & 63;
-                    if (!which) erow_all[rem] = __ldg(p.emat + (long long)t * p.mp_total + prow + j);
-                    else eb_all[rem] = scale_eb(t, prow + j);
+                int* eb_all = reinterpret_cast<int*>(rb + T * 64 * 8);            // eb[j] of trait s: [64]
+                for (int i = etid; i < (T + 1) * 64; i += 32 * I8_EPI_WARPS) {
+                    const int t = i >> 6, j = i & 63;
+                    if (t < T) erow_all[i] = __ldg(p.emat + (long long)t * p.mp_total + prow + j);
+                    else       // the row scale is a power of two >= 2^-900: its exponent field, biased for i8_cvt_bits
+                        eb_all[j] = (__double2hiint(__ldg(p.scale + (long long)s * p.mp_total + prow + j)) >> 20) + (63 - I8_FRAC - 1);
                 }
                 unsigned nz, ng;
                 load_mask(prow, nz, ng);
                 const unsigned rows = SKIP ? __reduce_or_sync(0xffffffffu, nz) : 0xffffffffu;
                 asm volatile("bar.sync 1, %0;" ::"n"(32 * I8_EPI_WARPS) : "memory");
                 const double* erow = erow_all + half * I8_RPT;       // erow[t * 64 + jr]
-                const int* ebh = eb_all + half * I8_RPT;              // ebh[s * 64 + jr]
+                const int* ebrow = eb_all + half * I8_RPT;            // ebrow[jr]
+                i8_mbar_wait(accfull, acc_it & 1u);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                if (I8_DBG(1)) { release(); continue; }
+                // ---- drain: TMEM -> 32 exact row sums in registers; loads of chunk c + 1 in flight while chunk c is recombined
+                long long W[I8_RPT];
+                {
+                    int dA[I8_DIG][4], dB[I8_DIG][4];
+                    auto comb4 = [&](int ch, const int (&d)[I8_DIG][4]) {
 #pragma unroll
-                for (int s = 0; s < TT; ++s, ++acc_it) {               // unrolled: Z[t][s] must stay in registers
-                    i8_mbar_wait(accfull, acc_it & 1u);
-                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    if (I8_DBG(1)) { release(); continue; }
-                    process_unit(rows, nz, ng, ebh + s * 64, [&](int jr, double v) {
+                        for (int q = 0; q < 4; ++q) {
+                            int sv[I8_DIG];
 #pragma unroll
-                        for (int t = 0; t < TT; ++t) Z[t][s] = fma(erow[t * 64 + jr], v, Z[t][s]);
-                    });
+                            for (int i = 0; i < I8_DIG; ++i) sv[i] = d[i][q];
+                            W[ch * 4 + q] = i8_combine(sv);
+                        }
+                    };
+                    constexpr int NCH = I8_RPT / 4;          // 8 chunks of 4 rows
+                    load4(0, dA);
+                    i8_tmem_wait(dA);
+#pragma unroll
+                    for (int cp = 0; cp < NCH / 2; ++cp) {
+                        load4(2 * cp + 1, dB);
+                        comb4(2 * cp, dA);
+                        i8_tmem_wait(dB);
+                        if (cp + 1 < NCH / 2) load4(2 * cp + 2, dA); else release();
+                        comb4(2 * cp + 1, dB);
+                        if (cp + 1 < NCH / 2) i8_tmem_wait(dA);
+                    }
+                }
+                if (I8_DBG(32)) continue;
+                // ---- math (overlaps the next unit's MMAs): v = xi_x[j] W[j] 2^(E - I8_FRAC) built with integer instructions,
+                // then the only FP64 instructions of the kernel: zs[t] += d_t[j] v. Rows no cross of the warp needs are skipped.
+#pragma unroll
+                for (int jr = 0; jr < I8_RPT; ++jr) {
+                    if ((rows >> jr) & 1u) {
+                        unsigned bh, bl;
+                        i8_cvt_bits(W[jr], ebrow[jr], (nz >> jr) & 1u, (ng >> jr) & 1u, bh, bl);
+                        const double v = __hiloint2double((int)bh, (int)bl);
+#pragma unroll
+                        for (int t = 0; t < TT; ++t)
+                            if (t < T) zs[t] = fma(erow[t * 64 + jr], v, zs[t]);
+                    }
                 }
             }
             if (live) {
@@ -558,46 +530,7 @@ __global__ void __launch_bounds__(I8_THREADS, 1) i8_contract_kernel(const I8Para
                 double* out = p.Zpart + ((long long)(split * 2 + half) * p.n_units + unit) * (T * T);
 #pragma unroll
                 for (int t = 0; t < TT; ++t)
-#pragma unroll
-                    for (int s = 0; s < TT; ++s) out[t * T + s] = Z[t][s];
-            }
-        } else {
-            // ---- trait s outer, tile inner: Z[:, s] in registers, any T <= TT
-            unsigned acc_it = 0;
-            for (int s = 0; s < T; ++s) {
-                double zs[TT];
-#pragma unroll
-                for (int t = 0; t < TT; ++t) zs[t] = 0.0;
-                for (int jt = jt_begin; jt < jt_end; ++jt, ++acc_it) {
-                    const long long prow = ttab[jt - jt_begin].y;
-                    unsigned char* rb = rowbuf + (acc_it & 1) * rowbuf_bytes;
-                    double* erow_all = reinterpret_cast<double*>(rb);             // d_t[j]: [t][64]
-                    int* eb_all = reinterpret_cast<int*>(rb + T * 64 * 8);        // eb_s[j] of trait s: [64]
-                    for (int i = etid; i < (T + 1) * 64; i += 32 * I8_EPI_WARPS) {
-                        const int t = i >> 6, j = i & 63;
-                        if (t < T) erow_all[i] = __ldg(p.emat + (long long)t * p.mp_total + prow + j);
-                        else eb_all[j] = scale_eb(s, prow + j);
-                    }
-                    unsigned nz, ng;
-                    load_mask(prow, nz, ng);
-                    const unsigned rows = SKIP ? __reduce_or_sync(0xffffffffu, nz) : 0xffffffffu;
-                    asm volatile("bar.sync 1, %0;" ::"n"(32 * I8_EPI_WARPS) : "memory");
-                    const double* erow = erow_all + half * I8_RPT;
-                    i8_mbar_wait(accfull, acc_it & 1u);
-                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    if (I8_DBG(1)) { release(); continue; }
-                    process_unit(rows, nz, ng, eb_all + half * I8_RPT, [&](int jr, double v) {
-#pragma unroll
-                        for (int t = 0; t < TT; ++t)
-                            if (t < T) zs[t] = fma(erow[t * 64 + jr], v, zs[t]);
-                    });
-                }
-                if (live) {
-                    double* out = p.Zpart + ((long long)(split * 2 + half) * p.n_units + unit) * (T * T);
-#pragma unroll
-                    for (int t = 0; t < TT; ++t)
-                        if (t < T) out[t * T + s] = zs[t];
-                }
+                    if (t < T) out[t * T + s] = zs[t];
             }
         }
     }
@@ -615,7 +548,7 @@ int i8_npart(int T) { (void)T; return 2; }                 // partial slabs per 
 int i8_max_tiles_per_split() { return I8_TTAB; }
 long long i8_block_bytes() { return I8_B_ALL; }            // digit image of one (64 x 64 block, trait)
 static size_t i8_fixed_smem(int T) {
-    const size_t rowbuf = (size_t)T * 64 * 8 + (size_t)(T <= 6 ? T : 1) * 64 * 4;          // per buffer (see the two epilogues)
+    const size_t rowbuf = (size_t)T * 64 * 8 + 64 * 4;          // per buffer (see the epilogue)
     return (2 * I8_MAX_STAGES + 4) * 8 + (size_t)I8_TTAB * 16 + 2 * rowbuf;
 }
 // pipeline stages: as many as fit in the 227 KiB a CTA may use (the kernel is bound by the latency of its operand stream)
@@ -669,33 +602,27 @@ cudaError_t launch_i8_contract(const I8Params& p, int ntiles, int nsplit, bool p
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = pair ? 1 : 0;
-#define GMS_I8_ONE(TV, SO, PR, SK)                                                                                              \
+#define GMS_I8_ONE(TV, PR, SK)                                                                                                  \
     {                                                                                                                           \
-        e = cudaFuncSetAttribute(i8_contract_kernel<TV, SO, PR, SK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);   \
+        e = cudaFuncSetAttribute(i8_contract_kernel<TV, PR, SK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);       \
         if (e != cudaSuccess) return e;                                                                                         \
-        e = cudaLaunchKernelEx(&cfg, i8_contract_kernel<TV, SO, PR, SK>, pp);                                                   \
+        e = cudaLaunchKernelEx(&cfg, i8_contract_kernel<TV, PR, SK>, pp);                                                       \
         if (e != cudaSuccess) return e;                                                                                         \
     }
-#define GMS_I8(TV, SO)                                                                                                          \
+#define GMS_I8(TV)                                                                                                              \
     {                                                                                                                           \
-        if (pair) { if (skip) GMS_I8_ONE(TV, SO, true, true) else GMS_I8_ONE(TV, SO, true, false) }                             \
-        else { if (skip) GMS_I8_ONE(TV, SO, false, true) else GMS_I8_ONE(TV, SO, false, false) }                                \
+        if (pair) { if (skip) GMS_I8_ONE(TV, true, true) else GMS_I8_ONE(TV, true, false) }                                     \
+        else { if (skip) GMS_I8_ONE(TV, false, true) else GMS_I8_ONE(TV, false, false) }                                        \
     }
-    switch (p.T) {
-        case 1: GMS_I8(1, false) break;
-        case 2: GMS_I8(2, false) break;
-        case 3: GMS_I8(3, false) break;
-        case 4: GMS_I8(4, false) break;
-        case 5: GMS_I8(5, false) break;
-        case 6: GMS_I8(6, false) break;
-        default:
-            if (p.T <= 8) GMS_I8(8, true)
-            else if (p.T <= 12) GMS_I8(12, true)
-            else if (p.T <= 16) GMS_I8(16, true)
-            else if (p.T <= 24) GMS_I8(24, true)
-            else if (p.T <= 32) GMS_I8(32, true)
-            else return cudaErrorInvalidValue;
-    }
+    if (p.T <= 2) GMS_I8(2)
+    else if (p.T <= 4) GMS_I8(4)
+    else if (p.T <= 6) GMS_I8(6)
+    else if (p.T <= 8) GMS_I8(8)
+    else if (p.T <= 12) GMS_I8(12)
+    else if (p.T <= 16) GMS_I8(16)
+    else if (p.T <= 24) GMS_I8(24)
+    else if (p.T <= 32) GMS_I8(32)
+    else return cudaErrorInvalidValue;
 #undef GMS_I8
 #undef GMS_I8_ONE
     return cudaGetLastError();

@@ -86,11 +86,14 @@ GMS_API int gms_set_haplotypes_u8rm(gms_handle* h, int64_t P, int64_t m, const u
 /* Optional: evaluation mode.
  * GMS_MODE_DENSE: the dense FP64 tensor (DMMA) contraction against the stored R / RoR blocks; any symmetric recombFreqMat.
  * GMS_MODE_INT8_TENSOR (any symmetric matrix, any model, T <= 32): all contractions run on the int8 tcgen05 tensor cores.
- *   G = (R or RoR) . diag(effects) is rounded, row by row, to 49 bits below a power-of-two ROW scale (>= the row's largest
- *   |entry|) and split into 7 radix-128 int8 digit planes; the masks are ternary; int32 accumulation in TMEM is exact; the
- *   digits are recombined exactly and scaled in FP64. This is FIXED POINT relative to the row maximum, so its accuracy
- *   depends on the data: a SNP with a huge effect that does not segregate in a cross leaves an absolute error of
- *   2^-50 x (row scale) on terms that may be many orders of magnitude smaller. THE CONTRACT: every table (per parent, per
+ *   G = (R or RoR) . diag(effects) is rounded, row by row, to 47 bits below a power-of-two ROW scale (>= the row's largest
+ *   |entry| / 0.996) and split into 6 balanced radix-256 int8 digit planes; the masks are ternary; int32 accumulation in
+ *   TMEM is exact; the digit sums are recombined exactly in 64-bit integers and converted to FP64 once per row. This is
+ *   FIXED POINT relative to the row maximum, so its accuracy depends on the data: a SNP with a huge effect that does not
+ *   segregate in a cross leaves an absolute error of 2^-48 x (row scale) on terms that may be many orders of magnitude
+ *   smaller. The per-cross pass evaluates the crosses in sire order internally (results come back in list order), because
+ *   crosses that share a parent share most of their zero mask rows and the kernel skips those.
+ *   THE CONTRACT: every table (per parent, per
  *   cross) is followed on the device by a worst-case a-posteriori bound of that error (csrc/verify.cu); a unit passes when
  *   the bound is at most tau x sqrt(X[t,t] X[s,s]) for every trait pair (tau = 2^-31 ~ 4.7e-10 by default,
  *   gms_set_int8_tolerance), i.e. every variance is good to tau relative and every covariance to tau of its variance scale. Units that fail (and units with

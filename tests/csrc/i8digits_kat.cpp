@@ -18,17 +18,17 @@ int main() {
     // 1. split: exact reconstruction, digits in range, rounding error <= 2^-48
     for (int it = 0; it < 2000000; ++it) {
         double x = U(rng);
-        if (it < 8) { const double edge[8] = {0.0, I8_FILL, -I8_FILL, 0x1p-47, -0x1p-47, 0x1p-48, 0.5, -0.5}; x = edge[it]; }
+        if (it < 8) { const double edge[8] = {0.0, I8_FILL, -I8_FILL, ldexp(1.0, -I8_FRAC), -ldexp(1.0, -I8_FRAC), ldexp(1.0, -I8_FRAC - 1), 0.5, -0.5}; x = edge[it]; }
         const long long w = i8_fixed(x);
         signed char d[I8_DIG];
         i8_split(w, d);
         long long r = 0;
         for (int i = 0; i < I8_DIG; ++i) r = r * 256 + d[i];
         CHECK(r == w, "split: x=%a w=%lld rebuilt %lld", x, w, r);
-        CHECK(fabs((double)w * 0x1p-47 - x) <= 0x1p-48, "rounding: x=%a", x);
+        CHECK(fabs(ldexp((double)w, -I8_FRAC) - x) <= ldexp(1.0, -I8_FRAC - 1), "rounding: x=%a", x);
         ++cases;
     }
-    {   // saturation instead of wrap-around
+    if (I8_DIG == 6) {   // saturation instead of wrap-around
         signed char d[I8_DIG];
         i8_split(i8_fixed(1.0), d);
         for (int i = 0; i < I8_DIG; ++i) CHECK(d[i] == 127, "clamp+ digit %d = %d", i, d[i]);
@@ -42,10 +42,10 @@ int main() {
         CHECK(v <= I8_FILL * ldexp(1.0, e) && v > I8_FILL * ldexp(1.0, e - 1) * (1 - 1e-15), "scale: v=%a e=%d", v, e);
         ++cases;
     }
-    // 3. digit sums -> W: exact for n < 2^15 terms, worst-case signs included
+    // 3. digit sums -> W: exact for n < 2^14 terms, worst-case signs included
     for (int it = 0; it < 3000; ++it) {
-        const int n = it < 4 ? 32767 : 1 + (int)(rng() % 20000);
-        int S[I8_DIG] = {0, 0, 0, 0, 0, 0};
+        const int n = it < 4 ? 16383 : 1 + (int)(rng() % 16383);
+        int S[I8_DIG] = {};
         __int128 exact = 0;
         for (int k = 0; k < n; ++k) {
             long long w;
@@ -60,7 +60,7 @@ int main() {
             for (int i = 0; i < I8_DIG; ++i) S[i] += d[i] * xi;
             exact += (__int128)w * xi;
         }
-        const long long W = i8_combine(S[0], S[1], S[2], S[3], S[4], S[5]);
+        const long long W = i8_combine(S);
         CHECK((__int128)W == exact, "combine: n=%d W=%lld", n, W);
         // 4. conversion of this W at a few scales, all four (keep, flip) combinations
         for (int q = 0; q < 8; ++q) {
@@ -69,7 +69,7 @@ int main() {
             for (unsigned keep = 0; keep < 2; ++keep)
                 for (unsigned flip = 0; flip < 2; ++flip) {
                     unsigned bh, bl;
-                    i8_cvt_bits(W, Ef + 15, keep, flip, bh, bl);
+                    i8_cvt_bits(W, Ef + 63 - I8_FRAC - 1, keep, flip, bh, bl);
                     const uint64_t bits = ((uint64_t)bh << 32) | bl;
                     double got;
                     memcpy(&got, &bits, 8);
@@ -90,7 +90,7 @@ int main() {
                                  (1LL << 62) - 1, (1LL << 62) + 12345, -(1LL << 62), 0};
     for (long long W : special) {
         unsigned bh, bl;
-        i8_cvt_bits(W, 1023 + 15, 1, 0, bh, bl);
+        i8_cvt_bits(W, 1023 + 63 - I8_FRAC - 1, 1, 0, bh, bl);
         const uint64_t bits = ((uint64_t)bh << 32) | bl;
         double got;
         memcpy(&got, &bits, 8);

@@ -7,8 +7,13 @@ import subprocess
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def test_i8digits_known_answers(tmp_path):
+import pytest
+
+
+@pytest.mark.parametrize("ndig", [6, 7])
+def test_i8digits_known_answers(tmp_path, ndig):
     exe = str(tmp_path / "i8digits_kat")
-    subprocess.run(["g++", "-O2", "-std=c++17", "-o", exe, os.path.join(ROOT, "tests", "csrc", "i8digits_kat.cpp")], check=True)
+    subprocess.run(["g++", "-O2", "-std=c++17", f"-DGMS_I8_DIG={ndig}", "-o", exe,
+                    os.path.join(ROOT, "tests", "csrc", "i8digits_kat.cpp")], check=True)
     r = subprocess.run([exe], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and r.stdout.startswith("ok "), r.stdout + r.stderr
