@@ -61,7 +61,7 @@ def build_library(force=False, verbose=False):
 if __name__ == "__main__":
     if "--variants" in sys.argv:
         print(build_variant("profile7", ["-DGMS_PROFILE"]))
-        print(build_variant("profile6", ["-DGMS_PROFILE", "-DGMS_I8_DIG=6"]))
         print(build_variant("dig6", ["-DGMS_I8_DIG=6"]))
+        print(build_variant("np2", ["-DGMS_I8_NP5=2"]))
     else:
         print(build_library(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -264,12 +264,11 @@ __device__ __forceinline__ void i8_tmem_wait(int (&d)[I8_DIG][4]) {
 }
 
 // Loop order: trait s outer, 64-row tile inner; one unit = the accumulator of one (trait, tile). TT >= T is the compile-time
-// size of the column Z[:, s] an epilogue thread keeps in registers.
+// size of the column Z[:, s] an epilogue thread keeps in registers (EXACT: TT == T, no run-time trait predicates).
 // CG2 = true: launched as clusters of 2 CTAs = two adjacent cross tiles forming ONE M = 256 tile (tcgen05 cta_group::2).
 // Each CTA stages its own xi tile and only HALF of every digit tile; the leader CTA's MMA thread issues the pair's MMAs once
 // both halves have landed (the peer relays its `full` phases to the leader), and its commits release the slot / publish the
 // accumulators in BOTH CTAs. This halves the shared-memory traffic per MAC, which is what bounds the single-CTA kernel.
-// SKIP = true: the epilogue arithmetic visits only the rows where some cross of the warp has a non-zero mask entry.
 //
 // The epilogue of a unit has two phases. DRAIN: tcgen05.ld of the warp's 32 rows x I8_DIG digit sums, recombined on the fly
 // into 32 exact 64-bit integers W[j] that stay in registers, then the accumulator is released - the next unit's MMAs wait
@@ -278,9 +277,9 @@ __device__ __forceinline__ void i8_tmem_wait(int (&d)[I8_DIG][4]) {
 // MATH: conversion to FP64 and the T FMAs per row, overlapped with the next unit's MMAs. W[] needs compile-time register
 // indices, so the rows are a fully unrolled sequence of warp-uniform predicated blocks - affordable only with ONE copy of it,
 // hence the trait-outer loop for every T (the tile-outer loop of round 1 unrolled the epilogue T times to keep Z[T][T]).
-template <int TT, bool CG2, bool SKIP>
+template <int TT, bool EXACT, bool CG2>
 __global__ void __launch_bounds__(I8_THREADS, 1) i8_contract_kernel(const I8Params p) {
-    const int T = p.T;
+    const int T = EXACT ? TT : p.T;          // EXACT: T == TT at compile time (every T <= 8 has its own instantiation)
     extern __shared__ __align__(1024) unsigned char smem[];
     unsigned char* stage0 = smem;
     constexpr int I8_STAGE_BYTES = I8Geo<CG2>::STAGE_BYTES, B_STAGE = I8Geo<CG2>::B_STAGE;
@@ -459,78 +458,164 @@ __global__ void __launch_bounds__(I8_THREADS, 1) i8_contract_kernel(const I8Para
 #pragma unroll
             for (int i = 0; i < I8_DIG; ++i) i8_tmem_ld4(tlane + i * I8_N + ch * 4, d[i]);
         };
-        unsigned acc_it = 0;
-        for (int s = 0; s < T; ++s) {
-            double zs[TT];
+        // FP64 FMAs have a long latency and a column Z[:, s] has only T accumulation chains: NP partial sums per trait (rows
+        // jr = k mod NP) keep >= 10 independent FMAs in flight per warp (measured: one chain per trait made the burst 3 x longer)
+#ifndef GMS_I8_NP5
+#define GMS_I8_NP5 2
+#endif
+        constexpr int NP = TT <= 5 ? GMS_I8_NP5 : (TT <= 8 ? 2 : 1);
+        double zs[TT][NP];
+        // row data of unit u + 1 is fetched while unit u is processed: NPF values per thread of the (T + 1) x 64 block
+        // [d_t[j] for T traits | scale_s[j]] plus the thread's four bit-plane words
+        constexpr int NPF = (TT + 1 + 3) / 4;
+        const int ntl = jt_end - jt_begin, nunits = T * ntl;
+        double pf[NPF];
+        unsigned pm[4] = {0u, 0u, 0u, 0u};
+        auto pf_issue = [&](int s_, int jt_) {
+            const long long prow = ttab[jt_].y;
 #pragma unroll
-            for (int t = 0; t < TT; ++t) zs[t] = 0.0;
-            for (int jt = jt_begin; jt < jt_end; ++jt, ++acc_it) {
-                const long long prow = ttab[jt - jt_begin].y;                    // padded index of the tile's first row
+            for (int k = 0; k < NPF; ++k) {
+                const int i = etid + k * (32 * I8_EPI_WARPS);
+                if (i < (T + 1) * 64) {
+                    const int t = i >> 6, j = i & 63;
+                    pf[k] = __ldg((t < T ? p.emat + (long long)t * p.mp_total : p.scale + (long long)s_ * p.mp_total) + prow + j);
+                }
+            }
+            if (live) {
+                const long long wi = (prow >> 5) + half;
+                pm[0] = __ldg(p.planeA + (long long)pa * p.wpp + wi);
+                pm[1] = __ldg(p.planeB + (long long)pa * p.wpp + wi);
+                if (p.mode == MASK_XI) {
+                    pm[2] = __ldg(p.planeA + (long long)pb * p.wpp + wi);
+                    pm[3] = __ldg(p.planeB + (long long)pb * p.wpp + wi);
+                }
+            }
+        };
+        if (nunits > 0) pf_issue(0, 0);
+        int s = 0, jl = 0;                                       // unit u = (trait s, tile jt_begin + jl)
+        for (int u = 0; u < nunits; ++u) {
+            const unsigned acc_it = (unsigned)u;
+            if (jl == 0) {
+#pragma unroll
+                for (int t = 0; t < TT; ++t)
+#pragma unroll
+                    for (int k = 0; k < NP; ++k) zs[t][k] = 0.0;
+            }
+            {
                 unsigned char* rb = rowbuf + (acc_it & 1) * rowbuf_bytes;
                 double* erow_all = reinterpret_cast<double*>(rb);                 // d_t[j]: [t][64]
                 int* eb_all = reinterpret_cast<int*>(rb + T * 64 * 8);            // eb[j] of trait s: [64]
-                for (int i = etid; i < (T + 1) * 64; i += 32 * I8_EPI_WARPS) {
-                    const int t = i >> 6, j = i & 63;
-                    if (t < T) erow_all[i] = __ldg(p.emat + (long long)t * p.mp_total + prow + j);
-                    else       // the row scale is a power of two >= 2^-900: its exponent field, biased for i8_cvt_bits
-                        eb_all[j] = (__double2hiint(__ldg(p.scale + (long long)s * p.mp_total + prow + j)) >> 20) + (63 - I8_FRAC - 1);
+                // commit the prefetched values of this unit ...
+#pragma unroll
+                for (int k = 0; k < NPF; ++k) {
+                    const int i = etid + k * (32 * I8_EPI_WARPS);
+                    if (i < T * 64) erow_all[i] = pf[k];
+                    else if (i < (T + 1) * 64)   // the row scale is a power of two >= 2^-900: its exponent field, biased for i8_cvt_bits
+                        eb_all[i & 63] = (__double2hiint(pf[k]) >> 20) + (63 - I8_FRAC - 1);
                 }
-                unsigned nz, ng;
-                load_mask(prow, nz, ng);
-                const unsigned rows = SKIP ? __reduce_or_sync(0xffffffffu, nz) : 0xffffffffu;
+                // this thread's mask entries of the tile's rows (one word of the bit-planes): nz = non-zero, ng = negative
+                unsigned nz = 0u, ng = 0u;
+                if (live) {
+                    if (p.mode == MASK_XI) {
+                        nz = (pm[0] ^ pm[1]) & (pm[2] ^ pm[3]);
+                        ng = ((~pm[0] & pm[1]) ^ (~pm[2] & pm[3])) & nz;
+                    } else {
+                        nz = pm[0] ^ pm[1];
+                        ng = (p.mode == MASK_DELTA) ? (~pm[0] & pm[1]) : 0u;
+                    }
+                }
+                // ... and start the loads of the next one
+                int s_n = s, jl_n = jl + 1;
+                if (jl_n == ntl) { jl_n = 0; ++s_n; }
+                if (u + 1 < nunits) pf_issue(s_n, jl_n);
+                const unsigned rows = __reduce_or_sync(0xffffffffu, nz);       // warp-uniform: rows some unit of the warp needs
                 asm volatile("bar.sync 1, %0;" ::"n"(32 * I8_EPI_WARPS) : "memory");
                 const double* erow = erow_all + half * I8_RPT;       // erow[t * 64 + jr]
                 const int* ebrow = eb_all + half * I8_RPT;            // ebrow[jr]
                 i8_mbar_wait(accfull, acc_it & 1u);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                if (I8_DBG(1)) { release(); continue; }
-                // ---- drain: TMEM -> 32 exact row sums in registers; loads of chunk c + 1 in flight while chunk c is recombined
-                long long W[I8_RPT];
-                {
-                    int dA[I8_DIG][4], dB[I8_DIG][4];
-                    auto comb4 = [&](int ch, const int (&d)[I8_DIG][4]) {
+                if (I8_DBG(1)) {
+                    release();
+                } else {
+                    // ---- drain: TMEM -> 32 exact row sums in registers; loads of chunk c + 1 in flight while chunk c is recombined.
+                    // TMEM reads run at ~64 B per cycle and SM sub-partition: ~900 cycles for the 448 columns of a unit, the one
+                    // part of the epilogue no MMA can overlap with while a unit's accumulator fills TMEM
+                    long long W[I8_RPT];
+                    {
+                        int dA[I8_DIG][4], dB[I8_DIG][4];
+                        auto comb4 = [&](int ch, const int (&d)[I8_DIG][4]) {
 #pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            int sv[I8_DIG];
+                            for (int q = 0; q < 4; ++q) {
+                                int sv[I8_DIG];
 #pragma unroll
-                            for (int i = 0; i < I8_DIG; ++i) sv[i] = d[i][q];
-                            W[ch * 4 + q] = i8_combine(sv);
+                                for (int i = 0; i < I8_DIG; ++i) sv[i] = d[i][q];
+                                W[ch * 4 + q] = i8_combine(sv);
+                            }
+                        };
+                        constexpr int NCH = I8_RPT / 4;          // 8 chunks of 4 rows
+                        load4(0, dA);
+                        i8_tmem_wait(dA);
+#pragma unroll
+                        for (int cp = 0; cp < NCH / 2; ++cp) {
+                            load4(2 * cp + 1, dB);
+                            comb4(2 * cp, dA);
+                            i8_tmem_wait(dB);
+                            if (cp + 1 < NCH / 2) load4(2 * cp + 2, dA);
+                            comb4(2 * cp + 1, dB);
+                            if (cp + 1 < NCH / 2) i8_tmem_wait(dA);
                         }
-                    };
-                    constexpr int NCH = I8_RPT / 4;          // 8 chunks of 4 rows
-                    load4(0, dA);
-                    i8_tmem_wait(dA);
-#pragma unroll
-                    for (int cp = 0; cp < NCH / 2; ++cp) {
-                        load4(2 * cp + 1, dB);
-                        comb4(2 * cp, dA);
-                        i8_tmem_wait(dB);
-                        if (cp + 1 < NCH / 2) load4(2 * cp + 2, dA); else release();
-                        comb4(2 * cp + 1, dB);
-                        if (cp + 1 < NCH / 2) i8_tmem_wait(dA);
                     }
-                }
-                if (I8_DBG(32)) continue;
-                // ---- math (overlaps the next unit's MMAs): v = xi_x[j] W[j] 2^(E - I8_FRAC) built with integer instructions,
-                // then the only FP64 instructions of the kernel: zs[t] += d_t[j] v. Rows no cross of the warp needs are skipped.
+                    release();
+                    if (!I8_DBG(32)) {
+                        // ---- convert (integer instructions only, one basic block: overlaps the next unit's MMAs for free):
+                        // W[j] <- bit pattern of v_j = xi_x[j] W[j] 2^(E_j - I8_FRAC)
 #pragma unroll
-                for (int jr = 0; jr < I8_RPT; ++jr) {
-                    if ((rows >> jr) & 1u) {
-                        unsigned bh, bl;
-                        i8_cvt_bits(W[jr], ebrow[jr], (nz >> jr) & 1u, (ng >> jr) & 1u, bh, bl);
-                        const double v = __hiloint2double((int)bh, (int)bl);
+                        for (int jr = 0; jr < I8_RPT; ++jr) {
+                            unsigned bh, bl;
+                            i8_cvt_bits(W[jr], ebrow[jr], (nz >> jr) & 1u, (ng >> jr) & 1u, bh, bl);
+                            W[jr] = (long long)(((unsigned long long)bh << 32) | bl);
+                        }
+                        // Every conversion is complete before the first FP64 instruction, and the FP64 instructions form ONE dense
+                        // burst per unit: next to running tcgen05 MMAs FMAs scattered over integer code cost the tensor pipe ~4-5 cycles
+                        // per warp instruction (tools/tc_contention_probe.cu; measured again on this kernel).
+                        // The empty asm pins the values for the compiler, the warp-uniform branch starts a new basic block for ptxas.
 #pragma unroll
-                        for (int t = 0; t < TT; ++t)
-                            if (t < T) zs[t] = fma(erow[t * 64 + jr], v, zs[t]);
+                        for (int jr = 0; jr < I8_RPT; ++jr) asm volatile("" : "+l"(W[jr]));
+                        // ---- FP64 burst, the only FP64 instructions of the kernel: zs[t] += d_t[j] v_j for all 32 rows (rows == 0:
+                        // no unit of this warp has a mask entry in the tile, e.g. a warp of padding units)
+                        if (rows != 0u && !I8_DBG(64)) {
+#pragma unroll
+                            for (int j0 = 0; j0 < I8_RPT; j0 += 2) {
+                                const double v0 = __longlong_as_double(W[j0]), v1 = __longlong_as_double(W[j0 + 1]);
+#pragma unroll
+                                for (int t = 0; t < TT; ++t)
+                                    if (t < T) {
+                                        const double2 e = *reinterpret_cast<const double2*>(erow + t * 64 + j0);      // d_t of two rows
+                                        zs[t][j0 % NP] = fma(e.x, v0, zs[t][j0 % NP]);
+                                        zs[t][(j0 + 1) % NP] = fma(e.y, v1, zs[t][(j0 + 1) % NP]);
+                                    }
+                            }
+                        }
                     }
                 }
             }
-            if (live) {
-                // the two row halves of a cross go to two partial slabs (summed by finalize_sym)
-                double* out = p.Zpart + ((long long)(split * 2 + half) * p.n_units + unit) * (T * T);
+            if (jl + 1 == ntl) {
+                if (live) {
+                    // the two row halves of a cross go to two partial slabs (summed by finalize_sym)
+                    double* out = p.Zpart + ((long long)(split * 2 + half) * p.n_units + unit) * (T * T);
 #pragma unroll
-                for (int t = 0; t < TT; ++t)
-                    if (t < T) out[t * T + s] = zs[t];
+                    for (int t = 0; t < TT; ++t)
+                        if (t < T) {
+                            double z = zs[t][0];
+                            if (NP == 4) z = (zs[t][0] + zs[t][1]) + (zs[t][2] + zs[t][3]);
+                            else if (NP == 2) z = zs[t][0] + zs[t][1];
+                            out[t * T + s] = z;
+                        }
+                }
+                jl = 0;
+                ++s;
+            } else {
+                ++jl;
             }
         }
     }
@@ -591,6 +676,7 @@ cudaError_t launch_i8_contract(const I8Params& p, int ntiles, int nsplit, bool p
     const size_t smem = i8_smem_bytes(p.T, pair);
     I8Params pp = p;
     pp.stages = i8_stages(p.T, pair);
+    pp.skip = skip ? 1 : 0;
     cudaError_t e = cudaSuccess;
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(pair ? (ntiles + 1) / 2 * 2 : ntiles, nsplit, 1);
@@ -602,27 +688,30 @@ cudaError_t launch_i8_contract(const I8Params& p, int ntiles, int nsplit, bool p
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = pair ? 1 : 0;
-#define GMS_I8_ONE(TV, PR, SK)                                                                                                  \
+#define GMS_I8_ONE(TV, EX, PR)                                                                                                  \
     {                                                                                                                           \
-        e = cudaFuncSetAttribute(i8_contract_kernel<TV, PR, SK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);       \
+        e = cudaFuncSetAttribute(i8_contract_kernel<TV, EX, PR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);       \
         if (e != cudaSuccess) return e;                                                                                         \
-        e = cudaLaunchKernelEx(&cfg, i8_contract_kernel<TV, PR, SK>, pp);                                                       \
+        e = cudaLaunchKernelEx(&cfg, i8_contract_kernel<TV, EX, PR>, pp);                                                       \
         if (e != cudaSuccess) return e;                                                                                         \
     }
-#define GMS_I8(TV)                                                                                                              \
-    {                                                                                                                           \
-        if (pair) { if (skip) GMS_I8_ONE(TV, true, true) else GMS_I8_ONE(TV, true, false) }                                     \
-        else { if (skip) GMS_I8_ONE(TV, false, true) else GMS_I8_ONE(TV, false, false) }                                        \
+#define GMS_I8(TV, EX) { if (pair) GMS_I8_ONE(TV, EX, true) else GMS_I8_ONE(TV, EX, false) }
+    switch (p.T) {
+        case 1: GMS_I8(1, true) break;
+        case 2: GMS_I8(2, true) break;
+        case 3: GMS_I8(3, true) break;
+        case 4: GMS_I8(4, true) break;
+        case 5: GMS_I8(5, true) break;
+        case 6: GMS_I8(6, true) break;
+        case 7: GMS_I8(7, true) break;
+        case 8: GMS_I8(8, true) break;
+        default:
+            if (p.T <= 12) GMS_I8(12, false)
+            else if (p.T <= 16) GMS_I8(16, false)
+            else if (p.T <= 24) GMS_I8(24, false)
+            else if (p.T <= 32) GMS_I8(32, false)
+            else return cudaErrorInvalidValue;
     }
-    if (p.T <= 2) GMS_I8(2)
-    else if (p.T <= 4) GMS_I8(4)
-    else if (p.T <= 6) GMS_I8(6)
-    else if (p.T <= 8) GMS_I8(8)
-    else if (p.T <= 12) GMS_I8(12)
-    else if (p.T <= 16) GMS_I8(16)
-    else if (p.T <= 24) GMS_I8(24)
-    else if (p.T <= 32) GMS_I8(32)
-    else return cudaErrorInvalidValue;
 #undef GMS_I8
 #undef GMS_I8_ONE
     return cudaGetLastError();

@@ -73,6 +73,7 @@ struct I8Params {
     int mode;
     double* Zpart;               // [nsplit][n_units][T*T]
     int stages;                  // pipeline depth (set by launch_i8_contract)
+    int skip;                    // the epilogue skips rows no unit of a warp needs (set by launch_i8_contract)
     int debug;                   // -DGMS_PROFILE builds only (GMS_I8_DEBUG bit mask; results are garbage): 1 no epilogue arithmetic, 2 no MMAs
 };
 size_t i8_smem_bytes(int T, bool cg2);
