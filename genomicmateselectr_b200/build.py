@@ -62,6 +62,10 @@ if __name__ == "__main__":
     if "--variants" in sys.argv:
         print(build_variant("profile7", ["-DGMS_PROFILE"]))
         print(build_variant("dig6", ["-DGMS_I8_DIG=6"]))
-        print(build_variant("np2", ["-DGMS_I8_NP5=2"]))
+        print(build_variant("dense7", ["-DGMS_I8_DENSE_EPI"]))
+        print(build_variant("split7", ["-DGMS_I8_SPLITREL"]))
+        print(build_variant("split6", ["-DGMS_I8_SPLITREL", "-DGMS_I8_DIG=6"]))
+        if "--all" in sys.argv:
+            print(build_variant("tri", ["-DGMS_I8_TRIANGLE"]))
     else:
         print(build_library(force="--force" in sys.argv, verbose="-v" in sys.argv))

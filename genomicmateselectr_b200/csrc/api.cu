@@ -243,21 +243,24 @@ int build_worklist(gms_handle* h) {
 }
 
 // equal-work contiguous ranges of a (c, I)-ordered tile list (weight I + 1); ranges no longer than `cap` tiles if cap > 0
-void cut_ranges(const std::vector<RowTile>& tiles, int ns, int cap, Plan& pl) {
+// (weights: k-blocks per tile when they are not I + 1 - the int8 path deals the blocks evenly, common.cuh)
+void cut_ranges(const std::vector<RowTile>& tiles, int ns, int cap, Plan& pl, const std::vector<int>* weights = nullptr) {
     const int n = (int)tiles.size();
     ns = std::max(1, std::min(ns, std::max(1, n)));
     if (cap > 0) ns = std::max(ns, (n + cap - 1) / cap);
+    auto wt = [&](int i) { return weights ? (double)(*weights)[i] : (double)(tiles[i].I + 1); };
     double total = 0;
-    for (const RowTile& r : tiles) total += r.I + 1;
+    for (int i = 0; i < n; ++i) total += wt(i);
     for (;; ++ns) {
         pl.nsplit = ns;
         pl.split_begin.assign(ns + 1, 0);
         double acc = 0;
         int sp = 1;
         for (int i = 0; i < n && sp < ns; ++i) {
-            acc += tiles[i].I + 1;
-            // close range sp-1 after tile i once its share is reached, keeping >= 1 tile for the rest
-            while (sp < ns && acc >= total * sp / ns && (n - (i + 1)) >= (ns - sp)) pl.split_begin[sp++] = i + 1;
+            acc += wt(i);
+            // close range sp-1 after tile i once its share is reached, keeping >= 1 tile for the rest - and never an empty
+            // range (a heavy tile can reach several shares at once): a CTA without tiles would leave its partial slab unwritten
+            while (sp < ns && acc >= total * sp / ns && (n - (i + 1)) >= (ns - sp) && i + 1 > pl.split_begin[sp - 1]) pl.split_begin[sp++] = i + 1;
         }
         for (; sp < ns; ++sp) pl.split_begin[sp] = std::max(pl.split_begin[sp - 1], n - (ns - sp));
         pl.split_begin[ns] = n;
@@ -476,7 +479,9 @@ unsigned long long hash_ints(const int32_t* a, size_t n, unsigned long long seed
 
 int make_i8_plan(gms_handle* h, long long units, Plan& pl, DevBuf<int>& dev) {
     pl.ntiles = (int)((units + 127) / 128);
-    cut_ranges(h->jtiles, pick_nsplit(pl.ntiles, h->num_sms), i8_max_tiles_per_split(), pl);
+    std::vector<int> w(h->jtiles.size());
+    for (size_t i = 0; i < w.size(); ++i) w[i] = i8_nassign((h->chrom[h->jtiles[i].c].m + 63) / 64, h->jtiles[i].I);
+    cut_ranges(h->jtiles, pick_nsplit(pl.ntiles, h->num_sms), i8_max_tiles_per_split(), pl, &w);
     return upload_plan(h, pl, dev);
 }
 
@@ -633,7 +638,7 @@ int stage_impl(gms_handle* h, int model, int T, const double* add, const double*
                                      model >= GMS_MODEL_AD ? (size_t)h->plan_x.nsplit * (size_t)N * TT : (size_t)0);
     }
     if (h->use_i8) {
-        // 64-row tiles of the lower block triangle + digit image offsets for the chromosome shard
+        // 64-row tiles (each owns about half of the chromosome's 64-blocks, common.cuh) + digit image offsets for the chromosome shard
         h->jtiles.clear();
         h->gbase.assign(h->C, 0);
         long long gb = 0;

@@ -41,6 +41,42 @@ struct RowTile { int c; int I; };
 __host__ __device__ inline long long chunks_before_rowtile(int I) { return 2LL * I * (I + 1); }
 __host__ __device__ inline long long chunks_of_chrom(int nI) { return 2LL * nI * (nI + 1); }
 
+// ---- int8 path: which 64 x 64 blocks of a chromosome's symmetric matrix a 64-row tile J contracts (i8path.cu) ----
+// x' M y = sum over unordered block pairs {J, K}; a pair may be evaluated in EITHER orientation, because
+// B_KJ[t,s] + B_KJ[s,t] = B_JK[s,t] + B_JK[t,s] for symmetric M and the table is X = Z + Z'. Instead of the lower block
+// triangle (row tile J owns K = 0 .. J: 1 to nb k-blocks per accumulator, and the epilogue of a short unit is longer than the
+// next unit's MMAs) the pairs are dealt round-robin: with h = nb / 2, row tile J owns K = (J + i) mod nb, i = 0 .. n_J - 1,
+//   nb odd:  n_J = h + 1 for every J;   nb even: n_J = h + 1 for J < h (they take the antipodal pair {J, J + h}), else h.
+// Every unordered pair is owned exactly once (circular distance d <= h has one orientation with (K - J) mod nb = d, the
+// antipodal distance of an even nb has two and goes to the smaller J); the block count stays nb (nb + 1) / 2 and every
+// accumulator now sums (nb + 1) / 2 k-blocks, give or take one. i = 0 is the diagonal block, stored times 0.5.
+// -DGMS_I8_TRIANGLE (tools only, for A/B timing) restores the lower block triangle: row tile J owns K = 0 .. J.
+__host__ __device__ inline long long i8_blocks_of_chrom(int nb) { return (long long)nb * (nb + 1) / 2; }
+#ifndef GMS_I8_TRIANGLE
+__host__ __device__ inline int i8_nassign(int nb, int J) { const int h = nb >> 1; return (nb & 1) ? h + 1 : (J < h ? h + 1 : h); }
+__host__ __device__ inline int i8_block_k(int nb, int J, int i) { const int k = J + i; return k >= nb ? k - nb : k; }   // i-th k-block of row tile J
+__host__ __device__ inline long long i8_blocks_before(int nb, int J) {      // blocks owned by row tiles 0 .. J - 1
+    const long long h = nb >> 1;
+    if (nb & 1) return (long long)J * (h + 1);
+    return J < h ? (long long)J * (h + 1) : h * (h + 1) + (J - h) * h;
+}
+__host__ __device__ inline void i8_block_decode(int nb, long long blk, int& J, int& i) {      // inverse of i8_blocks_before(J) + i
+    const long long h = nb >> 1;
+    if ((nb & 1) || blk < h * (h + 1)) { J = (int)(blk / (h + 1)); i = (int)(blk - (long long)J * (h + 1)); }
+    else { const long long b = blk - h * (h + 1); J = (int)(h + b / h); i = (int)(b % h); }
+}
+#else
+__host__ __device__ inline int i8_nassign(int nb, int J) { (void)nb; return J + 1; }
+__host__ __device__ inline int i8_block_k(int nb, int J, int i) { (void)nb; return i == 0 ? J : i - 1; }      // diagonal first, then 0 .. J - 1
+__host__ __device__ inline long long i8_blocks_before(int nb, int J) { (void)nb; return (long long)J * (J + 1) / 2; }
+__host__ __device__ inline void i8_block_decode(int nb, long long blk, int& J, int& i) {
+    (void)nb;
+    J = 0;
+    while ((long long)(J + 1) * (J + 2) / 2 <= blk) ++J;
+    i = (int)(blk - (long long)J * (J + 1) / 2);
+}
+#endif
+
 struct ContractParams {
     const double* tiles;         // R or RoR tile image
     const ChromDesc* chrom;

@@ -73,6 +73,16 @@ GMS_HD long long i8_combine(const int (&s)[I8_DIG]) {
     return (long long)w;
 }
 
+// the same W in two parts: digits 0-3 (the accumulator columns of the first MMA of a k32-step) and the remaining ones
+GMS_HD long long i8_combine_hi(int s0, int s1, int s2, int s3) {
+    return (long long)(((unsigned long long)(long long)(s0 * 256 + s1) << (8 * (I8_DIG - 2))) +
+                       ((unsigned long long)(long long)(s2 * 256 + s3) << (8 * (I8_DIG - 4))));
+}
+GMS_HD long long i8_combine_lo(const int (&s)[I8_DIG - 4]) {
+    const long long p = (long long)(s[0] * 256 + s[1]);
+    return I8_DIG == 7 ? (long long)(((unsigned long long)p << 8) + (unsigned long long)(long long)s[I8_DIG - 5]) : p;
+}
+
 #if defined(__CUDA_ARCH__)
 #define GMS_CLZ(x) __clz((int)(x))
 #define GMS_FSL(lo, hi, s) __funnelshift_l((lo), (hi), (s))

@@ -63,6 +63,7 @@ constexpr int I8_EPI_WARPS = 8;     // two per TMEM lane quarter, each takes 32 
                                     // per thread and x4 TMEM loads, measured 13 % slower at T = 5)
 constexpr int I8_RPT = 32;          // SNP rows per epilogue thread and tile = one word of the bit-planes
 constexpr int I8_THREADS = 32 * (I8_EPI_WARPS + 2);
+constexpr int I8_CSLOTS = 16;       // compaction slots per epilogue thread (rows per round of the epilogue)
 
 // ------------------------------------------------------------------------------------------ prep: xi images
 // image (X tile, global k-block) : [chunk cc (4)][r1 (16)][r0 (8)][16 bytes], row r = 8 r1 + r0, k = 16 cc + b
@@ -128,6 +129,11 @@ __device__ __forceinline__ double lprime64(const double* __restrict__ tiles, con
     if ((col >> 6) == (row >> 6)) v *= 0.5;            // apply the 64-granular one
     return v;
 }
+// element (row, col) of the chromosome's symmetric matrix for ANY pair of 64-blocks (diagonal blocks halved): blocks above
+// the diagonal are read through their mirror image in the stored lower block triangle
+__device__ __forceinline__ double lsym64(const double* __restrict__ tiles, const ChromDesc& cd, int row, int col) {
+    return (col >> 6) > (row >> 6) ? lprime64(tiles, cd, col, row) : lprime64(tiles, cd, row, col);
+}
 
 // Row scales, two steps. (1) rowmax[s][pj] = max_k |G_s[j,k]| over row j's lower-triangle range: one CTA per 64 x 64 block
 // with the digit builder's access pattern (every L' element read once, coalesced, used for all T traits), reduced in shared
@@ -140,10 +146,10 @@ __global__ void i8_rowmax_kernel(const double* __restrict__ tiles, const ChromDe
     while (c + 1 < c_end && (int)blockIdx.x >= blkpref[c + 1]) ++c;
     const ChromDesc cd = chrom[c];
     const int blk = blockIdx.x - blkpref[c];
-    int J = (int)((sqrt(8.0 * blk + 1.0) - 1.0) * 0.5);
-    while ((J + 1) * (J + 2) / 2 <= blk) ++J;
-    while (J * (J + 1) / 2 > blk) --J;
-    const int kb = blk - J * (J + 1) / 2;
+    const int nb = (cd.m + 63) >> 6;
+    int J, bi;
+    i8_block_decode(nb, blk, J, bi);                  // the bi-th block of row tile J (common.cuh) ...
+    const int kb = i8_block_k(nb, J, bi);             // ... is k-block kb of the chromosome
     const int r = threadIdx.x & 63, cc = threadIdx.x >> 6;      // 256 threads: 64 rows x 4 chunks of 16 columns
     const int row = J * 64 + r;
     __shared__ unsigned long long sh[64][MAX_T];
@@ -154,7 +160,7 @@ __global__ void i8_rowmax_kernel(const double* __restrict__ tiles, const ChromDe
 #pragma unroll
         for (int b = 0; b < 16; ++b) {
             const int col = kb * 64 + cc * 16 + b;
-            lp[b] = col < cd.m ? fabs(lprime64(tiles, cd, row, col)) : 0.0;
+            lp[b] = col < cd.m ? fabs(lsym64(tiles, cd, row, col)) : 0.0;
         }
         const double* ecol = emat + cd.pad_off + kb * 64 + cc * 16;
         for (int s = 0; s < T; ++s) {
@@ -188,18 +194,18 @@ __global__ void i8_build_digits_kernel(const double* __restrict__ tiles, const C
     while (c + 1 < c_end && (int)blockIdx.x >= blkpref[c + 1]) ++c;     // blkpref[c] = first block of chromosome c
     const ChromDesc cd = chrom[c];
     const long long gbase = gbase_c[c];
-    const int blk = blockIdx.x - blkpref[c];          // index of (J, kb) in the lower block triangle
-    int J = (int)((sqrt(8.0 * blk + 1.0) - 1.0) * 0.5);
-    while ((J + 1) * (J + 2) / 2 <= blk) ++J;
-    while (J * (J + 1) / 2 > blk) --J;
-    const int kb = blk - J * (J + 1) / 2;
+    const int blk = blockIdx.x - blkpref[c];          // index of the block in the chromosome's list: row tile J, its bi-th block
+    const int nb = (cd.m + 63) >> 6;
+    int J, bi;
+    i8_block_decode(nb, blk, J, bi);
+    const int kb = i8_block_k(nb, J, bi);
     const int r = threadIdx.x & 63, cc = threadIdx.x >> 6;      // 256 threads: 64 rows x 4 chunks
     const int row = J * 64 + r;
     double lp[16];
 #pragma unroll
     for (int b = 0; b < 16; ++b) {
         const int col = kb * 64 + cc * 16 + b;
-        lp[b] = (row < cd.m && col < cd.m) ? lprime64(tiles, cd, row, col) : 0.0;
+        lp[b] = (row < cd.m && col < cd.m) ? lsym64(tiles, cd, row, col) : 0.0;
     }
     // the 6 digit planes of one (block, trait) form ONE K-major operand of 6 x 64 = 384 rows:
     // [chunk cc (4)][row group R1 = 8 i + r1 (48)][r0 (8)][16 bytes]  ->  LBO = 48 * 128 B, SBO = 128 B,
@@ -263,6 +269,25 @@ __device__ __forceinline__ void i8_tmem_wait(int (&d)[I8_DIG][4]) {
 #endif
 }
 
+__device__ __forceinline__ void i8_tmem_wait16(int (&d)[4][4]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(d[0][0]), "+r"(d[0][1]), "+r"(d[0][2]), "+r"(d[0][3]), "+r"(d[1][0]), "+r"(d[1][1]), "+r"(d[1][2]), "+r"(d[1][3]),
+                   "+r"(d[2][0]), "+r"(d[2][1]), "+r"(d[2][2]), "+r"(d[2][3]), "+r"(d[3][0]), "+r"(d[3][1]), "+r"(d[3][2]), "+r"(d[3][3])
+                 :: "memory");
+}
+__device__ __forceinline__ void i8_tmem_wait_rest(int (&d)[I8_DIG - 4][4]) {
+#if GMS_I8_DIG == 7
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(d[0][0]), "+r"(d[0][1]), "+r"(d[0][2]), "+r"(d[0][3]), "+r"(d[1][0]), "+r"(d[1][1]), "+r"(d[1][2]), "+r"(d[1][3]),
+                   "+r"(d[2][0]), "+r"(d[2][1]), "+r"(d[2][2]), "+r"(d[2][3])
+                 :: "memory");
+#else
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(d[0][0]), "+r"(d[0][1]), "+r"(d[0][2]), "+r"(d[0][3]), "+r"(d[1][0]), "+r"(d[1][1]), "+r"(d[1][2]), "+r"(d[1][3])
+                 :: "memory");
+#endif
+}
+
 // Loop order: trait s outer, 64-row tile inner; one unit = the accumulator of one (trait, tile). TT >= T is the compile-time
 // size of the column Z[:, s] an epilogue thread keeps in registers (EXACT: TT == T, no run-time trait predicates).
 // CG2 = true: launched as clusters of 2 CTAs = two adjacent cross tiles forming ONE M = 256 tile (tcgen05 cta_group::2).
@@ -291,20 +316,28 @@ __global__ void __launch_bounds__(I8_THREADS, 1) i8_contract_kernel(const I8Para
     // I8_FRAC - 1 (int) for the unit's trait s
     unsigned char* rowbuf = reinterpret_cast<unsigned char*>(ttab + I8_TTAB);
     const int rowbuf_bytes = T * 64 * 8 + 64 * 4;
+    // compaction slots of the epilogue threads: [I8_CSLOTS][256 threads] row sums (64 bit) and row numbers (8 bit), one private
+    // column per thread
+    long long* cw = reinterpret_cast<long long*>(rowbuf + 2 * rowbuf_bytes);
+    unsigned char* cj = reinterpret_cast<unsigned char*>(cw + I8_CSLOTS * 32 * I8_EPI_WARPS);
     const unsigned full0 = i8_smem_u32(bars), empty0 = i8_smem_u32(bars + I8_MAX_STAGES);
     const unsigned accfull = i8_smem_u32(bars + 2 * I8_MAX_STAGES), accempty = i8_smem_u32(bars + 2 * I8_MAX_STAGES + 1);
+    // GMS_I8_SPLITREL: the accumulator columns of the second MMA of a k32-step (digits 4 ..) are released separately
+    const unsigned accemptyB = i8_smem_u32(bars + 2 * I8_MAX_STAGES + 3);
     const unsigned crank = CG2 ? i8_cta_rank() : 0u;       // 0 = leader of the pair
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const long long X = blockIdx.x;
     const int split = blockIdx.y;
     const int jt_begin = p.split_begin[split], jt_end = p.split_begin[split + 1];
     // the CTA's range of the work list, once, in shared memory: (J | nkb << 16, padded index of the tile's first row, index of
-    // its first (block, trait) digit image) - no role chases jtiles -> chrom -> gbase through global memory per unit
+    // its first (block, trait) digit image, 64-blocks of the chromosome) - no role chases jtiles -> chrom -> gbase through
+    // global memory per unit. The unit's nkb k-blocks are J, J + 1, ... modulo the chromosome's block count (common.cuh)
     for (int i = threadIdx.x; i < jt_end - jt_begin; i += I8_THREADS) {
         const RowTile t = p.jtiles[jt_begin + i];
         const ChromDesc cd = p.chrom[t.c];
-        const long long gblk = p.gbase[t.c] / I8_B_ALL + (long long)(t.I * (t.I + 1) / 2) * p.T;
-        ttab[i] = make_int4(t.I | (min(t.I + 1, (cd.m + I8_KB - 1) / I8_KB) << 16), cd.pad_off + 64 * t.I, (int)(gblk & 0xFFFFFFFFll), (int)(gblk >> 32));
+        const int nb = (cd.m + I8_KB - 1) / I8_KB;            // 64-blocks of the chromosome; row tile J owns i8_nassign(nb, J) of them
+        const long long gblk = p.gbase[t.c] / I8_B_ALL + i8_blocks_before(nb, t.I) * p.T;      // < 2^31 (checked by the host plan)
+        ttab[i] = make_int4(t.I | (i8_nassign(nb, t.I) << 16), cd.pad_off + 64 * t.I, (int)gblk, nb);
     }
     // every role walks the units (64-row tile, trait) in the same order: f(tile entry, s)
     auto for_units = [&](auto f) {
@@ -317,6 +350,7 @@ __global__ void __launch_bounds__(I8_THREADS, 1) i8_contract_kernel(const I8Para
         for (int s = 0; s < I8_STAGES; ++s) { i8_mbar_init(full0 + 8 * s, (CG2 && crank == 0) ? 2 : 1); i8_mbar_init(empty0 + 8 * s, 1); }
         i8_mbar_init(accfull, 1);
         i8_mbar_init(accempty, CG2 ? 2 * I8_EPI_WARPS : I8_EPI_WARPS);
+        i8_mbar_init(accemptyB, CG2 ? 2 * I8_EPI_WARPS : I8_EPI_WARPS);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == I8_EPI_WARPS) {
@@ -339,25 +373,31 @@ __global__ void __launch_bounds__(I8_THREADS, 1) i8_contract_kernel(const I8Para
         // counters stay in uniform registers), one elected lane issues the copies
         unsigned slot = 0, ph = 0;
         for_units([&](const int4 e, int s) {
-            const int J = e.x & 0xFFFF, nkb = e.x >> 16;
-            const long long gblk = ((long long)e.w << 32) | (unsigned)e.z;
-            const signed char* abase = p.xi + (X * p.nkb_total + ((e.y - 64 * J) >> 6)) * (long long)I8_A_BYTES;
+            const int J = e.x & 0xFFFF, nkb = e.x >> 16, nb = e.w;
+            const long long gblk = (long long)e.z;
+            const signed char* abase = p.xi + (X * p.nkb_total + ((e.y - 64 * J) >> 6)) * (long long)I8_A_BYTES;       // k-block 0 of the chromosome
             const signed char* gb = p.G + (gblk + s) * (long long)I8_B_ALL + crank * B_STAGE;       // CG2: this CTA's half
+            int ka = J;                                  // the chromosome's k-block of step kb: i8_block_k(nb, J, kb), stepped
             for (int kb = 0; kb < nkb; ++kb) {
                 i8_mbar_wait(empty0 + 8 * slot, ph ^ 1u);
                 if (v2_elect()) {
                     const unsigned dst = i8_smem_u32(stage0) + slot * I8_STAGE_BYTES, bar = full0 + 8 * slot;
                     if (I8_DBG(8 | 16)) {            // profiling: without the xi copy (8) / the digit copy (16)
                         i8_mbar_expect_tx(bar, (I8_DBG(8) ? 0 : I8_A_BYTES) + (I8_DBG(16) ? 0 : B_STAGE));
-                        if (!I8_DBG(8)) i8_bulk_g2s(dst, abase + (long long)kb * I8_A_BYTES, I8_A_BYTES, bar);
+                        if (!I8_DBG(8)) i8_bulk_g2s(dst, abase + (long long)ka * I8_A_BYTES, I8_A_BYTES, bar);
                         if (!I8_DBG(16)) i8_bulk_g2s(dst + I8_A_BYTES, gb + (long long)kb * T * I8_B_ALL, B_STAGE, bar);
                     } else {
                         i8_mbar_expect_tx(bar, I8_STAGE_BYTES);
-                        i8_bulk_g2s(dst, abase + (long long)kb * I8_A_BYTES, I8_A_BYTES, bar);
+                        i8_bulk_g2s(dst, abase + (long long)ka * I8_A_BYTES, I8_A_BYTES, bar);
                         i8_bulk_g2s(dst + I8_A_BYTES, gb + (long long)kb * T * I8_B_ALL, B_STAGE, bar);
                     }
                 }
                 __syncwarp();
+#ifndef GMS_I8_TRIANGLE
+                if (++ka == nb) ka = 0;
+#else
+                ka = kb;                                 // triangle order: J, 0, 1, .. J - 1
+#endif
                 if (++slot == I8_STAGES) { slot = 0; ph ^= 1u; }
             }
         });
@@ -388,28 +428,52 @@ __global__ void __launch_bounds__(I8_THREADS, 1) i8_contract_kernel(const I8Para
             const unsigned long long da0 = i8_desc(i8_smem_u32(stage0), I8_M * 16, 128);
             const unsigned long long db0 = i8_desc(i8_smem_u32(stage0) + I8_A_BYTES, B_LBO, 128);
             unsigned slot = 0, ph = 0, u = 0;
+            auto issue = [&](unsigned sl, int kb, bool partA, bool partB) {      // the MMAs of one 64-k stage (elected lane)
+                const unsigned long long das = da0 + ((sl * I8_STAGE_BYTES) >> 4), dbs = db0 + ((sl * I8_STAGE_BYTES) >> 4);
+#pragma unroll
+                for (int kk = 0; kk < I8_KB / 32; ++kk) {
+                    if (I8_DBG(2)) continue;
+                    const unsigned long long da = das + ((kk * 2 * (I8_M * 16)) >> 4);
+                    const unsigned long long dbA = dbs + ((kk * 2 * B_LBO) >> 4), dbB = dbs + ((B_SECOND + kk * 2 * B_LBO) >> 4);
+                    if (CG2) {
+                        if (partA) i8_mma_cg2(tmem_base, da, dbA, idescA, (kb | kk) != 0);
+                        if (partB && !I8_DBG(4)) i8_mma_cg2(tmem_base + I8_NA, da, dbB, idescB, (kb | kk) != 0);
+                    } else {
+                        if (partA) i8_mma(tmem_base, da, dbA, idescA, (kb | kk) != 0);
+                        if (partB && !I8_DBG(4)) i8_mma(tmem_base + I8_NA, da, dbB, idescB, (kb | kk) != 0);
+                    }
+                }
+            };
             for_units([&](const int4 e, int) {
                 const int nkb = e.x >> 16;
                 i8_mbar_wait(accempty, (u & 1u) ^ 1u);                     // the epilogue(s) have drained the accumulators
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#ifdef GMS_I8_SPLITREL
+                // `accempty` only covers the columns of the first MMA (digits 0-3): its MMAs of the first two stages run while
+                // the epilogues still read the other columns, then the second MMA catches up
+                const int pre = nkb < 2 ? nkb : 2;
+                {
+                    unsigned sl = slot, p2 = ph;
+                    for (int kb = 0; kb < pre; ++kb) {
+                        i8_mbar_wait(full0 + 8 * sl, p2);
+                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                        if (v2_elect()) issue(sl, kb, true, false);
+                        __syncwarp();
+                        if (++sl == (unsigned)I8_STAGES) { sl = 0; p2 ^= 1u; }
+                    }
+                }
+                i8_mbar_wait(accemptyB, (u & 1u) ^ 1u);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#else
+                const int pre = 0;
+#endif
                 for (int kb = 0; kb < nkb; ++kb) {
-                    i8_mbar_wait(full0 + 8 * slot, ph);
-                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    if (kb >= pre) {
+                        i8_mbar_wait(full0 + 8 * slot, ph);
+                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    }
                     if (v2_elect()) {
-                        const unsigned long long das = da0 + ((slot * I8_STAGE_BYTES) >> 4), dbs = db0 + ((slot * I8_STAGE_BYTES) >> 4);
-#pragma unroll
-                        for (int kk = 0; kk < I8_KB / 32; ++kk) {
-                            if (I8_DBG(2)) continue;
-                            const unsigned long long da = das + ((kk * 2 * (I8_M * 16)) >> 4);
-                            const unsigned long long dbA = dbs + ((kk * 2 * B_LBO) >> 4), dbB = dbs + ((B_SECOND + kk * 2 * B_LBO) >> 4);
-                            if (CG2) {
-                                i8_mma_cg2(tmem_base, da, dbA, idescA, (kb | kk) != 0);
-                                if (!I8_DBG(4)) i8_mma_cg2(tmem_base + I8_NA, da, dbB, idescB, (kb | kk) != 0);
-                            } else {
-                                i8_mma(tmem_base, da, dbA, idescA, (kb | kk) != 0);
-                                if (!I8_DBG(4)) i8_mma(tmem_base + I8_NA, da, dbB, idescB, (kb | kk) != 0);
-                            }
-                        }
+                        issue(slot, kb, kb >= pre, true);
                         if (CG2) i8_commit_cg2(empty0 + 8 * slot, 3);     // frees the slot in BOTH CTAs when these MMAs retire
                         else i8_commit(empty0 + 8 * slot);
                         if (kb + 1 == nkb) {                               // accumulators of this (tile, trait) are complete
@@ -449,10 +513,16 @@ __global__ void __launch_bounds__(I8_THREADS, 1) i8_contract_kernel(const I8Para
                 }
             }
         };
-        auto release = [&]() {                       // TMEM fully read: the next unit's MMAs may start
+        auto release_bar = [&](unsigned bar) {       // this warp has read its part of the accumulator columns `bar` stands for
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
-            if (lane == 0) { if (CG2) i8_mbar_arrive_remote(accempty, 0); else i8_mbar_arrive(accempty); }
+            if (lane == 0) { if (CG2) i8_mbar_arrive_remote(bar, 0); else i8_mbar_arrive(bar); }
+        };
+        auto release = [&]() {                       // TMEM fully read: the next unit's MMAs may start
+#ifdef GMS_I8_SPLITREL
+            release_bar(accemptyB);
+#endif
+            release_bar(accempty);
         };
         auto load4 = [&](int ch, int (&d)[I8_DIG][4]) {        // rows 4 ch .. 4 ch + 3 of this warp's half, all digit planes
 #pragma unroll
@@ -492,6 +562,10 @@ __global__ void __launch_bounds__(I8_THREADS, 1) i8_contract_kernel(const I8Para
             }
         };
         if (nunits > 0) pf_issue(0, 0);
+        else if (live) {                     // a range without tiles (the host plan makes none): its slab still has to read as zero
+            double* out = p.Zpart + ((long long)(split * 2 + half) * p.n_units + unit) * (T * T);
+            for (int i = 0; i < T * T; ++i) out[i] = 0.0;
+        }
         int s = 0, jl = 0;                                       // unit u = (trait s, tile jt_begin + jl)
         for (int u = 0; u < nunits; ++u) {
             const unsigned acc_it = (unsigned)u;
@@ -528,7 +602,9 @@ __global__ void __launch_bounds__(I8_THREADS, 1) i8_contract_kernel(const I8Para
                 int s_n = s, jl_n = jl + 1;
                 if (jl_n == ntl) { jl_n = 0; ++s_n; }
                 if (u + 1 < nunits) pf_issue(s_n, jl_n);
+#ifdef GMS_I8_DENSE_EPI
                 const unsigned rows = __reduce_or_sync(0xffffffffu, nz);       // warp-uniform: rows some unit of the warp needs
+#endif
                 asm volatile("bar.sync 1, %0;" ::"n"(32 * I8_EPI_WARPS) : "memory");
                 const double* erow = erow_all + half * I8_RPT;       // erow[t * 64 + jr]
                 const int* ebrow = eb_all + half * I8_RPT;            // ebrow[jr]
@@ -541,6 +617,63 @@ __global__ void __launch_bounds__(I8_THREADS, 1) i8_contract_kernel(const I8Para
                     // TMEM reads run at ~64 B per cycle and SM sub-partition: ~900 cycles for the 448 columns of a unit, the one
                     // part of the epilogue no MMA can overlap with while a unit's accumulator fills TMEM
                     long long W[I8_RPT];
+#ifdef GMS_I8_SPLITREL
+                    // the columns of the first MMA (digits 0-3) of all 32 rows first: once they are read the next unit's first MMAs
+                    // may run, while this warp reads the remaining digits
+                    constexpr int NCH = I8_RPT / 4;          // 8 chunks of 4 rows
+                    {
+                        int dA[4][4], dB[4][4];
+                        auto ld = [&](int ch, int (&d)[4][4]) {
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) i8_tmem_ld4(tlane + i * I8_N + ch * 4, d[i]);
+                        };
+                        auto cb = [&](int ch, const int (&d)[4][4]) {
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) W[ch * 4 + q] = i8_combine_hi(d[0][q], d[1][q], d[2][q], d[3][q]);
+                        };
+                        ld(0, dA);
+                        i8_tmem_wait16(dA);
+#pragma unroll
+                        for (int cp = 0; cp < NCH / 2; ++cp) {
+                            ld(2 * cp + 1, dB);
+                            cb(2 * cp, dA);
+                            i8_tmem_wait16(dB);
+                            if (cp + 1 < NCH / 2) ld(2 * cp + 2, dA);
+                            cb(2 * cp + 1, dB);
+                            if (cp + 1 < NCH / 2) i8_tmem_wait16(dA);
+                        }
+                    }
+                    release_bar(accempty);
+                    {
+                        constexpr int NR = I8_DIG - 4;
+                        int dA[NR][4], dB[NR][4];
+                        auto ld = [&](int ch, int (&d)[NR][4]) {
+#pragma unroll
+                            for (int i = 0; i < NR; ++i) i8_tmem_ld4(tlane + (4 + i) * I8_N + ch * 4, d[i]);
+                        };
+                        auto cb = [&](int ch, const int (&d)[NR][4]) {
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) {
+                                int sv[NR];
+#pragma unroll
+                                for (int i = 0; i < NR; ++i) sv[i] = d[i][q];
+                                W[ch * 4 + q] = (long long)((unsigned long long)W[ch * 4 + q] + (unsigned long long)i8_combine_lo(sv));
+                            }
+                        };
+                        ld(0, dA);
+                        i8_tmem_wait_rest(dA);
+#pragma unroll
+                        for (int cp = 0; cp < NCH / 2; ++cp) {
+                            ld(2 * cp + 1, dB);
+                            cb(2 * cp, dA);
+                            i8_tmem_wait_rest(dB);
+                            if (cp + 1 < NCH / 2) ld(2 * cp + 2, dA);
+                            cb(2 * cp + 1, dB);
+                            if (cp + 1 < NCH / 2) i8_tmem_wait_rest(dA);
+                        }
+                    }
+                    release_bar(accemptyB);
+#else
                     {
                         int dA[I8_DIG][4], dB[I8_DIG][4];
                         auto comb4 = [&](int ch, const int (&d)[I8_DIG][4]) {
@@ -566,23 +699,79 @@ __global__ void __launch_bounds__(I8_THREADS, 1) i8_contract_kernel(const I8Para
                         }
                     }
                     release();
+#endif
                     if (!I8_DBG(32)) {
-                        // ---- convert (integer instructions only, one basic block: overlaps the next unit's MMAs for free):
-                        // W[j] <- bit pattern of v_j = xi_x[j] W[j] 2^(E_j - I8_FRAC)
+#ifndef GMS_I8_DENSE_EPI
+                        // ---- COMPACTION. A mask entry is non-zero on ~13 % of a cross's rows, but which rows differs from lane to
+                        // lane, so a row-by-row loop runs all 32 rows for every lane. Instead each thread packs ITS non-zero rows
+                        // (row sum + row number) into a private column of shared memory, RS rows at a time, and the warp loops to the
+                        // LARGEST count of its lanes: ~6 of 16 slots for a per-cross mask, i.e. a third of the FP64 instructions, which
+                        // is what counts - every FP64 instruction stalls the SM's tcgen05 MMAs. Within a round
+                        // the rows of a warp's gathers lie in one 16-row window of d_t[.]: no shared-memory bank conflicts.
+                        constexpr int RS = TT <= 8 ? 16 : 8;          // rows per round (the round's values live in registers)
+#pragma unroll
+                        for (int r0 = 0; r0 < I8_RPT; r0 += RS) {
+                            int cnt = 0;
+#pragma unroll
+                            for (int r = 0; r < RS; ++r) {           // slot cnt is overwritten until a row with a mask entry takes it
+                                cw[cnt * (32 * I8_EPI_WARPS) + etid] = W[r0 + r];
+                                cj[cnt * (32 * I8_EPI_WARPS) + etid] = (unsigned char)r;
+                                cnt += (int)((nz >> (r0 + r)) & 1u);
+                            }
+                            const int kmax = __reduce_max_sync(0xffffffffu, cnt);      // warp-uniform trip count
+                            // convert (integer instructions only; overlaps the MMAs for free): bit pattern of
+                            // v = xi_x[j] W[j] 2^(E_j - I8_FRAC) for the thread's k-th non-zero row j (0 beyond its own count)
+                            long long vv[RS];
+                            int jj[RS];
+#pragma unroll
+                            for (int k = 0; k < RS; ++k) { vv[k] = 0; jj[k] = r0; }
+#pragma unroll
+                            for (int k0 = 0; k0 < RS; k0 += 2) {      // slots in pairs: two independent dependency chains per branch
+                                if (k0 < kmax) {
+#pragma unroll
+                                    for (int k = k0; k < k0 + 2; ++k) {
+                                        const long long w = cw[k * (32 * I8_EPI_WARPS) + etid];
+                                        const int j = r0 + (int)(cj[k * (32 * I8_EPI_WARPS) + etid] & (RS - 1));
+                                        unsigned bh, bl;
+                                        i8_cvt_bits(w, ebrow[j], k < cnt ? 1u : 0u, (ng >> j) & 1u, bh, bl);
+                                        vv[k] = (long long)(((unsigned long long)bh << 32) | bl);
+                                        jj[k] = j;
+                                    }
+                                }
+                            }
+                            // Every conversion is complete before the first FP64 instruction, and the FP64 instructions form one dense
+                            // burst per round: next to running tcgen05 MMAs FMAs scattered over integer code cost the tensor pipe ~4-5
+                            // cycles per warp instruction (tools/tc_contention_probe.cu). The empty asm pins the values for the compiler.
+#pragma unroll
+                            for (int k = 0; k < RS; ++k) asm volatile("" : "+l"(vv[k]), "+r"(jj[k]));
+                            // ---- FP64 burst, the only FP64 instructions of the kernel: zs[t] += d_t[j] v
+                            if (!I8_DBG(64)) {
+#pragma unroll
+                                for (int k0 = 0; k0 < RS; k0 += 2) {
+                                    if (k0 < kmax) {
+                                        const double v0 = __longlong_as_double(vv[k0]), v1 = __longlong_as_double(vv[k0 + 1]);
+                                        const double* e0 = erow + jj[k0];
+                                        const double* e1 = erow + jj[k0 + 1];
+#pragma unroll
+                                        for (int t = 0; t < TT; ++t)
+                                            if (t < T) {
+                                                zs[t][k0 % NP] = fma(e0[t * 64], v0, zs[t][k0 % NP]);
+                                                zs[t][(k0 + 1) % NP] = fma(e1[t * 64], v1, zs[t][(k0 + 1) % NP]);
+                                            }
+                                    }
+                                }
+                            }
+                        }
+#else
+                        // ---- every row (tools only, for A/B timing): convert all 32 rows, then one dense FP64 burst over all of them
 #pragma unroll
                         for (int jr = 0; jr < I8_RPT; ++jr) {
                             unsigned bh, bl;
                             i8_cvt_bits(W[jr], ebrow[jr], (nz >> jr) & 1u, (ng >> jr) & 1u, bh, bl);
                             W[jr] = (long long)(((unsigned long long)bh << 32) | bl);
                         }
-                        // Every conversion is complete before the first FP64 instruction, and the FP64 instructions form ONE dense
-                        // burst per unit: next to running tcgen05 MMAs FMAs scattered over integer code cost the tensor pipe ~4-5 cycles
-                        // per warp instruction (tools/tc_contention_probe.cu; measured again on this kernel).
-                        // The empty asm pins the values for the compiler, the warp-uniform branch starts a new basic block for ptxas.
 #pragma unroll
                         for (int jr = 0; jr < I8_RPT; ++jr) asm volatile("" : "+l"(W[jr]));
-                        // ---- FP64 burst, the only FP64 instructions of the kernel: zs[t] += d_t[j] v_j for all 32 rows (rows == 0:
-                        // no unit of this warp has a mask entry in the tile, e.g. a warp of padding units)
                         if (rows != 0u && !I8_DBG(64)) {
 #pragma unroll
                             for (int j0 = 0; j0 < I8_RPT; j0 += 2) {
@@ -596,6 +785,7 @@ __global__ void __launch_bounds__(I8_THREADS, 1) i8_contract_kernel(const I8Para
                                     }
                             }
                         }
+#endif
                     }
                 }
             }
@@ -607,8 +797,8 @@ __global__ void __launch_bounds__(I8_THREADS, 1) i8_contract_kernel(const I8Para
                     for (int t = 0; t < TT; ++t)
                         if (t < T) {
                             double z = zs[t][0];
-                            if (NP == 4) z = (zs[t][0] + zs[t][1]) + (zs[t][2] + zs[t][3]);
-                            else if (NP == 2) z = zs[t][0] + zs[t][1];
+#pragma unroll
+                            for (int k = 1; k < NP; ++k) z += zs[t][k];
                             out[t * T + s] = z;
                         }
                 }
@@ -634,7 +824,7 @@ int i8_max_tiles_per_split() { return I8_TTAB; }
 long long i8_block_bytes() { return I8_B_ALL; }            // digit image of one (64 x 64 block, trait)
 static size_t i8_fixed_smem(int T) {
     const size_t rowbuf = (size_t)T * 64 * 8 + 64 * 4;          // per buffer (see the epilogue)
-    return (2 * I8_MAX_STAGES + 4) * 8 + (size_t)I8_TTAB * 16 + 2 * rowbuf;
+    return (2 * I8_MAX_STAGES + 4) * 8 + (size_t)I8_TTAB * 16 + 2 * rowbuf + (size_t)I8_CSLOTS * 32 * I8_EPI_WARPS * 9;
 }
 // pipeline stages: as many as fit in the 227 KiB a CTA may use (the kernel is bound by the latency of its operand stream)
 int i8_stages(int T, bool cg2) {

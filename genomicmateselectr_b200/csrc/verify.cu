@@ -6,10 +6,11 @@
 // scale_s[j] = 2^E >= max_k |G_s[j,k]| / 0.996 (i8path.cu, i8digits.cuh). That is fixed point, not floating point: a SNP with
 // a huge effect sets the scale of every row it reaches, and a unit in which that SNP does not segregate (mask 0) sums only
 // small terms that each carry the absolute error u * scale_s[j], u = I8_U = 2^-48 (1 + 2^-4): 2^-48 from rounding to
-// nearest (i8_scale_kernel picks E so that no digit ever saturates) plus the 53-bit truncation of a row sum in the epilogue. For unit x with mask mu in {-1,0,1}^m, row j of the lower block triangle sums over the non-zero
-// mask entries k of its chromosome with k < 64 (floor(j / 64) + 1), at most n_j = (non-zeros before j) + 128 of them, so
-//     |Z[t][s] - exact| <= u * sum_j |e_t[j] mu_j| * scale_s[j] * n_j  <=  u * Smax_s * B_t(x),
-//     B_t(x) = sum_j |e_t[j] mu_j| n_j,   Smax_s = largest row scale of trait s.
+// nearest (i8_scale_kernel picks E so that no digit ever saturates) plus the 53-bit truncation of a row sum in the epilogue.
+// For unit x with mask mu in {-1,0,1}^m, row j sums over the non-zero mask entries k in the 64-blocks its row tile owns
+// (about half of the chromosome's, common.cuh), at most n_c(x) = the unit's non-zero entries on the chromosome, so
+//     |Z[t][s] - exact| <= u * sum_j |e_t[j] mu_j| * scale_s[j] * n_c  <=  u * Smax_s * B_t(x),
+//     B_t(x) = sum_c n_c(x) sum_{j in c} |e_t[j] mu_j|,   Smax_s = largest row scale of trait s.
 // The table entry is X[t,s] = Z[t][s] + Z[s][t], so a unit PASSES when
 //     2 u * max_t (B_t / sqrt|X[t,t]|) * max_s (Smax_s / sqrt|X[s,s]|)  <=  tau              (tau = 2^-31 ~ 4.7e-10)
 // which implies |error of X[t,s]| <= tau * sqrt(X[t,t] X[s,s]) for every trait pair: every variance to tau relative,
@@ -104,10 +105,9 @@ __global__ void __launch_bounds__(VER_THREADS) i8_verify_accumulate_kernel(const
                     while (nz) {
                         const int j = q * 128 + w * 32 + (__ffs(nz) - 1);
                         nz &= nz - 1;
-                        const double nj_bound = (double)(nnz + 128);          // n_j <= non-zeros before j + 128
                         ++nnz;
 #pragma unroll
-                        for (int i = 0; i < VER_TG; ++i) acc[i] = fma(se[i][j], nj_bound, acc[i]);
+                        for (int i = 0; i < VER_TG; ++i) acc[i] += se[i][j];
                     }
                 }
             }
@@ -115,7 +115,7 @@ __global__ void __launch_bounds__(VER_THREADS) i8_verify_accumulate_kernel(const
         if (live) {
 #pragma unroll
             for (int i = 0; i < VER_TG; ++i)
-                if (i < ng) vb[t0 + i] = acc[i];
+                if (i < ng) vb[t0 + i] = acc[i] * (double)nnz;        // n_j <= the unit's non-zeros on the chromosome
             if (t0 == 0) p.part_n[(long long)blockIdx.y * p.n_units + unit] = nnz;
         }
     }

@@ -17,3 +17,13 @@ def test_i8digits_known_answers(tmp_path, ndig):
                     os.path.join(ROOT, "tests", "csrc", "i8digits_kat.cpp")], check=True)
     r = subprocess.run([exe], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and r.stdout.startswith("ok "), r.stdout + r.stderr
+
+
+def test_i8_block_ownership(tmp_path):
+    """csrc/common.cuh: the round-robin deal of a chromosome's 64-blocks to its 64-row tiles covers every unordered pair once."""
+    exe = str(tmp_path / "i8blocks_kat")
+    cuda_inc = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "include")
+    subprocess.run(["g++", "-O2", "-std=c++17", "-I", cuda_inc, "-o", exe,
+                    os.path.join(ROOT, "tests", "csrc", "i8blocks_kat.cpp")], check=True)
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and r.stdout.startswith("ok "), r.stdout + r.stderr
