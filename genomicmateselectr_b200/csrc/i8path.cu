@@ -3,24 +3,29 @@
 //
 // FP64 has no tcgen05 kind, but this contraction has a special shape: one operand is TERNARY.
 //     C_s[j,x] = sum_k G_s[j,k] xi_x[k],   G_s[j,k] = L'[j,k] d_s[k]  (FP64),   xi in {-1,0,+1}
-// xi is exact in int8. G_s is rounded row-wise to 47 fractional bits of a shared power-of-two row scale 2^E(j,s) with
-// max_k |G_s[j,k]| <= 0.996 * 2^E and split into 6 BALANCED radix-256 digits g_i in [-128, 127] (i8digits.cuh: every plane
-// carries a full 8 bits, so six planes hold what seven sign-magnitude radix-128 planes held less two bits - 14 % fewer
-// MMAs and operand bytes):  G = 2^(E+1) sum_i g_i 256^-(i+1) + r,  |r| <= 2^(E-48) (round to nearest). Each digit plane times xi
+// xi is exact in int8. G_s is rounded row-wise to I8_FRAC = 49 fractional bits of a shared power-of-two row scale 2^E(j,s)
+// with max_k |G_s[j,k]| <= 2^E and split into I8_DIG = 7 BALANCED radix-256 digits g_i in [-128, 127] (i8digits.cuh; the
+// build variant -DGMS_I8_DIG=6 keeps 47 bits in six planes: 14 % fewer MMAs for 4 x the rounding error, tools only):
+// G = 2^(E - I8_FRAC) sum_i g_i 256^(I8_DIG-1-i) + r,  |r| <= 2^(E-50) (round to nearest). Each digit plane times xi
 // is an int8 x int8 -> int32 product whose sum over the k of a row is EXACT in int32 for any chromosome length this library
 // accepts (|sum| <= 128 n for n non-zero xi entries), so the 5th-generation tensor cores (tcgen05.mma kind::i8,
-// accumulators in TMEM) do the O(m^2) work at int8 rate. The epilogue recombines the six digit sums exactly in 64-bit
+// accumulators in TMEM) do the O(m^2) work at int8 rate. The epilogue recombines the digit sums exactly in 64-bit
 // integer arithmetic (exact while n < 2^15; verify.cu sends units with n >= 2^14 on one chromosome to the FP64 path),
-// builds the FP64 bit pattern of xi_x[j] W 2^(E-47) with integer instructions (i8digits.cuh: i8_cvt_bits - FP64
+// builds the FP64 bit pattern of xi_x[j] W 2^(E-I8_FRAC) with integer instructions (i8digits.cuh: i8_cvt_bits - FP64
 // instructions stall the MMAs of the SM, integer ones do not), multiplies by d_t[j] and accumulates the T x T quadratic
 // forms per cross in registers (TMEM lane = cross, so the reduction over SNPs j is thread-local: no shuffles, no atomics).
 // The only FP64 instructions left are those T FMAs per (cross, row, trait).
-// ROW SKIPPING (template parameter SKIP, used for the per-cross table): xi_x[j] is non-zero on ~13 % of a cross's SNPs, and
-// a warp only has to visit the rows j where ANY of its 32 crosses has a non-zero entry. api.cu orders the crosses of a pass
-// by sire, so the crosses of a warp share (mostly) one sire and the union of their non-zero rows is about that sire's
-// heterozygous SNPs: the warp ORs the masks (redux.sync), walks the set bits four at a time and loads exactly those
-// accumulator columns (tcgen05.ld .x1). That removes about half of the TMEM reads, the integer recombination and - what
-// matters - the FP64 FMAs, and shortens the time the next unit's MMAs wait for the accumulator.
+// WHICH BLOCKS A ROW TILE SUMS: the matrix is symmetric and the table is X = Z + Z', so each unordered pair of 64-blocks can
+// be evaluated in either orientation; common.cuh deals them evenly (row tile J owns blocks J, J + 1, ... modulo the
+// chromosome's block count, about half of them) instead of the lower block triangle's 1 .. nb blocks per row tile: every
+// accumulator then carries the same MMA work, longer than the epilogue of the previous one.
+// WHAT THE EPILOGUE COSTS (measured with the -DGMS_PROFILE switches, 50k cassava crosses, 7 planes): MMAs + loads alone
+// 27.3 ms; + the TMEM drain 31.5 (the one accumulator fills TMEM, so MMAs and drain alternate); + the integer conversion
+// 32.6; + the FP64 FMAs 37.0 when they run in the window where the tensor pipe is idle anyway (GMS_I8_LATE, below), 39.1
+// when they run next to the next unit's MMAs. Tried and dropped (all parity-green): compacting each thread's non-zero rows
+// through shared memory so that a warp loops to its largest count (a third of the FP64 instructions, but 45.8 ms: the
+// gathers spread the burst out); releasing the accumulator columns of the first MMA before the rest is read (+-0);
+// skipping rows no cross of a warp needs (predication breaks the dense burst: slower).
 // THE RESULT IS FIXED POINT RELATIVE TO THE ROW SCALE, not floating point: verify.cu bounds the error of every unit
 // a posteriori and api.cu re-evaluates the units that fail the bound with the FP64 contraction (contract.cu).
 //
@@ -63,7 +68,6 @@ constexpr int I8_EPI_WARPS = 8;     // two per TMEM lane quarter, each takes 32 
                                     // per thread and x4 TMEM loads, measured 13 % slower at T = 5)
 constexpr int I8_RPT = 32;          // SNP rows per epilogue thread and tile = one word of the bit-planes
 constexpr int I8_THREADS = 32 * (I8_EPI_WARPS + 2);
-constexpr int I8_CSLOTS = 16;       // compaction slots per epilogue thread (rows per round of the epilogue)
 
 // ------------------------------------------------------------------------------------------ prep: xi images
 // image (X tile, global k-block) : [chunk cc (4)][r1 (16)][r0 (8)][16 bytes], row r = 8 r1 + r0, k = 16 cc + b
@@ -180,11 +184,11 @@ __global__ void i8_scale_kernel(double* __restrict__ scale, long long n) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const double v = scale[i];
-    // rowmax <= 0.996 * 2^e, so that rn(G 2^(47 - e)) fits six balanced radix-256 digits: no entry ever saturates
+    // rowmax <= I8_FILL * 2^e, so that rn(G 2^(I8_FRAC - e)) fits I8_DIG balanced radix-256 digits: no entry ever saturates
     scale[i] = ldexp(1.0, v > 0x1p-900 ? i8_scale_exp(v) : 0);
 }
 
-// digit images: (c, J, kb <= J, s): one 384-row K-major operand per (block, trait); one thread = 16 consecutive k of a
+// digit images: (c, J, kb, s): one (I8_DIG x 64)-row K-major operand per (block, trait); one thread = 16 consecutive k of a
 // row, L' read once and reused for all T traits
 __global__ void i8_build_digits_kernel(const double* __restrict__ tiles, const ChromDesc* __restrict__ chrom, int c_begin,
                                        int c_end, const int* __restrict__ blkpref, const double* __restrict__ emat,
@@ -207,9 +211,9 @@ __global__ void i8_build_digits_kernel(const double* __restrict__ tiles, const C
         const int col = kb * 64 + cc * 16 + b;
         lp[b] = (row < cd.m && col < cd.m) ? lsym64(tiles, cd, row, col) : 0.0;
     }
-    // the 6 digit planes of one (block, trait) form ONE K-major operand of 6 x 64 = 384 rows:
-    // [chunk cc (4)][row group R1 = 8 i + r1 (48)][r0 (8)][16 bytes]  ->  LBO = 48 * 128 B, SBO = 128 B,
-    // so a k32-step needs two MMAs (N = 256: digits 0-3, N = 128: digits 4-5) instead of six N = 64 ones
+    // the I8_DIG digit planes of one (block, trait) form ONE K-major operand of I8_DIG x 64 rows:
+    // [chunk cc (4)][row group R1 = 8 i + r1 (8 I8_DIG)][r0 (8)][16 bytes]  ->  LBO = 8 I8_DIG * 128 B, SBO = 128 B,
+    // so a k32-step needs two MMAs (N = 256: digits 0-3, N = 192 or 128: the remaining ones) instead of one N = 64 MMA per plane
     const int r1 = r >> 3, r0 = r & 7;
     const double* ecol = emat + cd.pad_off + kb * 64 + cc * 16;
     for (int s = 0; s < T; ++s) {
@@ -217,8 +221,8 @@ __global__ void i8_build_digits_kernel(const double* __restrict__ tiles, const C
         signed char d[I8_DIG][16];
 #pragma unroll
         for (int b = 0; b < 16; ++b) {
-            // |x| <= 0.996 (i8_scale_kernel); round to nearest to 47 fractional bits (|error| <= 2^-48 of the row scale, the
-            // clamp never bites), then six balanced radix-256 digits: integer arithmetic only (i8digits.cuh)
+            // |x| <= I8_FILL (i8_scale_kernel); round to nearest to I8_FRAC fractional bits (|error| <= 2^-(I8_FRAC+1) of the row
+            // scale, the clamp never bites), then I8_DIG balanced radix-256 digits: integer arithmetic only (i8digits.cuh)
             signed char dg[I8_DIG];
             i8_split(i8_fixed((lp[b] * ecol[(long long)s * mp_total + b]) * inv), dg);
 #pragma unroll
@@ -269,27 +273,8 @@ __device__ __forceinline__ void i8_tmem_wait(int (&d)[I8_DIG][4]) {
 #endif
 }
 
-__device__ __forceinline__ void i8_tmem_wait16(int (&d)[4][4]) {
-    asm volatile("tcgen05.wait::ld.sync.aligned;"
-                 : "+r"(d[0][0]), "+r"(d[0][1]), "+r"(d[0][2]), "+r"(d[0][3]), "+r"(d[1][0]), "+r"(d[1][1]), "+r"(d[1][2]), "+r"(d[1][3]),
-                   "+r"(d[2][0]), "+r"(d[2][1]), "+r"(d[2][2]), "+r"(d[2][3]), "+r"(d[3][0]), "+r"(d[3][1]), "+r"(d[3][2]), "+r"(d[3][3])
-                 :: "memory");
-}
-__device__ __forceinline__ void i8_tmem_wait_rest(int (&d)[I8_DIG - 4][4]) {
-#if GMS_I8_DIG == 7
-    asm volatile("tcgen05.wait::ld.sync.aligned;"
-                 : "+r"(d[0][0]), "+r"(d[0][1]), "+r"(d[0][2]), "+r"(d[0][3]), "+r"(d[1][0]), "+r"(d[1][1]), "+r"(d[1][2]), "+r"(d[1][3]),
-                   "+r"(d[2][0]), "+r"(d[2][1]), "+r"(d[2][2]), "+r"(d[2][3])
-                 :: "memory");
-#else
-    asm volatile("tcgen05.wait::ld.sync.aligned;"
-                 : "+r"(d[0][0]), "+r"(d[0][1]), "+r"(d[0][2]), "+r"(d[0][3]), "+r"(d[1][0]), "+r"(d[1][1]), "+r"(d[1][2]), "+r"(d[1][3])
-                 :: "memory");
-#endif
-}
-
 // Loop order: trait s outer, 64-row tile inner; one unit = the accumulator of one (trait, tile). TT >= T is the compile-time
-// size of the column Z[:, s] an epilogue thread keeps in registers (EXACT: TT == T, no run-time trait predicates).
+// size of the column Z[:, s] an epilogue thread keeps in registers (EXACT: TT == T, no run-time trait predicates; every T <= 10).
 // CG2 = true: launched as clusters of 2 CTAs = two adjacent cross tiles forming ONE M = 256 tile (tcgen05 cta_group::2).
 // Each CTA stages its own xi tile and only HALF of every digit tile; the leader CTA's MMA thread issues the pair's MMAs once
 // both halves have landed (the peer relays its `full` phases to the leader), and its commits release the slot / publish the
@@ -304,7 +289,7 @@ __device__ __forceinline__ void i8_tmem_wait_rest(int (&d)[I8_DIG - 4][4]) {
 // hence the trait-outer loop for every T (the tile-outer loop of round 1 unrolled the epilogue T times to keep Z[T][T]).
 template <int TT, bool EXACT, bool CG2>
 __global__ void __launch_bounds__(I8_THREADS, 1) i8_contract_kernel(const I8Params p) {
-    const int T = EXACT ? TT : p.T;          // EXACT: T == TT at compile time (every T <= 8 has its own instantiation)
+    const int T = EXACT ? TT : p.T;          // EXACT: T == TT at compile time (every T <= 10 has its own instantiation)
     extern __shared__ __align__(1024) unsigned char smem[];
     unsigned char* stage0 = smem;
     constexpr int I8_STAGE_BYTES = I8Geo<CG2>::STAGE_BYTES, B_STAGE = I8Geo<CG2>::B_STAGE;
@@ -312,18 +297,12 @@ __global__ void __launch_bounds__(I8_THREADS, 1) i8_contract_kernel(const I8Para
     unsigned long long* bars = reinterpret_cast<unsigned long long*>(smem + I8_STAGES * I8_STAGE_BYTES);
     unsigned* tmem_slot = reinterpret_cast<unsigned*>(bars + 2 * I8_MAX_STAGES + 2);
     int4* ttab = reinterpret_cast<int4*>(bars + 2 * I8_MAX_STAGES + 4);        // this CTA's range of the 64-row tile list (I8_TTAB entries)
-    // row data of a unit, double-buffered: d_t[j] for T traits x 64 rows (FP64), then eb[j] = exponent field of scale_s[j] + 63 -
+    // row data of a unit, three buffers in turn: d_t[j] for T traits x 64 rows (FP64), then eb[j] = exponent field of scale_s[j] + 63 -
     // I8_FRAC - 1 (int) for the unit's trait s
     unsigned char* rowbuf = reinterpret_cast<unsigned char*>(ttab + I8_TTAB);
     const int rowbuf_bytes = T * 64 * 8 + 64 * 4;
-    // compaction slots of the epilogue threads: [I8_CSLOTS][256 threads] row sums (64 bit) and row numbers (8 bit), one private
-    // column per thread
-    long long* cw = reinterpret_cast<long long*>(rowbuf + 2 * rowbuf_bytes);
-    unsigned char* cj = reinterpret_cast<unsigned char*>(cw + I8_CSLOTS * 32 * I8_EPI_WARPS);
     const unsigned full0 = i8_smem_u32(bars), empty0 = i8_smem_u32(bars + I8_MAX_STAGES);
     const unsigned accfull = i8_smem_u32(bars + 2 * I8_MAX_STAGES), accempty = i8_smem_u32(bars + 2 * I8_MAX_STAGES + 1);
-    // GMS_I8_SPLITREL: the accumulator columns of the second MMA of a k32-step (digits 4 ..) are released separately
-    const unsigned accemptyB = i8_smem_u32(bars + 2 * I8_MAX_STAGES + 3);
     const unsigned crank = CG2 ? i8_cta_rank() : 0u;       // 0 = leader of the pair
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const long long X = blockIdx.x;
@@ -350,7 +329,6 @@ __global__ void __launch_bounds__(I8_THREADS, 1) i8_contract_kernel(const I8Para
         for (int s = 0; s < I8_STAGES; ++s) { i8_mbar_init(full0 + 8 * s, (CG2 && crank == 0) ? 2 : 1); i8_mbar_init(empty0 + 8 * s, 1); }
         i8_mbar_init(accfull, 1);
         i8_mbar_init(accempty, CG2 ? 2 * I8_EPI_WARPS : I8_EPI_WARPS);
-        i8_mbar_init(accemptyB, CG2 ? 2 * I8_EPI_WARPS : I8_EPI_WARPS);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == I8_EPI_WARPS) {
@@ -428,7 +406,7 @@ __global__ void __launch_bounds__(I8_THREADS, 1) i8_contract_kernel(const I8Para
             const unsigned long long da0 = i8_desc(i8_smem_u32(stage0), I8_M * 16, 128);
             const unsigned long long db0 = i8_desc(i8_smem_u32(stage0) + I8_A_BYTES, B_LBO, 128);
             unsigned slot = 0, ph = 0, u = 0;
-            auto issue = [&](unsigned sl, int kb, bool partA, bool partB) {      // the MMAs of one 64-k stage (elected lane)
+            auto issue = [&](unsigned sl, int kb) {      // the MMAs of one 64-k stage (elected lane)
                 const unsigned long long das = da0 + ((sl * I8_STAGE_BYTES) >> 4), dbs = db0 + ((sl * I8_STAGE_BYTES) >> 4);
 #pragma unroll
                 for (int kk = 0; kk < I8_KB / 32; ++kk) {
@@ -436,11 +414,11 @@ __global__ void __launch_bounds__(I8_THREADS, 1) i8_contract_kernel(const I8Para
                     const unsigned long long da = das + ((kk * 2 * (I8_M * 16)) >> 4);
                     const unsigned long long dbA = dbs + ((kk * 2 * B_LBO) >> 4), dbB = dbs + ((B_SECOND + kk * 2 * B_LBO) >> 4);
                     if (CG2) {
-                        if (partA) i8_mma_cg2(tmem_base, da, dbA, idescA, (kb | kk) != 0);
-                        if (partB && !I8_DBG(4)) i8_mma_cg2(tmem_base + I8_NA, da, dbB, idescB, (kb | kk) != 0);
+                        i8_mma_cg2(tmem_base, da, dbA, idescA, (kb | kk) != 0);
+                        if (!I8_DBG(4)) i8_mma_cg2(tmem_base + I8_NA, da, dbB, idescB, (kb | kk) != 0);
                     } else {
-                        if (partA) i8_mma(tmem_base, da, dbA, idescA, (kb | kk) != 0);
-                        if (partB && !I8_DBG(4)) i8_mma(tmem_base + I8_NA, da, dbB, idescB, (kb | kk) != 0);
+                        i8_mma(tmem_base, da, dbA, idescA, (kb | kk) != 0);
+                        if (!I8_DBG(4)) i8_mma(tmem_base + I8_NA, da, dbB, idescB, (kb | kk) != 0);
                     }
                 }
             };
@@ -448,32 +426,11 @@ __global__ void __launch_bounds__(I8_THREADS, 1) i8_contract_kernel(const I8Para
                 const int nkb = e.x >> 16;
                 i8_mbar_wait(accempty, (u & 1u) ^ 1u);                     // the epilogue(s) have drained the accumulators
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-#ifdef GMS_I8_SPLITREL
-                // `accempty` only covers the columns of the first MMA (digits 0-3): its MMAs of the first two stages run while
-                // the epilogues still read the other columns, then the second MMA catches up
-                const int pre = nkb < 2 ? nkb : 2;
-                {
-                    unsigned sl = slot, p2 = ph;
-                    for (int kb = 0; kb < pre; ++kb) {
-                        i8_mbar_wait(full0 + 8 * sl, p2);
-                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                        if (v2_elect()) issue(sl, kb, true, false);
-                        __syncwarp();
-                        if (++sl == (unsigned)I8_STAGES) { sl = 0; p2 ^= 1u; }
-                    }
-                }
-                i8_mbar_wait(accemptyB, (u & 1u) ^ 1u);
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-#else
-                const int pre = 0;
-#endif
                 for (int kb = 0; kb < nkb; ++kb) {
-                    if (kb >= pre) {
-                        i8_mbar_wait(full0 + 8 * slot, ph);
-                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    }
+                    i8_mbar_wait(full0 + 8 * slot, ph);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     if (v2_elect()) {
-                        issue(slot, kb, kb >= pre, true);
+                        issue(slot, kb);
                         if (CG2) i8_commit_cg2(empty0 + 8 * slot, 3);     // frees the slot in BOTH CTAs when these MMAs retire
                         else i8_commit(empty0 + 8 * slot);
                         if (kb + 1 == nkb) {                               // accumulators of this (tile, trait) are complete
@@ -497,44 +454,30 @@ __global__ void __launch_bounds__(I8_THREADS, 1) i8_contract_kernel(const I8Para
         if (live) { pa = p.unit_a[unit]; pb = (p.mode == MASK_XI) ? p.unit_b[unit] : 0; }
         const unsigned tlane = tmem_base + ((unsigned)(quarter * 32) << 16) + half * I8_RPT;
 
-        // this thread's mask entries of the tile's rows (one word of the bit-planes): nz = non-zero, ng = negative
-        auto load_mask = [&](long long prow, unsigned& nz, unsigned& ng) {
-            nz = ng = 0u;
-            if (live) {
-                const long long wi = (prow >> 5) + half;
-                const unsigned A = __ldg(p.planeA + (long long)pa * p.wpp + wi), B = __ldg(p.planeB + (long long)pa * p.wpp + wi);
-                if (p.mode == MASK_XI) {
-                    const unsigned A2 = __ldg(p.planeA + (long long)pb * p.wpp + wi), B2 = __ldg(p.planeB + (long long)pb * p.wpp + wi);
-                    nz = (A ^ B) & (A2 ^ B2);
-                    ng = ((~A & B) ^ (~A2 & B2)) & nz;
-                } else {
-                    nz = A ^ B;
-                    ng = (p.mode == MASK_DELTA) ? (~A & B) : 0u;
-                }
-            }
-        };
-        auto release_bar = [&](unsigned bar) {       // this warp has read its part of the accumulator columns `bar` stands for
+        auto release = [&]() {                       // TMEM fully read: the next unit's MMAs may start
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
-            if (lane == 0) { if (CG2) i8_mbar_arrive_remote(bar, 0); else i8_mbar_arrive(bar); }
-        };
-        auto release = [&]() {                       // TMEM fully read: the next unit's MMAs may start
-#ifdef GMS_I8_SPLITREL
-            release_bar(accemptyB);
-#endif
-            release_bar(accempty);
+            if (lane == 0) { if (CG2) i8_mbar_arrive_remote(accempty, 0); else i8_mbar_arrive(accempty); }
         };
         auto load4 = [&](int ch, int (&d)[I8_DIG][4]) {        // rows 4 ch .. 4 ch + 3 of this warp's half, all digit planes
 #pragma unroll
             for (int i = 0; i < I8_DIG; ++i) i8_tmem_ld4(tlane + i * I8_N + ch * 4, d[i]);
         };
         // FP64 FMAs have a long latency and a column Z[:, s] has only T accumulation chains: NP partial sums per trait (rows
-        // jr = k mod NP) keep >= 10 independent FMAs in flight per warp (measured: one chain per trait made the burst 3 x longer)
+        // jr = k mod NP) keep >= 10 independent FMAs in flight per warp (measured: one chain per trait made the burst 3 x longer,
+        // four per trait spill at T = 5)
 #ifndef GMS_I8_NP5
 #define GMS_I8_NP5 2
 #endif
-        constexpr int NP = TT <= 5 ? GMS_I8_NP5 : (TT <= 8 ? 2 : 1);
+#ifndef GMS_I8_NP8
+#define GMS_I8_NP8 2
+#endif
+        constexpr int NP = TT <= 5 ? GMS_I8_NP5 : (TT <= 8 ? GMS_I8_NP8 : 1);
         double zs[TT][NP];
+#pragma unroll
+        for (int t = 0; t < TT; ++t)
+#pragma unroll
+            for (int k = 0; k < NP; ++k) zs[t][k] = 0.0;
         // row data of unit u + 1 is fetched while unit u is processed: NPF values per thread of the (T + 1) x 64 block
         // [d_t[j] for T traits | scale_s[j]] plus the thread's four bit-plane words
         constexpr int NPF = (TT + 1 + 3) / 4;
@@ -561,253 +504,152 @@ __global__ void __launch_bounds__(I8_THREADS, 1) i8_contract_kernel(const I8Para
                 }
             }
         };
+        // ---- FP64 burst of one unit, the only FP64 instructions of the kernel: zs[t] += d_t[j] v_j for the unit's 32 rows, v_j as
+        // bit patterns in V[], d_t[j] from the unit's row buffer. `rows` == 0: no unit of this warp has a mask entry in the tile
+        // (a warp of padding units). Writes the finished column Z[:, s] out when the unit was the last tile of trait s.
+        long long V[I8_RPT];
+        auto fma_rows = [&](const double* erow, int jbeg, int jend) {       // rows [jbeg, jend) of the unit whose values are in V[]
+#pragma unroll
+            for (int j0 = jbeg; j0 < jend; j0 += 2) {
+                const double v0 = __longlong_as_double(V[j0]), v1 = __longlong_as_double(V[j0 + 1]);
+#pragma unroll
+                for (int t = 0; t < TT; ++t)
+                    if (t < T) {
+                        const double2 e = *reinterpret_cast<const double2*>(erow + t * 64 + j0);      // d_t of two rows
+                        zs[t][j0 % NP] = fma(e.x, v0, zs[t][j0 % NP]);
+                        zs[t][(j0 + 1) % NP] = fma(e.y, v1, zs[t][(j0 + 1) % NP]);
+                    }
+            }
+        };
+        auto finish_trait = [&](int s_) {                                   // the column Z[:, s_] is complete
+            if (live) {
+                // the two row halves of a cross go to two partial slabs (summed by finalize_sym)
+                double* out = p.Zpart + ((long long)(split * 2 + half) * p.n_units + unit) * (T * T);
+#pragma unroll
+                for (int t = 0; t < TT; ++t)
+                    if (t < T) {
+                        double z = zs[t][0];
+#pragma unroll
+                        for (int k = 1; k < NP; ++k) z += zs[t][k];
+                        out[t * T + s_] = z;
+                    }
+            }
+#pragma unroll
+            for (int t = 0; t < TT; ++t)
+#pragma unroll
+                for (int k = 0; k < NP; ++k) zs[t][k] = 0.0;
+        };
+        auto burst = [&](const double* erow, unsigned rows, bool last_of_trait, int s_) {
+            if (rows != 0u && !I8_DBG(64)) fma_rows(erow, 0, I8_RPT);
+            if (last_of_trait) finish_trait(s_);
+        };
         if (nunits > 0) pf_issue(0, 0);
         else if (live) {                     // a range without tiles (the host plan makes none): its slab still has to read as zero
             double* out = p.Zpart + ((long long)(split * 2 + half) * p.n_units + unit) * (T * T);
             for (int i = 0; i < T * T; ++i) out[i] = 0.0;
         }
+        // GMS_I8_LATE (default): the FP64 burst of unit u runs at the top of iteration u + 1, after `accfull` - the window in
+        // which the tensor pipe has nothing to do anyway (the MMAs of unit u + 1 are done, those of u + 2 wait for the drain):
+        // FP64 instructions next to running tcgen05 MMAs stall them (tools/tc_contention_probe.cu), here they cannot.
+        // Measured at cassava scale: 37.0 ms against 39.1 ms with the burst right after the conversion (-DGMS_I8_LATE=0).
+        // The row data of a unit then lives for two iterations: three row buffers. (Interleaving the burst with the drain loop,
+        // chunk by chunk in the same registers, was no faster: 37.5 ms - the drain loses its double-buffered TMEM loads.)
+#ifndef GMS_I8_LATE
+#define GMS_I8_LATE 1
+#endif
+        constexpr bool LATE = GMS_I8_LATE && TT <= 10;           // T > 10: V[] next to a long column Z[:, s] would spill
         int s = 0, jl = 0;                                       // unit u = (trait s, tile jt_begin + jl)
+        unsigned rows_prev = 0u;
+        bool last_prev = false;
+        int s_prev = 0;
         for (int u = 0; u < nunits; ++u) {
             const unsigned acc_it = (unsigned)u;
-            if (jl == 0) {
+            unsigned char* rb = rowbuf + (acc_it % 3u) * rowbuf_bytes;
+            double* erow_all = reinterpret_cast<double*>(rb);                 // d_t[j]: [t][64]
+            int* eb_all = reinterpret_cast<int*>(rb + T * 64 * 8);            // eb[j] of trait s: [64]
+            // commit the prefetched values of this unit ...
 #pragma unroll
-                for (int t = 0; t < TT; ++t)
-#pragma unroll
-                    for (int k = 0; k < NP; ++k) zs[t][k] = 0.0;
+            for (int k = 0; k < NPF; ++k) {
+                const int i = etid + k * (32 * I8_EPI_WARPS);
+                if (i < T * 64) erow_all[i] = pf[k];
+                else if (i < (T + 1) * 64)   // the row scale is a power of two >= 2^-900: its exponent field, biased for i8_cvt_bits
+                    eb_all[i & 63] = (__double2hiint(pf[k]) >> 20) + (63 - I8_FRAC - 1);
             }
-            {
-                unsigned char* rb = rowbuf + (acc_it & 1) * rowbuf_bytes;
-                double* erow_all = reinterpret_cast<double*>(rb);                 // d_t[j]: [t][64]
-                int* eb_all = reinterpret_cast<int*>(rb + T * 64 * 8);            // eb[j] of trait s: [64]
-                // commit the prefetched values of this unit ...
-#pragma unroll
-                for (int k = 0; k < NPF; ++k) {
-                    const int i = etid + k * (32 * I8_EPI_WARPS);
-                    if (i < T * 64) erow_all[i] = pf[k];
-                    else if (i < (T + 1) * 64)   // the row scale is a power of two >= 2^-900: its exponent field, biased for i8_cvt_bits
-                        eb_all[i & 63] = (__double2hiint(pf[k]) >> 20) + (63 - I8_FRAC - 1);
-                }
-                // this thread's mask entries of the tile's rows (one word of the bit-planes): nz = non-zero, ng = negative
-                unsigned nz = 0u, ng = 0u;
-                if (live) {
-                    if (p.mode == MASK_XI) {
-                        nz = (pm[0] ^ pm[1]) & (pm[2] ^ pm[3]);
-                        ng = ((~pm[0] & pm[1]) ^ (~pm[2] & pm[3])) & nz;
-                    } else {
-                        nz = pm[0] ^ pm[1];
-                        ng = (p.mode == MASK_DELTA) ? (~pm[0] & pm[1]) : 0u;
-                    }
-                }
-                // ... and start the loads of the next one
-                int s_n = s, jl_n = jl + 1;
-                if (jl_n == ntl) { jl_n = 0; ++s_n; }
-                if (u + 1 < nunits) pf_issue(s_n, jl_n);
-#ifdef GMS_I8_DENSE_EPI
-                const unsigned rows = __reduce_or_sync(0xffffffffu, nz);       // warp-uniform: rows some unit of the warp needs
-#endif
-                asm volatile("bar.sync 1, %0;" ::"n"(32 * I8_EPI_WARPS) : "memory");
-                const double* erow = erow_all + half * I8_RPT;       // erow[t * 64 + jr]
-                const int* ebrow = eb_all + half * I8_RPT;            // ebrow[jr]
-                i8_mbar_wait(accfull, acc_it & 1u);
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                if (I8_DBG(1)) {
-                    release();
+            // this thread's mask entries of the tile's rows (one word of the bit-planes): nz = non-zero, ng = negative
+            unsigned nz = 0u, ng = 0u;
+            if (live) {
+                if (p.mode == MASK_XI) {
+                    nz = (pm[0] ^ pm[1]) & (pm[2] ^ pm[3]);
+                    ng = ((~pm[0] & pm[1]) ^ (~pm[2] & pm[3])) & nz;
                 } else {
-                    // ---- drain: TMEM -> 32 exact row sums in registers; loads of chunk c + 1 in flight while chunk c is recombined.
-                    // TMEM reads run at ~64 B per cycle and SM sub-partition: ~900 cycles for the 448 columns of a unit, the one
-                    // part of the epilogue no MMA can overlap with while a unit's accumulator fills TMEM
-                    long long W[I8_RPT];
-#ifdef GMS_I8_SPLITREL
-                    // the columns of the first MMA (digits 0-3) of all 32 rows first: once they are read the next unit's first MMAs
-                    // may run, while this warp reads the remaining digits
-                    constexpr int NCH = I8_RPT / 4;          // 8 chunks of 4 rows
-                    {
-                        int dA[4][4], dB[4][4];
-                        auto ld = [&](int ch, int (&d)[4][4]) {
-#pragma unroll
-                            for (int i = 0; i < 4; ++i) i8_tmem_ld4(tlane + i * I8_N + ch * 4, d[i]);
-                        };
-                        auto cb = [&](int ch, const int (&d)[4][4]) {
-#pragma unroll
-                            for (int q = 0; q < 4; ++q) W[ch * 4 + q] = i8_combine_hi(d[0][q], d[1][q], d[2][q], d[3][q]);
-                        };
-                        ld(0, dA);
-                        i8_tmem_wait16(dA);
-#pragma unroll
-                        for (int cp = 0; cp < NCH / 2; ++cp) {
-                            ld(2 * cp + 1, dB);
-                            cb(2 * cp, dA);
-                            i8_tmem_wait16(dB);
-                            if (cp + 1 < NCH / 2) ld(2 * cp + 2, dA);
-                            cb(2 * cp + 1, dB);
-                            if (cp + 1 < NCH / 2) i8_tmem_wait16(dA);
-                        }
-                    }
-                    release_bar(accempty);
-                    {
-                        constexpr int NR = I8_DIG - 4;
-                        int dA[NR][4], dB[NR][4];
-                        auto ld = [&](int ch, int (&d)[NR][4]) {
-#pragma unroll
-                            for (int i = 0; i < NR; ++i) i8_tmem_ld4(tlane + (4 + i) * I8_N + ch * 4, d[i]);
-                        };
-                        auto cb = [&](int ch, const int (&d)[NR][4]) {
-#pragma unroll
-                            for (int q = 0; q < 4; ++q) {
-                                int sv[NR];
-#pragma unroll
-                                for (int i = 0; i < NR; ++i) sv[i] = d[i][q];
-                                W[ch * 4 + q] = (long long)((unsigned long long)W[ch * 4 + q] + (unsigned long long)i8_combine_lo(sv));
-                            }
-                        };
-                        ld(0, dA);
-                        i8_tmem_wait_rest(dA);
-#pragma unroll
-                        for (int cp = 0; cp < NCH / 2; ++cp) {
-                            ld(2 * cp + 1, dB);
-                            cb(2 * cp, dA);
-                            i8_tmem_wait_rest(dB);
-                            if (cp + 1 < NCH / 2) ld(2 * cp + 2, dA);
-                            cb(2 * cp + 1, dB);
-                            if (cp + 1 < NCH / 2) i8_tmem_wait_rest(dA);
-                        }
-                    }
-                    release_bar(accemptyB);
-#else
-                    {
-                        int dA[I8_DIG][4], dB[I8_DIG][4];
-                        auto comb4 = [&](int ch, const int (&d)[I8_DIG][4]) {
-#pragma unroll
-                            for (int q = 0; q < 4; ++q) {
-                                int sv[I8_DIG];
-#pragma unroll
-                                for (int i = 0; i < I8_DIG; ++i) sv[i] = d[i][q];
-                                W[ch * 4 + q] = i8_combine(sv);
-                            }
-                        };
-                        constexpr int NCH = I8_RPT / 4;          // 8 chunks of 4 rows
-                        load4(0, dA);
-                        i8_tmem_wait(dA);
-#pragma unroll
-                        for (int cp = 0; cp < NCH / 2; ++cp) {
-                            load4(2 * cp + 1, dB);
-                            comb4(2 * cp, dA);
-                            i8_tmem_wait(dB);
-                            if (cp + 1 < NCH / 2) load4(2 * cp + 2, dA);
-                            comb4(2 * cp + 1, dB);
-                            if (cp + 1 < NCH / 2) i8_tmem_wait(dA);
-                        }
-                    }
-                    release();
-#endif
-                    if (!I8_DBG(32)) {
-#ifndef GMS_I8_DENSE_EPI
-                        // ---- COMPACTION. A mask entry is non-zero on ~13 % of a cross's rows, but which rows differs from lane to
-                        // lane, so a row-by-row loop runs all 32 rows for every lane. Instead each thread packs ITS non-zero rows
-                        // (row sum + row number) into a private column of shared memory, RS rows at a time, and the warp loops to the
-                        // LARGEST count of its lanes: ~6 of 16 slots for a per-cross mask, i.e. a third of the FP64 instructions, which
-                        // is what counts - every FP64 instruction stalls the SM's tcgen05 MMAs. Within a round
-                        // the rows of a warp's gathers lie in one 16-row window of d_t[.]: no shared-memory bank conflicts.
-                        constexpr int RS = TT <= 8 ? 16 : 8;          // rows per round (the round's values live in registers)
-#pragma unroll
-                        for (int r0 = 0; r0 < I8_RPT; r0 += RS) {
-                            int cnt = 0;
-#pragma unroll
-                            for (int r = 0; r < RS; ++r) {           // slot cnt is overwritten until a row with a mask entry takes it
-                                cw[cnt * (32 * I8_EPI_WARPS) + etid] = W[r0 + r];
-                                cj[cnt * (32 * I8_EPI_WARPS) + etid] = (unsigned char)r;
-                                cnt += (int)((nz >> (r0 + r)) & 1u);
-                            }
-                            const int kmax = __reduce_max_sync(0xffffffffu, cnt);      // warp-uniform trip count
-                            // convert (integer instructions only; overlaps the MMAs for free): bit pattern of
-                            // v = xi_x[j] W[j] 2^(E_j - I8_FRAC) for the thread's k-th non-zero row j (0 beyond its own count)
-                            long long vv[RS];
-                            int jj[RS];
-#pragma unroll
-                            for (int k = 0; k < RS; ++k) { vv[k] = 0; jj[k] = r0; }
-#pragma unroll
-                            for (int k0 = 0; k0 < RS; k0 += 2) {      // slots in pairs: two independent dependency chains per branch
-                                if (k0 < kmax) {
-#pragma unroll
-                                    for (int k = k0; k < k0 + 2; ++k) {
-                                        const long long w = cw[k * (32 * I8_EPI_WARPS) + etid];
-                                        const int j = r0 + (int)(cj[k * (32 * I8_EPI_WARPS) + etid] & (RS - 1));
-                                        unsigned bh, bl;
-                                        i8_cvt_bits(w, ebrow[j], k < cnt ? 1u : 0u, (ng >> j) & 1u, bh, bl);
-                                        vv[k] = (long long)(((unsigned long long)bh << 32) | bl);
-                                        jj[k] = j;
-                                    }
-                                }
-                            }
-                            // Every conversion is complete before the first FP64 instruction, and the FP64 instructions form one dense
-                            // burst per round: next to running tcgen05 MMAs FMAs scattered over integer code cost the tensor pipe ~4-5
-                            // cycles per warp instruction (tools/tc_contention_probe.cu). The empty asm pins the values for the compiler.
-#pragma unroll
-                            for (int k = 0; k < RS; ++k) asm volatile("" : "+l"(vv[k]), "+r"(jj[k]));
-                            // ---- FP64 burst, the only FP64 instructions of the kernel: zs[t] += d_t[j] v
-                            if (!I8_DBG(64)) {
-#pragma unroll
-                                for (int k0 = 0; k0 < RS; k0 += 2) {
-                                    if (k0 < kmax) {
-                                        const double v0 = __longlong_as_double(vv[k0]), v1 = __longlong_as_double(vv[k0 + 1]);
-                                        const double* e0 = erow + jj[k0];
-                                        const double* e1 = erow + jj[k0 + 1];
-#pragma unroll
-                                        for (int t = 0; t < TT; ++t)
-                                            if (t < T) {
-                                                zs[t][k0 % NP] = fma(e0[t * 64], v0, zs[t][k0 % NP]);
-                                                zs[t][(k0 + 1) % NP] = fma(e1[t * 64], v1, zs[t][(k0 + 1) % NP]);
-                                            }
-                                    }
-                                }
-                            }
-                        }
-#else
-                        // ---- every row (tools only, for A/B timing): convert all 32 rows, then one dense FP64 burst over all of them
-#pragma unroll
-                        for (int jr = 0; jr < I8_RPT; ++jr) {
-                            unsigned bh, bl;
-                            i8_cvt_bits(W[jr], ebrow[jr], (nz >> jr) & 1u, (ng >> jr) & 1u, bh, bl);
-                            W[jr] = (long long)(((unsigned long long)bh << 32) | bl);
-                        }
-#pragma unroll
-                        for (int jr = 0; jr < I8_RPT; ++jr) asm volatile("" : "+l"(W[jr]));
-                        if (rows != 0u && !I8_DBG(64)) {
-#pragma unroll
-                            for (int j0 = 0; j0 < I8_RPT; j0 += 2) {
-                                const double v0 = __longlong_as_double(W[j0]), v1 = __longlong_as_double(W[j0 + 1]);
-#pragma unroll
-                                for (int t = 0; t < TT; ++t)
-                                    if (t < T) {
-                                        const double2 e = *reinterpret_cast<const double2*>(erow + t * 64 + j0);      // d_t of two rows
-                                        zs[t][j0 % NP] = fma(e.x, v0, zs[t][j0 % NP]);
-                                        zs[t][(j0 + 1) % NP] = fma(e.y, v1, zs[t][(j0 + 1) % NP]);
-                                    }
-                            }
-                        }
-#endif
-                    }
+                    nz = pm[0] ^ pm[1];
+                    ng = (p.mode == MASK_DELTA) ? (~pm[0] & pm[1]) : 0u;
                 }
             }
-            if (jl + 1 == ntl) {
-                if (live) {
-                    // the two row halves of a cross go to two partial slabs (summed by finalize_sym)
-                    double* out = p.Zpart + ((long long)(split * 2 + half) * p.n_units + unit) * (T * T);
-#pragma unroll
-                    for (int t = 0; t < TT; ++t)
-                        if (t < T) {
-                            double z = zs[t][0];
-#pragma unroll
-                            for (int k = 1; k < NP; ++k) z += zs[t][k];
-                            out[t * T + s] = z;
-                        }
-                }
-                jl = 0;
-                ++s;
+            // ... and start the loads of the next one
+            int s_n = s, jl_n = jl + 1;
+            if (jl_n == ntl) { jl_n = 0; ++s_n; }
+            if (u + 1 < nunits) pf_issue(s_n, jl_n);
+            const unsigned rows = __reduce_or_sync(0xffffffffu, nz);       // warp-uniform: rows some unit of the warp needs
+            asm volatile("bar.sync 1, %0;" ::"n"(32 * I8_EPI_WARPS) : "memory");
+            const double* erow = erow_all + half * I8_RPT;       // erow[t * 64 + jr]
+            const int* ebrow = eb_all + half * I8_RPT;            // ebrow[jr]
+            i8_mbar_wait(accfull, acc_it & 1u);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const double* erow_prev = reinterpret_cast<const double*>(rowbuf + ((acc_it + 2u) % 3u) * rowbuf_bytes) + half * I8_RPT;
+            if (LATE && u > 0 && !I8_DBG(1 | 32)) burst(erow_prev, rows_prev, last_prev, s_prev);
+            if (I8_DBG(1)) {
+                release();
             } else {
-                ++jl;
+                // ---- drain: TMEM -> 32 exact row sums in registers; loads of chunk c + 1 in flight while chunk c is recombined.
+                // The one part of the epilogue no MMA can overlap with while a unit's accumulator fills TMEM
+                {
+                    int dA[I8_DIG][4], dB[I8_DIG][4];
+                    auto comb4 = [&](int ch, const int (&d)[I8_DIG][4]) {
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            int sv[I8_DIG];
+#pragma unroll
+                            for (int i = 0; i < I8_DIG; ++i) sv[i] = d[i][q];
+                            V[ch * 4 + q] = i8_combine(sv);
+                        }
+                    };
+                    constexpr int NCH = I8_RPT / 4;          // 8 chunks of 4 rows
+                    load4(0, dA);
+                    i8_tmem_wait(dA);
+#pragma unroll
+                    for (int cp = 0; cp < NCH / 2; ++cp) {
+                        load4(2 * cp + 1, dB);
+                        comb4(2 * cp, dA);
+                        i8_tmem_wait(dB);
+                        if (cp + 1 < NCH / 2) load4(2 * cp + 2, dA);
+                        comb4(2 * cp + 1, dB);
+                        if (cp + 1 < NCH / 2) i8_tmem_wait(dA);
+                    }
+                }
+                release();
+                if (!I8_DBG(32)) {
+                    // ---- convert (integer instructions only: overlaps the next unit's MMAs for free):
+                    // V[j] <- bit pattern of v_j = xi_x[j] W[j] 2^(E_j - I8_FRAC)
+#pragma unroll
+                    for (int jr = 0; jr < I8_RPT; ++jr) {
+                        unsigned bh, bl;
+                        i8_cvt_bits(V[jr], ebrow[jr], (nz >> jr) & 1u, (ng >> jr) & 1u, bh, bl);
+                        V[jr] = (long long)(((unsigned long long)bh << 32) | bl);
+                    }
+                    // Every conversion is complete before the first FP64 instruction, and the FP64 instructions form ONE dense
+                    // burst per unit: FMAs scattered over integer code cost the tensor pipe ~4-5 cycles per warp instruction.
+                    // The empty asm pins the values for the compiler.
+#pragma unroll
+                    for (int jr = 0; jr < I8_RPT; ++jr) asm volatile("" : "+l"(V[jr]));
+                    if (!LATE) burst(erow, rows, jl + 1 == ntl, s);
+                }
             }
+            rows_prev = rows; last_prev = (jl + 1 == ntl); s_prev = s;
+            if (jl + 1 == ntl) { jl = 0; ++s; } else ++jl;
         }
+        if (LATE && nunits > 0 && !I8_DBG(1 | 32))
+            burst(reinterpret_cast<const double*>(rowbuf + ((unsigned)(nunits - 1) % 3u) * rowbuf_bytes) + half * I8_RPT, rows_prev, last_prev, s_prev);
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
@@ -824,7 +666,7 @@ int i8_max_tiles_per_split() { return I8_TTAB; }
 long long i8_block_bytes() { return I8_B_ALL; }            // digit image of one (64 x 64 block, trait)
 static size_t i8_fixed_smem(int T) {
     const size_t rowbuf = (size_t)T * 64 * 8 + 64 * 4;          // per buffer (see the epilogue)
-    return (2 * I8_MAX_STAGES + 4) * 8 + (size_t)I8_TTAB * 16 + 2 * rowbuf + (size_t)I8_CSLOTS * 32 * I8_EPI_WARPS * 9;
+    return (2 * I8_MAX_STAGES + 4) * 8 + (size_t)I8_TTAB * 16 + 3 * rowbuf;          // three row buffers: see GMS_I8_LATE
 }
 // pipeline stages: as many as fit in the 227 KiB a CTA may use (the kernel is bound by the latency of its operand stream)
 int i8_stages(int T, bool cg2) {
@@ -895,6 +737,8 @@ cudaError_t launch_i8_contract(const I8Params& p, int ntiles, int nsplit, bool p
         case 6: GMS_I8(6, true) break;
         case 7: GMS_I8(7, true) break;
         case 8: GMS_I8(8, true) break;
+        case 9: GMS_I8(9, true) break;
+        case 10: GMS_I8(10, true) break;
         default:
             if (p.T <= 12) GMS_I8(12, false)
             else if (p.T <= 16) GMS_I8(16, false)

@@ -2,10 +2,10 @@
 // (parent or cross), evaluated on the device right after each table, and a list of the units that fail it. The
 // failing units are re-evaluated by the FP64 contraction (contract.cu) in the same stream; see api.cu.
 //
-// Why a bound is needed. The int8 path rounds G_s[j,k] = L'[j,k] e_s[k] to 47 fractional bits RELATIVE TO THE ROW SCALE
-// scale_s[j] = 2^E >= max_k |G_s[j,k]| / 0.996 (i8path.cu, i8digits.cuh). That is fixed point, not floating point: a SNP with
+// Why a bound is needed. The int8 path rounds G_s[j,k] = L'[j,k] e_s[k] to I8_FRAC = 49 fractional bits RELATIVE TO THE ROW
+// SCALE scale_s[j] = 2^E >= max_k |G_s[j,k]| (i8path.cu, i8digits.cuh; 47 bits in the six-plane build variant). That is fixed point, not floating point: a SNP with
 // a huge effect sets the scale of every row it reaches, and a unit in which that SNP does not segregate (mask 0) sums only
-// small terms that each carry the absolute error u * scale_s[j], u = I8_U = 2^-48 (1 + 2^-4): 2^-48 from rounding to
+// small terms that each carry the absolute error u * scale_s[j], u = I8_U = 2^-50 + 2^-52: 2^-50 from rounding to
 // nearest (i8_scale_kernel picks E so that no digit ever saturates) plus the 53-bit truncation of a row sum in the epilogue.
 // For unit x with mask mu in {-1,0,1}^m, row j sums over the non-zero mask entries k in the 64-blocks its row tile owns
 // (about half of the chromosome's, common.cuh), at most n_c(x) = the unit's non-zero entries on the chromosome, so
