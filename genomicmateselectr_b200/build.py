@@ -32,7 +32,8 @@ def build_variant(name, defines):
     """Another build of the same library for tools/ (never the product): lib/<name>/libgms_b200.so, loaded through GMS_B200_LIB.
     -DGMS_PROFILE compiles the profiling switches of csrc/i8path.cu in (GMS_I8_DEBUG then turns the MMAs, the copies or the
     epilogue arithmetic off - results are garbage); -DGMS_I8_DIG=6 selects six digit planes (default seven), -DGMS_I8_LATE=0 the FP64 burst right after the conversion,
-    -DGMS_I8_TRIANGLE the lower block triangle instead of the even deal of 64-blocks."""
+    -DGMS_I8_TRIANGLE the lower block triangle instead of the even deal of 64-blocks, -DGMS_I8_TRAIT_OUTER the unit order trait > tile
+    instead of chromosome > trait > tile."""
     out = os.path.join(LIBDIR, name)
     os.makedirs(out, exist_ok=True)
     lib = os.path.join(out, "libgms_b200.so")
@@ -63,6 +64,7 @@ if __name__ == "__main__":
     if "--variants" in sys.argv:
         print(build_variant("profile", ["-DGMS_PROFILE"]))
         print(build_variant("dig6", ["-DGMS_I8_DIG=6"]))
+        print(build_variant("traitouter", ["-DGMS_I8_TRAIT_OUTER"]))
         if "--all" in sys.argv:
             print(build_variant("early", ["-DGMS_I8_LATE=0"]))
         if "--all" in sys.argv:

@@ -318,10 +318,31 @@ __global__ void __launch_bounds__(I8_THREADS, 1) i8_contract_kernel(const I8Para
         const long long gblk = p.gbase[t.c] / I8_B_ALL + i8_blocks_before(nb, t.I) * p.T;      // < 2^31 (checked by the host plan)
         ttab[i] = make_int4(t.I | (i8_nassign(nb, t.I) << 16), cd.pad_off + 64 * t.I, (int)gblk, nb);
     }
-    // every role walks the units (64-row tile, trait) in the same order: f(tile entry, s)
+    // every role walks the units (64-row tile, trait) in the same order: f(tile entry, s). GROUP-OUTER: the CTA's tile range is
+    // cut into groups = runs of tiles of one chromosome (a tile with J == 0 opens a group; the list is ordered by (c, J)), and
+    // the order is group, trait, tile. All T passes over a chromosome then re-read the same xi k-blocks (128 crosses x m_c bytes
+    // per CTA: 35 MB over the 148 resident CTAs at cassava scale) and the chromosome's digit images from L2. With the trait
+    // outermost (every trait pass walks the CTA's whole range, 218 MB of xi over the resident CTAs) ncu counted 14.0 GB of
+    // DRAM reads per launch against 2.9 GB of operand images.
+    // -DGMS_I8_TRAIT_OUTER (tools only, for A/B timing): one group = the whole range, i.e. trait, tile.
+    auto group_end = [&](int g0, int n) {
+#ifdef GMS_I8_TRAIT_OUTER
+        (void)g0;
+        return n;
+#else
+        int g1 = g0 + 1;
+        while (g1 < n && (ttab[g1].x & 0xFFFF) != 0) ++g1;
+        return g1;
+#endif
+    };
     auto for_units = [&](auto f) {
-        for (int s = 0; s < T; ++s)
-            for (int jt = jt_begin; jt < jt_end; ++jt) f(ttab[jt - jt_begin], s);
+        const int n = jt_end - jt_begin;
+        for (int g0 = 0; g0 < n;) {
+            const int g1 = group_end(g0, n);
+            for (int s = 0; s < T; ++s)
+                for (int jt = g0; jt < g1; ++jt) f(ttab[jt], s);
+            g0 = g1;
+        }
     };
 
     if (threadIdx.x == 0) {
@@ -521,17 +542,20 @@ __global__ void __launch_bounds__(I8_THREADS, 1) i8_contract_kernel(const I8Para
                     }
             }
         };
-        auto finish_trait = [&](int s_) {                                   // the column Z[:, s_] is complete
+        // the two row halves of a cross go to two partial slabs (summed by finalize_sym); a slab entry belongs to this thread
+        // alone, so the groups after the first add to it with a plain read-modify-write, in a fixed order
+        double* const zout = p.Zpart + ((long long)(split * 2 + half) * p.n_units + unit) * (T * T);
+        constexpr int NPRE = TT <= 5 ? TT : 1;       // T <= 5: the old slab values are loaded before the FMAs of the burst (registers to spare)
+        auto finish_trait = [&](int s_, bool first_group, const double (&zold)[NPRE]) {      // the column Z[:, s_] of one group of tiles is complete
             if (live) {
-                // the two row halves of a cross go to two partial slabs (summed by finalize_sym)
-                double* out = p.Zpart + ((long long)(split * 2 + half) * p.n_units + unit) * (T * T);
 #pragma unroll
                 for (int t = 0; t < TT; ++t)
                     if (t < T) {
                         double z = zs[t][0];
 #pragma unroll
                         for (int k = 1; k < NP; ++k) z += zs[t][k];
-                        out[t * T + s_] = z;
+                        if (NPRE == TT) zout[t * T + s_] = zold[t < NPRE ? t : 0] + z;
+                        else zout[t * T + s_] = first_group ? z : zout[t * T + s_] + z;
                     }
             }
 #pragma unroll
@@ -539,14 +563,16 @@ __global__ void __launch_bounds__(I8_THREADS, 1) i8_contract_kernel(const I8Para
 #pragma unroll
                 for (int k = 0; k < NP; ++k) zs[t][k] = 0.0;
         };
-        auto burst = [&](const double* erow, unsigned rows, bool last_of_trait, int s_) {
+        auto burst = [&](const double* erow, unsigned rows, int last_of_trait, int s_) {       // last_of_trait: 0 no, 1 yes, 2 yes + first group
+            double zold[NPRE];                       // what the slab holds from the earlier groups: loaded before the FMAs, used after
+#pragma unroll
+            for (int t = 0; t < NPRE; ++t) zold[t] = (NPRE == TT && last_of_trait == 1 && live && t < T) ? zout[t * T + s_] : 0.0;
             if (rows != 0u && !I8_DBG(64)) fma_rows(erow, 0, I8_RPT);
-            if (last_of_trait) finish_trait(s_);
+            if (last_of_trait) finish_trait(s_, last_of_trait == 2, zold);
         };
         if (nunits > 0) pf_issue(0, 0);
         else if (live) {                     // a range without tiles (the host plan makes none): its slab still has to read as zero
-            double* out = p.Zpart + ((long long)(split * 2 + half) * p.n_units + unit) * (T * T);
-            for (int i = 0; i < T * T; ++i) out[i] = 0.0;
+            for (int i = 0; i < T * T; ++i) zout[i] = 0.0;
         }
         // GMS_I8_LATE (default): the FP64 burst of unit u runs at the top of iteration u + 1, after `accfull` - the window in
         // which the tensor pipe has nothing to do anyway (the MMAs of unit u + 1 are done, those of u + 2 wait for the drain):
@@ -558,9 +584,10 @@ __global__ void __launch_bounds__(I8_THREADS, 1) i8_contract_kernel(const I8Para
 #define GMS_I8_LATE 1
 #endif
         constexpr bool LATE = GMS_I8_LATE && TT <= 10;           // T > 10: V[] next to a long column Z[:, s] would spill
-        int s = 0, jl = 0;                                       // unit u = (trait s, tile jt_begin + jl)
+        int s = 0, jl = 0;                                       // unit u = (trait s, tile jt_begin + jl), jl in the group [g0, g1)
+        int g0 = 0, g1 = ntl > 0 ? group_end(0, ntl) : 0;
         unsigned rows_prev = 0u;
-        bool last_prev = false;
+        int last_prev = 0;
         int s_prev = 0;
         for (int u = 0; u < nunits; ++u) {
             const unsigned acc_it = (unsigned)u;
@@ -586,9 +613,13 @@ __global__ void __launch_bounds__(I8_THREADS, 1) i8_contract_kernel(const I8Para
                     ng = (p.mode == MASK_DELTA) ? (~pm[0] & pm[1]) : 0u;
                 }
             }
-            // ... and start the loads of the next one
-            int s_n = s, jl_n = jl + 1;
-            if (jl_n == ntl) { jl_n = 0; ++s_n; }
+            // ... and start the loads of the next one (for_units order: group, trait, tile)
+            int s_n = s, jl_n = jl + 1, g0_n = g0, g1_n = g1;
+            if (jl_n == g1) {
+                if (++s_n == T) { s_n = 0; g0_n = g1; g1_n = g1 < ntl ? group_end(g1, ntl) : g1; }
+                jl_n = g0_n;
+            }
+            const int last_now = (jl + 1 == g1) ? (g0 == 0 ? 2 : 1) : 0;       // this unit ends the pass of trait s over the group
             if (u + 1 < nunits) pf_issue(s_n, jl_n);
             const unsigned rows = __reduce_or_sync(0xffffffffu, nz);       // warp-uniform: rows some unit of the warp needs
             asm volatile("bar.sync 1, %0;" ::"n"(32 * I8_EPI_WARPS) : "memory");
@@ -642,11 +673,11 @@ __global__ void __launch_bounds__(I8_THREADS, 1) i8_contract_kernel(const I8Para
                     // The empty asm pins the values for the compiler.
 #pragma unroll
                     for (int jr = 0; jr < I8_RPT; ++jr) asm volatile("" : "+l"(V[jr]));
-                    if (!LATE) burst(erow, rows, jl + 1 == ntl, s);
+                    if (!LATE) burst(erow, rows, last_now, s);
                 }
             }
-            rows_prev = rows; last_prev = (jl + 1 == ntl); s_prev = s;
-            if (jl + 1 == ntl) { jl = 0; ++s; } else ++jl;
+            rows_prev = rows; last_prev = last_now; s_prev = s;
+            s = s_n; jl = jl_n; g0 = g0_n; g1 = g1_n;
         }
         if (LATE && nunits > 0 && !I8_DBG(1 | 32))
             burst(reinterpret_cast<const double*>(rowbuf + ((unsigned)(nunits - 1) % 3u) * rowbuf_bytes) + half * I8_RPT, rows_prev, last_prev, s_prev);
