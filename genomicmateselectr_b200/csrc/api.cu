@@ -131,7 +131,6 @@ struct gms_handle {
     bool use_i8 = false;
     bool i8_pair = true;               // tcgen05 cta_group::2: CTA pairs form one M = 256 tile (GMS_I8_CG2=0: one CTA per 128 crosses)
     bool i8_sort = true;               // per-cross passes run in sire order (GMS_I8_SORT=0: list order), so that the crosses of a warp share a parent
-    bool i8_skip = true;               // ... and the epilogue skips the rows where none of a warp's crosses has a mask entry (GMS_I8_SKIP=0)
     bool xi_image_valid = false;       // the per-cross xi image in xi_d belongs to the staged cross list (single pass only)
     double tau = 0x1p-31;              // int8 error-bound tolerance (gms_set_int8_tolerance); <= 0: no verification
     int fb_cap = 0;
@@ -379,7 +378,7 @@ int run_scan(gms_handle* h, const double* S, int mode, const int* ua, const int*
 
 // int8 tcgen05 contraction of `n_units` units (their xi image in `xi`) into table rows
 int run_i8(gms_handle* h, const EffClass& cl, const signed char* xi, int mode, const int* ua, const int* ub, long long n_units,
-           const Plan& pl, const int* split_d, double* Xout, const int* row_index, bool skip, cudaEvent_t e0 = nullptr,
+           const Plan& pl, const int* split_d, double* Xout, const int* row_index, cudaEvent_t e0 = nullptr,
            cudaEvent_t e1 = nullptr) {
     if (n_units == 0) return GMS_OK;
     I8Params ip{};
@@ -391,7 +390,7 @@ int run_i8(gms_handle* h, const EffClass& cl, const signed char* xi, int mode, c
     ip.Zpart = h->Z.p;
     ip.debug = h->i8_debug;
     if (e0) CU(cudaEventRecord(e0, h->stream));
-    CU(launch_i8_contract(ip, pl.ntiles, pl.nsplit, h->i8_pair, skip, h->stream));
+    CU(launch_i8_contract(ip, pl.ntiles, pl.nsplit, h->i8_pair, h->stream));
     if (e1) CU(cudaEventRecord(e1, h->stream));
     CU(launch_finalize_sym(h->Z.p, i8_npart(h->T) * pl.nsplit, n_units, h->T, Xout, h->stream, true, row_index));
     h->st.last_launches += 2;
@@ -796,7 +795,7 @@ int compute_parents_impl(gms_handle* h) {
             for (int k = 0; k < ncls; ++k) {
                 const EffClass& cl = h->cls[k];
                 if (int rc = run_i8(h, cl, k == 1 ? h->xi_het_d.p : h->xi_delta_d.p, class_mask(k), units, nullptr, nun, h->plan_i8_par,
-                                    h->split_i8_par_d.p, h->cls[k].table.p, units, false)) return rc;
+                                    h->split_i8_par_d.p, h->cls[k].table.p, units)) return rc;
                 if (int rc = verify_and_repair(h, cl, class_tiles(h, k), class_mask(k), units, nullptr, nun, h->cls[k].table.p, true, k)) return rc;
             }
         } else {
@@ -855,7 +854,7 @@ int compute_crosses_impl(gms_handle* h, int sync) {
                 double* Xp = h->X.p + off * (long long)TT;
                 if (int rc = run_i8(h, dm, h->xi_d.p, MASK_XI, ua + off, ub + off, n,
                                     tail ? h->plan_i8_tail : h->plan_i8, tail ? h->split_i8_tail_d.p : h->split_i8_d.p, Xp,
-                                    h->i8_sort ? h->perm_d.p + off : nullptr, h->i8_skip,
+                                    h->i8_sort ? h->perm_d.p + off : nullptr,
                                     one_pass ? h->ev[4] : nullptr, one_pass ? h->ev[5] : nullptr)) return rc;
                 if (int rc = verify_and_repair(h, dm, h->R2.p, MASK_XI, h->sire_d.p + off, h->dam_d.p + off, n, Xp, false, 3 + pass)) return rc;
             }
@@ -995,8 +994,7 @@ int gms_create(gms_handle** out, int device) {
     }
     nh->stream = nh->own_stream;
     if (const char* ev = getenv("GMS_I8_CG2")) nh->i8_pair = atoi(ev) != 0;      // test hook: one CTA per 128 crosses
-    if (const char* ev = getenv("GMS_I8_SORT")) nh->i8_sort = atoi(ev) != 0;     // test hooks: list order / every row in the epilogue
-    if (const char* ev = getenv("GMS_I8_SKIP")) nh->i8_skip = atoi(ev) != 0;
+    if (const char* ev = getenv("GMS_I8_SORT")) nh->i8_sort = atoi(ev) != 0;     // test hook: list order
 #ifdef GMS_PROFILE
     if (const char* ev = getenv("GMS_I8_DEBUG")) nh->i8_debug = atoi(ev);        // profiling builds only: results are garbage
 #endif

@@ -734,12 +734,11 @@ cudaError_t launch_i8_build_digits(const double* tiles, const ChromDesc* chrom_d
     return cudaGetLastError();
 }
 
-cudaError_t launch_i8_contract(const I8Params& p, int ntiles, int nsplit, bool pair, bool skip, cudaStream_t st) {
+cudaError_t launch_i8_contract(const I8Params& p, int ntiles, int nsplit, bool pair, cudaStream_t st) {
     if (ntiles == 0) return cudaSuccess;
     const size_t smem = i8_smem_bytes(p.T, pair);
     I8Params pp = p;
     pp.stages = i8_stages(p.T, pair);
-    pp.skip = skip ? 1 : 0;
     cudaError_t e = cudaSuccess;
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(pair ? (ntiles + 1) / 2 * 2 : ntiles, nsplit, 1);

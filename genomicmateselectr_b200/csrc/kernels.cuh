@@ -73,7 +73,6 @@ struct I8Params {
     int mode;
     double* Zpart;               // [nsplit][n_units][T*T]
     int stages;                  // pipeline depth (set by launch_i8_contract)
-    int skip;                    // the epilogue skips rows no unit of a warp needs (set by launch_i8_contract)
     int debug;                   // -DGMS_PROFILE builds only (GMS_I8_DEBUG bit mask; results are garbage): 1 no epilogue arithmetic, 2 no MMAs
 };
 size_t i8_smem_bytes(int T, bool cg2);
@@ -84,8 +83,7 @@ cudaError_t launch_i8_build_digits(const double* tiles, const ChromDesc* chrom_d
                                    const int* blkpref_d, int nblks, const double* emat, long long mp_total, int T,
                                    double* scale, double* smax, const long long* gbase_d, signed char* G, int layout,
                                    cudaStream_t st);     // layout: 0 / 1 = plain / cta_group::2; smax[T][C]: see verify.cu
-// skip: the epilogue visits only rows where some cross of a warp has a non-zero mask entry (pays when the units of a warp share a parent)
-cudaError_t launch_i8_contract(const I8Params& p, int ntiles, int nsplit, bool pair, bool skip, cudaStream_t st);
+cudaError_t launch_i8_contract(const I8Params& p, int ntiles, int nsplit, bool pair, cudaStream_t st);
 long long i8_block_bytes();         // bytes of the digit image of one (64 x 64 block, trait)
 int i8_npart(int T);        // partial slabs per split written by launch_i8_contract
 int i8_max_tiles_per_split();       // the plan must cut the 64-row tile list into splits no longer than this

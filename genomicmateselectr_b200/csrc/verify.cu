@@ -54,8 +54,14 @@ __global__ void i8_smax_kernel(const double* __restrict__ rowmax, const ChromDes
 // Step 1: B_t(x) restricted to one chromosome and the chromosome's non-zero count. grid (unit blocks, chromosomes of the
 // shard): 18 x more CTAs and 18 x shorter serial walks than one thread per unit over the whole genome (measured: 2 ms ->
 // ~0.15 ms per table at cassava scale); partial sums per chromosome, added in a fixed order by step 2 (no atomics).
+// |e_t[j]| is staged TRAIT-CONTIGUOUS (se[j][0 .. TG)): a set mask bit costs TG / 2 128-bit shared-memory loads of one row
+// instead of one 64-bit load per trait from TG different rows. The lanes of a warp sit at unrelated j, so every such load is
+// a ~6-way bank conflict - the loads were the whole cost of this kernel (1.27 ms per 50k cassava crosses with eight 64-bit
+// loads per bit). TG = T rounded up to even (at most VER_TG per pass); the sums run over j in the same order as before.
+template <int TG>
 __global__ void __launch_bounds__(VER_THREADS) i8_verify_accumulate_kernel(const VerifyParams p) {
-    __shared__ double se[VER_TG][VER_CH];
+    static_assert(TG % 2 == 0 && TG <= VER_TG, "trait group");
+    __shared__ __align__(16) double se[VER_CH * TG];
     const long long unit = (long long)blockIdx.x * VER_THREADS + threadIdx.x;
     const int c = p.c_begin + blockIdx.y;
     const bool live = unit < p.n_units;
@@ -76,11 +82,11 @@ __global__ void __launch_bounds__(VER_THREADS) i8_verify_accumulate_kernel(const
         }
     };
     double* vb = p.part_b + ((long long)blockIdx.y * p.n_units + unit) * p.T;
-    for (int t0 = 0; t0 < p.T; t0 += VER_TG) {
-        const int ng = min(VER_TG, p.T - t0);
-        double acc[VER_TG];
+    for (int t0 = 0; t0 < p.T; t0 += TG) {
+        const int ng = min(TG, p.T - t0);
+        double acc[TG];
 #pragma unroll
-        for (int i = 0; i < VER_TG; ++i) acc[i] = 0.0;
+        for (int i = 0; i < TG; ++i) acc[i] = 0.0;
         int nnz = 0;                                           // non-zero mask entries of this chromosome so far
         const long long qbase = (long long)cd.pad_off >> 7;   // uint4 index (128 SNPs)
         uint4 nxt = make_uint4(0u, 0u, 0u, 0u);
@@ -88,9 +94,13 @@ __global__ void __launch_bounds__(VER_THREADS) i8_verify_accumulate_kernel(const
         for (int j0 = 0; j0 < cd.mp; j0 += VER_CH) {
             const int nj = min(VER_CH, cd.mp - j0);            // multiple of 128
             __syncthreads();
-            for (int i = threadIdx.x; i < VER_TG * nj; i += VER_THREADS) {
-                const int t = i / nj, j = i - t * nj;
-                se[t][j] = t < ng ? fabs(p.emat[(long long)(t0 + t) * p.mp_total + cd.pad_off + j0 + j]) : 0.0;
+            for (int j = threadIdx.x; j < nj; j += VER_THREADS) {      // one row per thread: coalesced reads per trait, 128-bit stores
+                double v[TG];
+#pragma unroll
+                for (int i = 0; i < TG; ++i)
+                    v[i] = i < ng ? fabs(p.emat[(long long)(t0 + i) * p.mp_total + cd.pad_off + j0 + j]) : 0.0;
+#pragma unroll
+                for (int i = 0; i < TG; i += 2) *reinterpret_cast<double2*>(se + j * TG + i) = make_double2(v[i], v[i + 1]);
             }
             __syncthreads();
             if (!live) continue;
@@ -106,15 +116,20 @@ __global__ void __launch_bounds__(VER_THREADS) i8_verify_accumulate_kernel(const
                         const int j = q * 128 + w * 32 + (__ffs(nz) - 1);
                         nz &= nz - 1;
                         ++nnz;
+                        const double2* row = reinterpret_cast<const double2*>(se + j * TG);
 #pragma unroll
-                        for (int i = 0; i < VER_TG; ++i) acc[i] += se[i][j];
+                        for (int i = 0; i < TG / 2; ++i) {
+                            const double2 e = row[i];
+                            acc[2 * i] += e.x;
+                            acc[2 * i + 1] += e.y;
+                        }
                     }
                 }
             }
         }
         if (live) {
 #pragma unroll
-            for (int i = 0; i < VER_TG; ++i)
+            for (int i = 0; i < TG; ++i)
                 if (i < ng) vb[t0 + i] = acc[i] * (double)nnz;        // n_j <= the unit's non-zeros on the chromosome
             if (t0 == 0) p.part_n[(long long)blockIdx.y * p.n_units + unit] = nnz;
         }
@@ -170,7 +185,11 @@ size_t i8_verify_scratch_doubles(long long n_units, int nchrom, int T) { return 
 cudaError_t launch_i8_verify(const VerifyParams& p, cudaStream_t st) {
     if (p.n_units == 0) return cudaSuccess;
     const unsigned gx = (unsigned)((p.n_units + VER_THREADS - 1) / VER_THREADS);
-    i8_verify_accumulate_kernel<<<dim3(gx, p.c_end - p.c_begin), VER_THREADS, 0, st>>>(p);
+    const dim3 grid(gx, p.c_end - p.c_begin);
+    if (p.T <= 2) i8_verify_accumulate_kernel<2><<<grid, VER_THREADS, 0, st>>>(p);
+    else if (p.T <= 4) i8_verify_accumulate_kernel<4><<<grid, VER_THREADS, 0, st>>>(p);
+    else if (p.T <= 6) i8_verify_accumulate_kernel<6><<<grid, VER_THREADS, 0, st>>>(p);
+    else i8_verify_accumulate_kernel<VER_TG><<<grid, VER_THREADS, 0, st>>>(p);
     i8_verify_check_kernel<<<(unsigned)((p.n_units + 127) / 128), 128, 0, st>>>(p);
     return cudaGetLastError();
 }

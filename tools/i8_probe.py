@@ -1,6 +1,6 @@
 """Times the per-cross int8 kernel under the test / profiling hooks, one engine per configuration in ONE process:
     python tools/i8_probe.py N "SORT,SKIP,DEBUG" ["SORT,SKIP,DEBUG" ...]
-SORT / SKIP: GMS_I8_SORT / GMS_I8_SKIP (api.cu); DEBUG: GMS_I8_DEBUG, only honoured by a -DGMS_PROFILE build selected with
+SORT: GMS_I8_SORT (api.cu); SKIP: ignored since the row-skipping epilogue was dropped (kept so that old command lines still parse); DEBUG: GMS_I8_DEBUG, only honoured by a -DGMS_PROFILE build selected with
 GMS_B200_LIB (bits: 1 no epilogue, 2 no MMAs, 4 no second MMA, 8 no xi copy, 16 no digit copy, 32 drain but no arithmetic;
 results are garbage then). Prints the kernel time (CUDA events inside the library, best of 3) per configuration."""
 import os
