@@ -252,7 +252,7 @@ def main():
               "sharding": "crosses by rank; tiles + haplotypes replicated per chromosome shard; per-parent stage split over the "
                           "cross shards + one all-gather of the table slices"
                           + ("; partial slabs all-reduced over the chromosome axis" if gc > 1 else ""),
-              "cache": "off (every step rebuilds operand images and per-parent tables)",
+              "cache": "off (every step rebuilds every operand image - digit planes, row scales, ternary mask images - and the per-parent tables)",
               "l2_policy": "inputs larger than L2 (digit images > 1 GB, RoR tile image 283 MB at cassava scale, re-streamed every step)"}
     if not strong:
         config["crosses_per_gpu"] = n_per
@@ -326,6 +326,7 @@ def main():
     int8_lib = int8_peak_tops(torch)
     pk = measured_peaks()
     bf16_burst = pk.get("bf16_tflops")
+    bf16_sust = pk.get("bf16_tflops_sustained")
     int8_peak = 2.0 * bf16_burst if bf16_burst else 4500.0           # dense int8 = 2 x dense bf16 on the tcgen05 pipe
 
     # pinned host buffers for the e2e legs (the WHOLE cross list: every rank derives the same parent set from it)
@@ -451,6 +452,10 @@ def main():
                 "peak_source": "2 x MEASURED_PEAKS.json bf16_tflops (burst; dense int8 runs at twice the bf16 rate on the tcgen05 pipe)"
                                if bf16_burst else "nominal dense int8 4500 (MEASURED_PEAKS.json absent)",
                 "frac_of_nominal_int8": ach / 4500.0,
+                # kernel_ms is taken inside a long back-to-back run (the board sits at its power cap), for which the profiling
+                # recipe names the SUSTAINED figure as the peak; `frac` above stays on the burst figure (the stricter one)
+                "peak_sustained": (2.0 * bf16_sust) if bf16_sust else None,
+                "frac_of_sustained_peak": (ach / (2.0 * bf16_sust)) if bf16_sust else None,
                 "library_int8_gemm_tops_in_run": int8_lib,
                 "frac_of_library_int8_gemm_in_run": (ach / int8_lib) if int8_lib else None,
                 "algorithmic_ops_per_launch": alg, "executed_ops_per_launch": exe,
@@ -563,7 +568,7 @@ def main():
                 "fallback": {"units_failing_int8_bound": int(st["last_fallback_units"]), "overflow": int(st["last_fallback_overflow"])},
                 "stages_ms": head["stages_ms"], "fp64_dmma": fp64_leg, "map_scan": map_scan, "cached": cached,
                 "setup_s": setup_s, "hbm_tile_bytes": int(st["tile_bytes"]),
-                "measured_peaks": {"hbm_gbs": pk.get("hbm_gbs"), "bf16_tflops_burst": bf16_burst, "fp64_dgemm_tflops": fp64_peak,
+                "measured_peaks": {"hbm_gbs": pk.get("hbm_gbs"), "bf16_tflops_burst": bf16_burst, "bf16_tflops_sustained": bf16_sust, "fp64_dgemm_tflops": fp64_peak,
                                    "int8_gemm_tops_library_in_run": int8_lib}}
         emit(line)
     eng.close()

@@ -846,7 +846,7 @@ int compute_crosses_impl(gms_handle* h, int sync) {
             for (long long off = 0; off < h->N; off += h->i8_chunk, ++pass) {
                 const long long n = std::min<long long>(h->i8_chunk, h->N - off);
                 const bool tail = n < h->i8_chunk && h->N > h->i8_chunk;
-                if (!(one_pass && h->xi_image_valid)) {
+                if (!(one_pass && h->xi_image_valid && h->cache_on)) {       // cache off: every compute rebuilds every operand image
                     CU(launch_i8_build_xi(h->planeA.p, h->planeB.p, h->wpp, ua + off, ub + off, n, MASK_XI,
                                           h->mp_total / 64, h->xi_d.p, h->stream));
                     h->st.last_launches += 1;
