@@ -74,51 +74,59 @@ constexpr int I8_THREADS = 32 * (I8_EPI_WARPS + 2);
 __global__ void i8_build_xi_kernel(const unsigned* __restrict__ planeA, const unsigned* __restrict__ planeB,
                                    long long wpp, const int* __restrict__ sire, const int* __restrict__ dam,
                                    long long n_units, int mode, long long nkb_total, signed char* __restrict__ xi) {
-    // one thread = one (unit, 16-byte chunk): 16 consecutive k of one cross
+    // one thread = one (unit, 64-k block): the unit's 64 mask entries come from two words of each bit-plane (one 8-byte load per
+    // plane and parent) and fill the block's four 16-byte chunks. (One thread per 16-byte chunk re-read the same words four
+    // times through 32-byte sectors: 0.95 ms per 50k cassava crosses for 1.7 GB written.)
     const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long long chunks_per_unit = nkb_total * 4;
     const long long npad = (n_units + 2 * I8_M - 1) / (2 * I8_M) * (2 * I8_M);     // an even number of 128-cross tiles (CTA pairs)
-    if (gid >= npad * chunks_per_unit) return;
-    // consecutive threads -> consecutive rows (so that the 16-byte stores of a warp are contiguous)
-    const long long tile_chunk = gid / I8_M;            // (X, kbglobal, cc)
-    const int r = (int)(gid - tile_chunk * I8_M);
-    const long long X = tile_chunk / chunks_per_unit;
-    const long long rem = tile_chunk - X * chunks_per_unit;
-    const long long kbg = rem >> 2;
-    const int cc = (int)(rem & 3);
+    if (gid >= npad * nkb_total) return;
+    // consecutive threads -> consecutive rows of one (X, k-block) tile, so that the 16-byte stores of a warp are contiguous
+    const long long tile = gid / I8_M;                  // (X, kbglobal)
+    const int r = (int)(gid - tile * I8_M);
+    const long long X = tile / nkb_total;
+    const long long kbg = tile - X * nkb_total;
     const long long unit = X * I8_M + r;
-    unsigned nz = 0, ng = 0;
+    unsigned nzw[2] = {0u, 0u}, ngw[2] = {0u, 0u};
     if (unit < n_units) {
-        const long long w = kbg * 2 + (cc >> 1);
+        // words 2 kbg, 2 kbg + 1 of the parent's planes: 8-byte aligned (wpp is a multiple of 4)
+        const long long w = kbg * 2;
         const int pa = sire[unit];
-        const unsigned A = planeA[(long long)pa * wpp + w], B = planeB[(long long)pa * wpp + w];
+        const uint2 A = *reinterpret_cast<const uint2*>(planeA + (long long)pa * wpp + w);
+        const uint2 B = *reinterpret_cast<const uint2*>(planeB + (long long)pa * wpp + w);
         if (mode == MASK_XI) {
             const int pb = dam[unit];
-            const unsigned A2 = planeA[(long long)pb * wpp + w], B2 = planeB[(long long)pb * wpp + w];
-            nz = (A ^ B) & (A2 ^ B2);
-            ng = ((~A & B) ^ (~A2 & B2)) & nz;
+            const uint2 A2 = *reinterpret_cast<const uint2*>(planeA + (long long)pb * wpp + w);
+            const uint2 B2 = *reinterpret_cast<const uint2*>(planeB + (long long)pb * wpp + w);
+            nzw[0] = (A.x ^ B.x) & (A2.x ^ B2.x);
+            nzw[1] = (A.y ^ B.y) & (A2.y ^ B2.y);
+            ngw[0] = ((~A.x & B.x) ^ (~A2.x & B2.x)) & nzw[0];
+            ngw[1] = ((~A.y & B.y) ^ (~A2.y & B2.y)) & nzw[1];
         } else {
-            nz = A ^ B;
-            ng = (mode == MASK_DELTA) ? (~A & B) : 0u;
+            nzw[0] = A.x ^ B.x;
+            nzw[1] = A.y ^ B.y;
+            ngw[0] = (mode == MASK_DELTA) ? (~A.x & B.x) : 0u;
+            ngw[1] = (mode == MASK_DELTA) ? (~A.y & B.y) : 0u;
         }
-        nz >>= 16 * (cc & 1);
-        ng >>= 16 * (cc & 1);
-    }
-    unsigned out[4];
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-        unsigned v = 0;
-#pragma unroll
-        for (int b = 0; b < 4; ++b) {
-            const int bit = 4 * q + b;
-            const unsigned byte = ((nz >> bit) & 1u) ? (((ng >> bit) & 1u) ? 0xFFu : 0x01u) : 0u;
-            v |= byte << (8 * b);
-        }
-        out[q] = v;
     }
     const int r1 = r >> 3, r0 = r & 7;
-    signed char* dst = xi + ((X * nkb_total + kbg) * (long long)I8_A_BYTES) + ((cc * 16 + r1) * 8 + r0) * 16;
-    *reinterpret_cast<uint4*>(dst) = make_uint4(out[0], out[1], out[2], out[3]);
+    signed char* tile_base = xi + (X * nkb_total + kbg) * (long long)I8_A_BYTES;
+#pragma unroll
+    for (int cc = 0; cc < 4; ++cc) {                    // chunk cc = k 16 cc .. 16 cc + 15 of the block
+        const unsigned nz = nzw[cc >> 1] >> (16 * (cc & 1)), ng = ngw[cc >> 1] >> (16 * (cc & 1));
+        unsigned out[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            unsigned v = 0;
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+                const int bit = 4 * q + b;
+                const unsigned byte = ((nz >> bit) & 1u) ? (((ng >> bit) & 1u) ? 0xFFu : 0x01u) : 0u;
+                v |= byte << (8 * b);
+            }
+            out[q] = v;
+        }
+        *reinterpret_cast<uint4*>(tile_base + ((cc * 16 + r1) * 8 + r0) * 16) = make_uint4(out[0], out[1], out[2], out[3]);
+    }
 }
 
 // ------------------------------------------------------------------------------------------ prep: G digits
@@ -713,7 +721,7 @@ cudaError_t launch_i8_build_xi(const unsigned* planeA, const unsigned* planeB, l
                                const int* dam, long long n_units, int mode, long long nkb_total, signed char* xi,
                                cudaStream_t st) {
     const long long npad = (n_units + 2 * I8_M - 1) / (2 * I8_M) * (2 * I8_M);
-    const long long total = npad * nkb_total * 4;
+    const long long total = npad * nkb_total;           // one thread per (unit, 64-k block)
     if (total == 0) return cudaSuccess;
     i8_build_xi_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(planeA, planeB, wpp, sire, dam, n_units, mode,
                                                                          nkb_total, xi);
