@@ -411,10 +411,17 @@ def predictCrosses(modelType, stdSelInt=2.67, selInd=False, SIwts=None, CrossesT
         print("Computing SELECTION INDEX means and variances.")
         w = pd.Series(SIwts, dtype=np.float64)
         if predTheMeans:
-            wide = pm.pivot_table(index=["sireID", "damID", "predOf"], columns="Trait1", values="predMean", sort=False)
-            si = (wide[list(w.index)] * w.values).sum(axis=1).rename("predMean").reset_index()
-            si["Trait1"] = si["Trait2"] = "SELIND"
-            pm = pd.concat([si[pm.columns], pm], ignore_index=True)
+            # spread -> SELIND column after predOf -> pivot_longer (R/gmsFunctions.R:808-822): per (cross, predOf) the rows are
+            # SELIND, then the traits. (Keys stay in cross-list order here; tidyr::spread sorts them.)
+            mtraits = [str(t) for t in pd.unique(pm["Trait1"])]
+            wide = pm.pivot_table(index=["sireID", "damID", "predOf"], columns="Trait1", values="predMean", sort=False)[mtraits]
+            si = (wide[list(w.index)] * w.values).sum(axis=1).to_numpy()
+            vals = np.column_stack([si, wide.to_numpy()])                       # [key, (SELIND, traits...)]
+            keys = wide.index.to_frame(index=False)
+            pm = keys.iloc[np.repeat(np.arange(len(keys)), 1 + len(mtraits))].reset_index(drop=True)
+            pm["Trait1"] = np.tile(np.array(["SELIND"] + mtraits, dtype=object), len(keys))
+            pm["Trait2"] = pm["Trait1"]
+            pm["predMean"] = vals.reshape(-1)
         if predTheVars:
             parts = []
             for (s, d, n, of), grp in pv.groupby(["sireID", "damID", "Nsegsnps", "predOf"], sort=False):
