@@ -156,3 +156,22 @@ def test_pandas_tidy_paths_without_the_fused_table(g, bundled, objs):
     assert list(mns.Trait[:3]) == ["SELIND", "Trait1", "Trait2"] and [G.sig(x, 3) for x in mns.predMean[:3]] == [115, 194, -119]
     full = g.predictCrosses(**kw)["tidyPreds"]
     assert np.allclose(full.predVar, v.predVar, rtol=1e-12) and np.allclose(full.predMean, mns.predMean, rtol=1e-12)
+
+
+def test_long_form_equals_the_unnested_nested_form(g, bundled, objs):
+    """nest=False (one frame, what large cross lists use) is tidyr::unnest(predVars) of the reference's nested result,
+    including the dropped zero-segregation cross and the carried extra column."""
+    from genomicmateselectr_b200.predcrossvar import _unnest
+    b = bundled
+    hap = objs["hap"].copy()
+    hap.loc[["49_HapA", "49_HapB"]] = 1                                  # 49 x 49 has no segregating SNP
+    crosses = g.crosses2predict(b.PARENTS[:4])
+    crosses["note"] = [f"row{i}" for i in range(len(crosses))]
+    kw = dict(CrossesToPredict=crosses, modelType="AD", AddEffectList=objs["eff"](b.effAD_add),
+              DomEffectList=objs["eff"](b.effAD_dom), haploMat=hap, recombFreqMat=objs["R"])
+    nested, long = g.predCrossVars(**kw), g.predCrossVars(nest=False, **kw)
+    assert len(nested) == len(crosses) - 1 and len(long) == len(nested) * 6
+    flat = _unnest(nested)
+    cols = ["sireID", "damID", "note", "Nsegsnps", "Trait1", "Trait2", "predOf"]
+    assert list(long.columns) == list(flat.columns)
+    assert flat[cols].astype(str).equals(long[cols].astype(str)) and np.array_equal(flat.predVar, long.predVar)
